@@ -1,0 +1,143 @@
+"""ctypes binding of libgcgcn_b200.so (the C ABI declared in include/gcgcn_b200.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing
+or a call fails, a ``GcgcnError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+import threading
+from ctypes import c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p, c_char_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libgcgcn_b200.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+F32, BF16 = 0, 1
+STACK_RELU, STACK_RESIDUAL, STACK_LINEAR = 1, 2, 4
+
+
+class GcgcnError(RuntimeError):
+    pass
+
+
+class Batch(ctypes.Structure):
+    """struct gcgcn_batch"""
+    _fields_ = [
+        ("num_docs", c_int32), ("total_nodes", c_int32), ("total_pairs", c_int64),
+        ("max_nodes", c_int32), ("reserved", c_int32),
+        ("node_ptr", c_void_p), ("pair_ptr", c_void_p), ("row_doc", c_void_p),
+    ]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree shared library (nvcc
+    cross-compiles without a GPU).  Skipped when the library is newer than its sources."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(p) for p in deps)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise GcgcnError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_P = c_void_p
+_BT = POINTER(Batch)
+
+# name -> (restype, argtypes); mirrors include/gcgcn_b200.h one to one
+SIGNATURES = {
+    "gcgcn_version": (c_char_p, []),
+    "gcgcn_last_error": (c_char_p, []),
+    "gcgcn_launch_count": (c_uint64, []),
+    "gcgcn_device_info": (c_int32, [POINTER(c_int32)] * 3),
+    "gcgcn_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "gcgcn_pool_fwd": (c_int32, [_P, _P, _P, _P, c_int32, _P, _P]),
+    "gcgcn_pool_bwd": (c_int32, [_P, _P, _P, _P, c_int32, _P, _P]),
+    "gcgcn_edge_mean_fwd": (c_int32, [_BT, _P, c_int32, _P, _P]),
+    "gcgcn_edge_mean_bwd": (c_int32, [_BT, _P, c_int32, _P, _P]),
+    "gcgcn_gat_fwd": (c_int32, [_BT, _P, _P, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P,
+                                _P, c_size_t, _P]),
+    "gcgcn_gat_bwd": (c_int32, [_BT, _P, _P, c_int32, _P, _P, _P, c_int32, _P, _P, _P, _P,
+                                _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gcgcn_mha_fwd": (c_int32, [_BT, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gcgcn_mha_bwd": (c_int32, [_BT, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gcgcn_graphconv_stack_fwd": (c_int32, [_BT, c_int32, c_int32, c_int32, c_int32, c_int32]
+                                  + [_P] * 13 + [_P, c_size_t, _P]),
+    "gcgcn_graphconv_stack_bwd": (c_int32, [_BT, c_int32, c_int32, c_int32, c_int32, c_int32]
+                                  + [_P] * 20 + [_P, c_size_t, _P]),
+    "gcgcn_pair_gather_fwd": (c_int32, [_BT, _P, c_int32, _P, c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "gcgcn_pair_gather_bwd": (c_int32, [_BT, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P,
+                                        _P, c_size_t, _P]),
+    "gcgcn_block_saved_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "gcgcn_caggc_fwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 8 + [_P, _P, _P, c_size_t, _P]),
+    "gcgcn_caggc_bwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 6 + [_P, _P]
+                        + [_P] * 10 + [_P, c_size_t, _P]),
+    "gcgcn_maggc_fwd": (c_int32, [_BT, c_int32, c_int32, _P, _P, c_int32] + [_P] * 7
+                        + [_P, _P, _P, c_size_t, _P]),
+    "gcgcn_maggc_bwd": (c_int32, [_BT, c_int32, c_int32, _P, c_int32] + [_P] * 5 + [_P, _P]
+                        + [_P] * 9 + [_P, c_size_t, _P]),
+    "gcgcn_gemm": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, c_int32, _P,
+                             c_int32, c_float, _P, c_int32, _P, _P, c_size_t, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> ctypes.CDLL:
+    """Load the in-tree library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise GcgcnError(
+                f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "gcgcn_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on a non-zero return code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GcgcnError(f"{name} failed (code {rc}): {lib.gcgcn_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().gcgcn_launch_count())
+
+
+def version() -> str:
+    return load().gcgcn_version().decode()

@@ -1,0 +1,576 @@
+// extern "C" surface of libgcgcn_b200.so (declared in include/gcgcn_b200.h).
+// Host-side orchestration only: argument checks, workspace carving and kernel sequencing.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gcgcn {
+
+// ---- launchers implemented in the kernel files ---------------------------------------------
+int launch_node_score(const float* x, const float* u, const float* c, float* ux, int rows, cudaStream_t st);
+int launch_edge_fwd(const gcgcn_batch* bt, const void* e, int dtype, const float* v, const float* ux,
+                    const uint8_t* mask, const float* keep, float* P, float* A, float* ebar, cudaStream_t st);
+int launch_edge_bwd(const gcgcn_batch* bt, const void* e, int dtype, const float* v, const float* dS,
+                    const float* debar, void* de, float* dv_partial, cudaStream_t st);
+int edge_bwd_grid();
+int node_bwd_grid();
+int launch_softmax_bwd(const gcgcn_batch* bt, int heads, const float* P, const float* keep, const float* dA,
+                       const uint8_t* mask, float* dS, cudaStream_t st);
+int launch_gat_node_bwd(const gcgcn_batch* bt, const float* dS, const float* x, const float* u, float* dx,
+                        float* partial, int* parts_out, cudaStream_t st);
+int launch_reduce_partials(const float* partial, int parts, int width, float* out0, int width0, float* out1,
+                           cudaStream_t st);
+int launch_mha_fwd(const gcgcn_batch* bt, int heads, const float* q, const float* keep, float* P, float* A,
+                   cudaStream_t st);
+int launch_mha_bwd(const gcgcn_batch* bt, int heads, const float* q, const float* dS, float* dq, cudaStream_t st);
+int launch_stack_fwd(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A, float* Z,
+                     const float* E, const float* Winner, const float* keep, const float* x, float* G, float* F,
+                     cudaStream_t st);
+int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A, const float* Z,
+                     const float* G, const float* Winner, const float* keep, const float* dF, float* dZ,
+                     float* dE, float* dA, cudaStream_t st);
+int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+int launch_colsum(const float* X, int M, int N, int ldx, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_csr_gather(const float* src, const int* ptr, const int* idx, const float* w, int rows, float* out,
+                      cudaStream_t st);
+int launch_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int feat_w, const float* dis, int dis_w,
+                           const int* h_idx, const int* t_idx, const int* dis_h, const int* dis_t, float* out_h,
+                           float* out_t, cudaStream_t st);
+int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, int feat_w,
+                           int dis_w, int dis_rows, const int* dis_h, const int* dis_t, float* dfeat,
+                           float* ddis, void* ws, size_t ws_bytes, cudaStream_t st);
+int pair_dis_warps();
+
+// ---- error text, launch counter, device cache --------------------------------------------------
+std::atomic<uint64_t> g_launches{0};
+
+char* error_buffer() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int check_device_ptr(const void* p, const char* name) {
+    if (p == nullptr) return fail(GCGCN_ERR_INVALID_ARG, "%s is NULL", name);
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GCGCN_ERR_INVALID_ARG, "%s: not a CUDA pointer (%s); this library has no CPU path", name,
+                    cudaGetErrorString(e));
+    }
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+        return fail(GCGCN_ERR_INVALID_ARG, "%s is host memory; this library has no CPU path", name);
+    return GCGCN_OK;
+}
+
+int check_batch(const gcgcn_batch* bt) {
+    if (bt == nullptr) return fail(GCGCN_ERR_INVALID_ARG, "batch descriptor is NULL");
+    if (bt->num_docs < 0 || bt->total_nodes < 0 || bt->total_pairs < 0 || bt->max_nodes < 0)
+        return fail(GCGCN_ERR_INVALID_ARG, "negative size in batch descriptor");
+    if (bt->num_docs > 0) {
+        GCGCN_TRY(check_device_ptr(bt->node_ptr, "batch.node_ptr"));
+        GCGCN_TRY(check_device_ptr(bt->pair_ptr, "batch.pair_ptr"));
+        GCGCN_TRY(check_device_ptr(bt->row_doc, "batch.row_doc"));
+    }
+    return GCGCN_OK;
+}
+
+constexpr size_t GEMM_WS_BYTES = size_t(24) << 20;
+
+static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+__global__ void __launch_bounds__(256)
+head_sum_kernel(const float* __restrict__ dF, int heads, int rows, float* __restrict__ dx) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // float4 index
+    if (idx >= static_cast<size_t>(rows) * (D / 4)) return;
+    const size_t r = idx / (D / 4), q = idx % (D / 4);
+    const float4* src = reinterpret_cast<const float4*>(dF) + r * heads * (D / 4) + q;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int h = 0; h < heads; ++h) {
+        const float4 v = src[static_cast<size_t>(h) * (D / 4)];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dx)[idx] = acc;
+}
+
+__global__ void __launch_bounds__(256) add_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n4) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= n4) return;
+    float4 a = reinterpret_cast<float4*>(dst)[idx];
+    const float4 b = reinterpret_cast<const float4*>(src)[idx];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[idx] = a;
+}
+
+// dst += src, n a multiple of 4
+static int launch_add(float* dst, const float* src, size_t n, cudaStream_t st) {
+    if (n == 0) return GCGCN_OK;
+    add_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(dst, src, n / 4);
+    GCGCN_CHECK_LAUNCH("add");
+    return GCGCN_OK;
+}
+
+static int launch_head_sum(const float* dF, int heads, int rows, float* dx, cudaStream_t st) {
+    if (rows == 0) return GCGCN_OK;
+    const size_t total = static_cast<size_t>(rows) * (D / 4);
+    head_sum_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dF, heads, rows, dx);
+    GCGCN_CHECK_LAUNCH("head_sum");
+    return GCGCN_OK;
+}
+
+}  // namespace gcgcn
+
+using namespace gcgcn;
+
+extern "C" {
+
+const char* gcgcn_version(void) { return "gcgcn_b200 0.1.0 (sm_100a)"; }
+const char* gcgcn_last_error(void) { return error_buffer(); }
+uint64_t gcgcn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gcgcn_device_info(int32_t* sms, int32_t* major, int32_t* minor) {
+    int dev = 0;
+    GCGCN_TRY(cuda_ok(cudaGetDevice(&dev), "cudaGetDevice"));
+    int a = 0, b = 0, c = 0;
+    GCGCN_TRY(cuda_ok(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev), "device attr"));
+    GCGCN_TRY(cuda_ok(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev), "device attr"));
+    GCGCN_TRY(cuda_ok(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev), "device attr"));
+    if (sms) *sms = a;
+    if (major) *major = b;
+    if (minor) *minor = c;
+    return GCGCN_OK;
+}
+
+size_t gcgcn_workspace_bytes(int32_t total_nodes, int64_t total_pairs, int32_t heads) {
+    const size_t hd = static_cast<size_t>(heads < 1 ? 1 : heads) * D;
+    const size_t nodes = static_cast<size_t>(total_nodes < 0 ? 0 : total_nodes);
+    const size_t pairs = static_cast<size_t>(total_pairs < 0 ? 0 : total_pairs);
+    size_t b = 0;
+    b += 3 * align256(nodes * hd * sizeof(float));                     // dF, dZ, dE
+    b += align256(pairs * (heads < 1 ? 1 : heads) * sizeof(float));    // dS
+    b += 2 * align256(nodes * D * sizeof(float));                      // dq / ux / misc
+    b += GEMM_WS_BYTES + (size_t(8) << 20);                            // split-K and reduction partials
+    return b;
+}
+
+// ---- a1 pooling ------------------------------------------------------------------------------
+int gcgcn_pool_fwd(const float* ctx, const int32_t* ent_ptr, const int32_t* tok_idx, const float* w,
+                   int32_t total_nodes, float* x0, void* stream) {
+    GCGCN_REQUIRE(total_nodes >= 0, "pool_fwd: total_nodes < 0");
+    if (total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(ctx, "ctx"));
+    GCGCN_TRY(check_device_ptr(ent_ptr, "ent_ptr"));
+    GCGCN_TRY(check_device_ptr(x0, "x0"));
+    return launch_csr_gather(ctx, ent_ptr, tok_idx, w, total_nodes, x0, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_pool_bwd(const float* dx0, const int32_t* tok_ptr, const int32_t* ent_idx, const float* w_t,
+                   int32_t total_tokens, float* dctx, void* stream) {
+    GCGCN_REQUIRE(total_tokens >= 0, "pool_bwd: total_tokens < 0");
+    if (total_tokens == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(dx0, "dx0"));
+    GCGCN_TRY(check_device_ptr(tok_ptr, "tok_ptr"));
+    GCGCN_TRY(check_device_ptr(dctx, "dctx"));
+    return launch_csr_gather(dx0, tok_ptr, ent_idx, w_t, total_tokens, dctx, static_cast<cudaStream_t>(stream));
+}
+
+// ---- shared edge pass ------------------------------------------------------------------------
+int gcgcn_edge_mean_fwd(const gcgcn_batch* bt, const void* e, int32_t edge_dtype, float* ebar, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(e, "edge_feat"));
+    GCGCN_TRY(check_device_ptr(ebar, "ebar"));
+    return launch_edge_fwd(bt, e, edge_dtype, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ebar,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_edge_mean_bwd(const gcgcn_batch* bt, const float* debar, int32_t edge_dtype, void* de, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(debar, "debar"));
+    GCGCN_TRY(check_device_ptr(de, "de"));
+    return launch_edge_bwd(bt, nullptr, edge_dtype, nullptr, nullptr, debar, de, nullptr,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// ---- a2 GATAttention -------------------------------------------------------------------------
+int gcgcn_gat_fwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype, const float* u,
+                  const float* v, const float* c, const uint8_t* mask, int32_t apply_mask, const float* keep,
+                  float* P, float* A, float* ebar, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(e, "edge_feat"));
+    GCGCN_TRY(check_device_ptr(u, "u"));
+    GCGCN_TRY(check_device_ptr(v, "v"));
+    GCGCN_TRY(check_device_ptr(P, "P"));
+    GCGCN_TRY(check_device_ptr(A, "A"));
+    GCGCN_TRY(check_device_ptr(ebar, "ebar"));
+    GCGCN_REQUIRE(keep == nullptr || A != P, "gat_fwd: A must not alias P when a keep mask is given");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(ws, ws_bytes);
+    float* ux = ar.take<float>(bt->total_nodes);
+    if (ux == nullptr) return fail(GCGCN_ERR_WORKSPACE, "gat_fwd: workspace too small");
+    GCGCN_TRY(launch_node_score(x, u, c, ux, bt->total_nodes, st));
+    return launch_edge_fwd(bt, e, edge_dtype, v, ux, (apply_mask ? mask : nullptr), keep, P, A, ebar, st);
+}
+
+int gcgcn_gat_bwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype, const float* u,
+                  const float* v, const uint8_t* mask, int32_t apply_mask, const float* keep, const float* P,
+                  const float* dA, const float* debar, float* dx, void* de, float* du, float* dv, float* dc,
+                  void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(e, "edge_feat"));
+    GCGCN_TRY(check_device_ptr(P, "P"));
+    GCGCN_TRY(check_device_ptr(dA, "dA"));
+    GCGCN_TRY(check_device_ptr(dx, "dx"));
+    GCGCN_TRY(check_device_ptr(de, "de"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(ws, ws_bytes);
+    float* dS = ar.take<float>(bt->total_pairs);
+    float* node_part = ar.take<float>(static_cast<size_t>(node_bwd_grid()) * (D + 1));
+    float* dv_part = ar.take<float>(static_cast<size_t>(edge_bwd_grid()) * D);
+    if (dS == nullptr || node_part == nullptr || dv_part == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "gat_bwd: workspace too small");
+    GCGCN_TRY(launch_softmax_bwd(bt, 1, P, keep, dA, (apply_mask ? mask : nullptr), dS, st));
+    int parts = 0;
+    GCGCN_TRY(launch_gat_node_bwd(bt, dS, x, u, dx, node_part, &parts, st));
+    GCGCN_TRY(launch_reduce_partials(node_part, parts, D + 1, du, D, dc, st));
+    GCGCN_TRY(launch_edge_bwd(bt, e, edge_dtype, v, dS, debar, de, dv_part, st));
+    const int grid = edge_bwd_grid() < bt->total_nodes ? edge_bwd_grid() : bt->total_nodes;
+    return launch_reduce_partials(dv_part, grid, D, dv, D, nullptr, st);
+}
+
+// ---- a5 MultiHeadAttention -------------------------------------------------------------------
+int gcgcn_mha_fwd(const gcgcn_batch* bt, int32_t heads, const float* x, const float* Wq, const float* bq,
+                  const float* keep, float* q, float* P, float* A, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(heads >= 1 && D % heads == 0, "mha_fwd: head_num %d must divide %d", heads, D);
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(Wq, "Wq"));
+    GCGCN_TRY(check_device_ptr(q, "q"));
+    GCGCN_TRY(check_device_ptr(P, "P"));
+    GCGCN_TRY(check_device_ptr(A, "A"));
+    GCGCN_REQUIRE(keep == nullptr || A != P, "mha_fwd: A must not alias P when a keep mask is given");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GCGCN_TRY(launch_gemm(0, 1, bt->total_nodes, D, D, 1.f, x, D, Wq, D, 0.f, q, D, bq, ws, ws_bytes, st));
+    return launch_mha_fwd(bt, heads, q, keep, P, A, st);
+}
+
+int gcgcn_mha_bwd(const gcgcn_batch* bt, int32_t heads, const float* x, const float* Wq, const float* q,
+                  const float* keep, const float* P, const float* dA, float* dx, float* dWq, float* dbq,
+                  void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(heads >= 1 && D % heads == 0, "mha_bwd: head_num %d must divide %d", heads, D);
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(q, "q"));
+    GCGCN_TRY(check_device_ptr(P, "P"));
+    GCGCN_TRY(check_device_ptr(dA, "dA"));
+    GCGCN_TRY(check_device_ptr(dx, "dx"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(ws, ws_bytes);
+    float* dS = ar.take<float>(static_cast<size_t>(bt->total_pairs) * heads);
+    float* dq = ar.take<float>(static_cast<size_t>(bt->total_nodes) * D);
+    float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
+    if (dS == nullptr || dq == nullptr || gws == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "mha_bwd: workspace too small");
+    GCGCN_TRY(launch_softmax_bwd(bt, heads, P, keep, dA, nullptr, dS, st));
+    GCGCN_TRY(launch_mha_bwd(bt, heads, q, dS, dq, st));
+    GCGCN_TRY(launch_gemm(0, 0, bt->total_nodes, D, D, 1.f, dq, D, Wq, D, 0.f, dx, D, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWq != nullptr)
+        GCGCN_TRY(launch_gemm(1, 0, D, D, bt->total_nodes, 1.f, dq, D, x, D, 0.f, dWq, D, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dbq != nullptr) GCGCN_TRY(launch_colsum(dq, bt->total_nodes, D, D, dbq, gws, GEMM_WS_BYTES, st));
+    return GCGCN_OK;
+}
+
+// ---- a3/a4/a6 GraphConv stack ----------------------------------------------------------------
+int gcgcn_graphconv_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim,
+                              int32_t slab, int32_t flags, const float* x, const float* ebar, const float* A,
+                              const float* WnX, const float* We, const float* Winner, const float* Wout,
+                              const float* bout, const float* keep, float* Z, float* G, float* F, float* y,
+                              void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(heads >= 1 && layers >= 1 && in_dim >= 1 && slab >= 1, "stack_fwd: bad heads/layers/widths");
+    const bool linear = flags & GCGCN_STACK_LINEAR;
+    GCGCN_REQUIRE(linear || heads == 1, "stack_fwd: without the output linear there can be only one head");
+    GCGCN_REQUIRE(!(flags & GCGCN_STACK_RESIDUAL) || in_dim == slab,
+                  "stack_fwd: the residual needs input width %d == output width %d", in_dim, slab);
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(ebar, "ebar"));
+    GCGCN_TRY(check_device_ptr(A, "adj_matrix"));
+    GCGCN_TRY(check_device_ptr(WnX, "WnX"));
+    GCGCN_TRY(check_device_ptr(We, "We"));
+    GCGCN_TRY(check_device_ptr(Z, "Z"));
+    GCGCN_TRY(check_device_ptr(G, "G"));
+    GCGCN_TRY(check_device_ptr(y, "y"));
+    if (linear) GCGCN_TRY(check_device_ptr(F, "F"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HD = heads * slab, M = bt->total_nodes;
+    Arena ar(ws, ws_bytes);
+    float* E = ar.take<float>(static_cast<size_t>(M) * HD);
+    float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
+    if (E == nullptr || gws == nullptr) return fail(GCGCN_ERR_WORKSPACE, "stack_fwd: workspace too small");
+    GCGCN_TRY(launch_gemm(0, 0, M, HD, in_dim, 1.f, x, in_dim, WnX, HD, 0.f, Z, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, ebar, D, We, HD, 0.f, E, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    float* Fout = linear ? F : y;
+    GCGCN_TRY(launch_stack_fwd(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, Fout, st));
+    if (linear)
+        GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, F, HD, Wout, HD, 0.f, y, D, bout, gws, GEMM_WS_BYTES, st));
+    return GCGCN_OK;
+}
+
+int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim,
+                              int32_t slab, int32_t flags, const float* x, const float* ebar, const float* A,
+                              const float* WnX, const float* We, const float* Winner, const float* Wout,
+                              const float* keep, const float* Z, const float* G, const float* F,
+                              const float* dy, float* dx, float* debar, float* dA, float* dWnX, float* dWe,
+                              float* dWinner, float* dWout, float* dbout, void* ws, size_t ws_bytes,
+                              void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(heads >= 1 && layers >= 1 && in_dim >= 1 && slab >= 1 && slab % layers == 0,
+                  "stack_bwd: bad heads/layers/widths");
+    const bool linear = flags & GCGCN_STACK_LINEAR;
+    GCGCN_REQUIRE(linear || heads == 1, "stack_bwd: without the output linear there can be only one head");
+    GCGCN_REQUIRE(!(flags & GCGCN_STACK_RESIDUAL) || (in_dim == slab && slab == D),
+                  "stack_bwd: the residual needs input width == output width == %d", D);
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(A, "adj_matrix"));
+    GCGCN_TRY(check_device_ptr(Z, "Z"));
+    GCGCN_TRY(check_device_ptr(G, "G"));
+    GCGCN_TRY(check_device_ptr(dy, "dy"));
+    GCGCN_TRY(check_device_ptr(dx, "dx"));
+    GCGCN_TRY(check_device_ptr(debar, "debar"));
+    GCGCN_TRY(check_device_ptr(dA, "dA"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HD = heads * slab, M = bt->total_nodes, gd = slab / layers;
+    Arena ar(ws, ws_bytes);
+    float* dFbuf = linear ? ar.take<float>(static_cast<size_t>(M) * HD) : nullptr;
+    float* dZ = ar.take<float>(static_cast<size_t>(M) * HD);
+    float* dE = ar.take<float>(static_cast<size_t>(M) * HD);
+    float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
+    if ((linear && dFbuf == nullptr) || dZ == nullptr || dE == nullptr || gws == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "stack_bwd: workspace too small");
+    const float* dF = dy;
+    if (linear) {
+        GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, dy, D, Wout, HD, 0.f, dFbuf, HD, nullptr, gws, GEMM_WS_BYTES, st));
+        if (dWout != nullptr)
+            GCGCN_TRY(launch_gemm(1, 0, D, HD, M, 1.f, dy, D, F, HD, 0.f, dWout, HD, nullptr, gws, GEMM_WS_BYTES, st));
+        if (dbout != nullptr) GCGCN_TRY(launch_colsum(dy, M, D, D, dbout, gws, GEMM_WS_BYTES, st));
+        dF = dFbuf;
+    }
+    GCGCN_TRY(launch_stack_bwd(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, dA, st));
+    // dx = [residual: sum_h dF_h] + dZ WnX^T ; debar = dE We^T
+    float beta = 0.f;
+    if (flags & GCGCN_STACK_RESIDUAL) {
+        GCGCN_TRY(launch_head_sum(dF, heads, M, dx, st));
+        beta = 1.f;
+    }
+    GCGCN_TRY(launch_gemm(0, 1, M, in_dim, HD, 1.f, dZ, HD, WnX, HD, beta, dx, in_dim, nullptr, gws, GEMM_WS_BYTES, st));
+    GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, dE, HD, We, HD, 0.f, debar, D, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWnX != nullptr)
+        GCGCN_TRY(launch_gemm(1, 0, in_dim, HD, M, 1.f, x, in_dim, dZ, HD, 0.f, dWnX, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWe != nullptr)
+        GCGCN_TRY(launch_gemm(1, 0, D, HD, M, 1.f, ebar, D, dE, HD, 0.f, dWe, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWinner != nullptr && layers > 1) {
+        GCGCN_TRY(cuda_ok(cudaMemsetAsync(dWinner, 0, static_cast<size_t>(heads) * layers * slab * gd * sizeof(float), st),
+                          "memset dWinner"));
+        // dWinner[h][l][m*g + k][c] = sum_rows G[row][h*S + m*g + k] * dZ[row][h*S + l*g + c],  m < l
+        for (int h = 0; h < heads; ++h)
+            for (int l = 1; l < layers; ++l)
+                GCGCN_TRY(launch_gemm(1, 0, l * gd, gd, M, 1.f, G + static_cast<size_t>(h) * slab, HD,
+                                      dZ + static_cast<size_t>(h) * slab + l * gd, HD, 0.f,
+                                      dWinner + (static_cast<size_t>(h) * layers + l) * slab * gd, gd, nullptr,
+                                      gws, GEMM_WS_BYTES, st));
+    }
+    return GCGCN_OK;
+}
+
+// ---- a8 pair gathers -------------------------------------------------------------------------
+int gcgcn_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int32_t feat_w, const float* dis,
+                          int32_t dis_w, const int32_t* h_idx, const int32_t* t_idx, const int32_t* dis_h,
+                          const int32_t* dis_t, float* out_h, float* out_t, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(feat_w > 0 && feat_w % 4 == 0 && dis_w >= 0 && dis_w % 4 == 0,
+                  "pair_gather: widths must be multiples of 4 (feat_w=%d, dis_w=%d)", feat_w, dis_w);
+    if (bt->total_pairs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(feat, "feat"));
+    GCGCN_TRY(check_device_ptr(h_idx, "h_idx"));
+    GCGCN_TRY(check_device_ptr(t_idx, "t_idx"));
+    GCGCN_TRY(check_device_ptr(out_h, "out_h"));
+    GCGCN_TRY(check_device_ptr(out_t, "out_t"));
+    if (dis_w > 0) {
+        GCGCN_TRY(check_device_ptr(dis, "dis"));
+        GCGCN_TRY(check_device_ptr(dis_h, "dis_h"));
+        GCGCN_TRY(check_device_ptr(dis_t, "dis_t"));
+    }
+    return launch_pair_gather_fwd(bt, feat, feat_w, dis, dis_w, h_idx, t_idx, dis_h, dis_t, out_h, out_t,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, int32_t feat_w,
+                          int32_t dis_w, int32_t dis_rows, const int32_t* dis_h, const int32_t* dis_t,
+                          float* dfeat, float* ddis, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(feat_w > 0 && feat_w % 4 == 0 && dis_w >= 0 && dis_w % 4 == 0,
+                  "pair_gather: widths must be multiples of 4 (feat_w=%d, dis_w=%d)", feat_w, dis_w);
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(dout_h, "dout_h"));
+    GCGCN_TRY(check_device_ptr(dout_t, "dout_t"));
+    GCGCN_TRY(check_device_ptr(dfeat, "dfeat"));
+    return launch_pair_gather_bwd(bt, dout_h, dout_t, feat_w, dis_w, dis_rows, dis_h, dis_t, dfeat, ddis, ws,
+                                  ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- dense projection ------------------------------------------------------------------------
+int gcgcn_gemm(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A,
+               int32_t lda, const float* B, int32_t ldb, float beta, float* C, int32_t ldc, const float* bias,
+               void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+    if (M == 0 || N == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(C, "C"));
+    if (K > 0) {
+        GCGCN_TRY(check_device_ptr(A, "A"));
+        GCGCN_TRY(check_device_ptr(B, "B"));
+    }
+    return launch_gemm(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+// ---- block-level composites ------------------------------------------------------------------
+namespace {
+struct CagSaved { float *P, *ebar, *Z, *G, *F; };
+struct MagSaved { float *ebar, *q, *P, *Z, *G, *F; };
+
+CagSaved carve_cag(void* saved, int nodes, long long pairs) {
+    Arena ar(saved, ~size_t(0) >> 1);
+    CagSaved s;
+    s.P = ar.take<float>(pairs);
+    s.ebar = ar.take<float>(static_cast<size_t>(nodes) * D);
+    s.Z = ar.take<float>(static_cast<size_t>(nodes) * D);
+    s.G = ar.take<float>(static_cast<size_t>(nodes) * D);
+    s.F = ar.take<float>(static_cast<size_t>(nodes) * D);
+    return s;
+}
+MagSaved carve_mag(void* saved, int nodes, long long pairs, int heads) {
+    Arena ar(saved, ~size_t(0) >> 1);
+    MagSaved s;
+    s.ebar = ar.take<float>(static_cast<size_t>(nodes) * D);
+    s.q = ar.take<float>(static_cast<size_t>(nodes) * D);
+    s.P = ar.take<float>(static_cast<size_t>(pairs) * heads);
+    s.Z = ar.take<float>(static_cast<size_t>(nodes) * heads * D);
+    s.G = ar.take<float>(static_cast<size_t>(nodes) * heads * D);
+    s.F = ar.take<float>(static_cast<size_t>(nodes) * heads * D);
+    return s;
+}
+constexpr int BLOCK_FLAGS = GCGCN_STACK_RELU | GCGCN_STACK_RESIDUAL | GCGCN_STACK_LINEAR;
+}  // namespace
+
+size_t gcgcn_block_saved_bytes(int32_t total_nodes, int64_t total_pairs, int32_t heads) {
+    const size_t nodes = static_cast<size_t>(total_nodes), h = static_cast<size_t>(heads < 1 ? 1 : heads);
+    return align256(static_cast<size_t>(total_pairs) * h * sizeof(float)) +
+           2 * align256(nodes * D * sizeof(float)) + 3 * align256(nodes * h * D * sizeof(float)) + 1024;
+}
+
+int gcgcn_caggc_fwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e, int32_t edge_dtype,
+                    const float* u, const float* v, const float* c, const float* WnX, const float* We,
+                    const float* Winner, const float* Wout, const float* bout, float* y, void* saved, void* ws,
+                    size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_TRY(check_device_ptr(saved, "saved"));
+    CagSaved s = carve_cag(saved, bt->total_nodes, bt->total_pairs);
+    GCGCN_TRY(gcgcn_gat_fwd(bt, x, e, edge_dtype, u, v, c, nullptr, 0, nullptr, s.P, s.P, s.ebar, ws, ws_bytes, stream));
+    return gcgcn_graphconv_stack_fwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, bout,
+                                     nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, stream);
+}
+
+int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e, int32_t edge_dtype,
+                    const float* u, const float* v, const float* WnX, const float* We, const float* Winner,
+                    const float* Wout, const float* dy, const void* saved, float* dx, void* de, float* du,
+                    float* dv, float* dc, float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
+                    void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_TRY(check_device_ptr(saved, "saved"));
+    CagSaved s = carve_cag(const_cast<void*>(saved), bt->total_nodes, bt->total_pairs);
+    // tail of the workspace holds the gradients that flow between the two halves of the block
+    Arena ar(ws, ws_bytes);
+    float* dx_stack = ar.take<float>(static_cast<size_t>(bt->total_nodes) * D);
+    float* debar = ar.take<float>(static_cast<size_t>(bt->total_nodes) * D);
+    float* dA = ar.take<float>(bt->total_pairs);
+    if (dx_stack == nullptr || debar == nullptr || dA == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "caggc_bwd: workspace too small");
+    void* rest = static_cast<char*>(ws) + ar.off;
+    const size_t rest_bytes = ws_bytes - ar.off;
+    GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, nullptr,
+                                        s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner, dWout, dbout,
+                                        rest, rest_bytes, stream));
+    GCGCN_TRY(gcgcn_gat_bwd(bt, x, e, edge_dtype, u, v, nullptr, 0, nullptr, s.P, dA, debar, dx, de, du, dv, dc,
+                            rest, rest_bytes, stream));
+    return launch_add(dx, dx_stack, static_cast<size_t>(bt->total_nodes) * D, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x, const void* e,
+                    int32_t edge_dtype, const float* Wq, const float* bq, const float* WnX, const float* We,
+                    const float* Winner, const float* Wout, const float* bout, float* y, void* saved, void* ws,
+                    size_t ws_bytes, void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_TRY(check_device_ptr(saved, "saved"));
+    MagSaved s = carve_mag(saved, bt->total_nodes, bt->total_pairs, heads);
+    GCGCN_TRY(gcgcn_edge_mean_fwd(bt, e, edge_dtype, s.ebar, stream));
+    GCGCN_TRY(gcgcn_mha_fwd(bt, heads, x, Wq, bq, nullptr, s.q, s.P, s.P, ws, ws_bytes, stream));
+    return gcgcn_graphconv_stack_fwd(bt, heads, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, bout,
+                                     nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, stream);
+}
+
+int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x, int32_t edge_dtype,
+                    const float* Wq, const float* WnX, const float* We, const float* Winner, const float* Wout,
+                    const float* dy, const void* saved, float* dx, void* de, float* dWq, float* dbq, float* dWnX,
+                    float* dWe, float* dWinner, float* dWout, float* dbout, void* ws, size_t ws_bytes,
+                    void* stream) {
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_TRY(check_device_ptr(saved, "saved"));
+    MagSaved s = carve_mag(const_cast<void*>(saved), bt->total_nodes, bt->total_pairs, heads);
+    Arena ar(ws, ws_bytes);
+    float* dx_stack = ar.take<float>(static_cast<size_t>(bt->total_nodes) * D);
+    float* debar = ar.take<float>(static_cast<size_t>(bt->total_nodes) * D);
+    float* dA = ar.take<float>(static_cast<size_t>(bt->total_pairs) * heads);
+    if (dx_stack == nullptr || debar == nullptr || dA == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "maggc_bwd: workspace too small");
+    void* rest = static_cast<char*>(ws) + ar.off;
+    const size_t rest_bytes = ws_bytes - ar.off;
+    GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, heads, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout,
+                                        nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner,
+                                        dWout, dbout, rest, rest_bytes, stream));
+    GCGCN_TRY(gcgcn_mha_bwd(bt, heads, x, Wq, s.q, nullptr, s.P, dA, dx, dWq, dbq, rest, rest_bytes, stream));
+    GCGCN_TRY(launch_add(dx, dx_stack, static_cast<size_t>(bt->total_nodes) * D, static_cast<cudaStream_t>(stream)));
+    return gcgcn_edge_mean_bwd(bt, debar, edge_dtype, de, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Shared helpers for the gcgcn_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/gcgcn_b200.h"
+
+namespace gcgcn {
+
+constexpr int D = GCGCN_HIDDEN;  // hidden width, G:234
+constexpr int WARP = 32;
+
+// ---- per-thread error text + process-wide launch counter --------------------------------
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return GCGCN_OK;
+    return fail(GCGCN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define GCGCN_CHECK_LAUNCH(name)                                        \
+    do {                                                                \
+        ::gcgcn::g_launches.fetch_add(1, std::memory_order_relaxed);    \
+        int rc__ = ::gcgcn::cuda_ok(cudaPeekAtLastError(), name);       \
+        if (rc__ != GCGCN_OK) return rc__;                              \
+    } while (0)
+
+#define GCGCN_TRY(expr)                    \
+    do {                                   \
+        int rc__ = (expr);                 \
+        if (rc__ != GCGCN_OK) return rc__; \
+    } while (0)
+
+#define GCGCN_REQUIRE(cond, ...)                                        \
+    do {                                                                \
+        if (!(cond)) return ::gcgcn::fail(GCGCN_ERR_INVALID_ARG, __VA_ARGS__); \
+    } while (0)
+
+int sm_count();
+int check_batch(const gcgcn_batch* bt);
+int check_device_ptr(const void* p, const char* name);
+
+// bump allocator over a caller-owned workspace
+struct Arena {
+    char* base;
+    size_t cap;
+    size_t off = 0;
+    Arena(void* p, size_t bytes) : base(static_cast<char*>(p)), cap(bytes) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (base == nullptr || off + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Streaming 4-element loads/stores of an edge vector slice, fp32 or bf16 storage, fp32 math.
+// The n^2 x 128 tensors are read/written exactly once per pass: bypass L1 allocation.
+template <typename T>
+struct Vec4;
+
+template <>
+struct Vec4<float> {
+    static __device__ __forceinline__ float4 load(const float* p) {
+        float4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                     : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ void store(float* p, float4 v) {
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+};
+
+template <>
+struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+        uint32_t a, b;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+        float4 r;
+        r.x = __uint_as_float(a << 16);
+        r.y = __uint_as_float(a & 0xffff0000u);
+        r.z = __uint_as_float(b << 16);
+        r.w = __uint_as_float(b & 0xffff0000u);
+        return r;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint32_t a = *reinterpret_cast<uint32_t*>(&lo);
+        uint32_t b = *reinterpret_cast<uint32_t*>(&hi);
+        asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b)
+                     : "memory");
+    }
+};
+
+}  // namespace gcgcn

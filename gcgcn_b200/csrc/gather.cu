@@ -1,0 +1,171 @@
+// Mention->entity pooling (G:297-298) and head/tail pair gathers (G:351-352, 321-322) as
+// index-driven, 128-bit vectorised row gathers instead of dense mapping-matrix products.
+#include "common.cuh"
+
+namespace gcgcn {
+
+int launch_reduce_partials(const float* partial, int parts, int width, float* out0, int width0,
+                           float* out1, cudaStream_t st);
+
+// out[row,:] = sum_{k in [ptr[row], ptr[row+1])} w[k] * src[idx[k],:]      (one warp per row)
+// forward: rows = entities, idx = tokens; backward: rows = tokens, idx = entities.
+__global__ void __launch_bounds__(256)
+csr_gather_kernel(const float* __restrict__ src, const int* __restrict__ ptr,
+                  const int* __restrict__ idx, const float* __restrict__ w, int rows,
+                  float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < rows; r += nwarps) {
+        const int k0 = ptr[r], k1 = ptr[r + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = k0; k < k1; ++k) {
+            const float wk = w[k];
+            const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(idx[k]) * D + lane * 4);
+            acc.x = fmaf(wk, v.x, acc.x); acc.y = fmaf(wk, v.y, acc.y);
+            acc.z = fmaf(wk, v.z, acc.z); acc.w = fmaf(wk, v.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * D + lane * 4) = acc;
+    }
+}
+
+int launch_csr_gather(const float* src, const int* ptr, const int* idx, const float* w, int rows,
+                      float* out, cudaStream_t st) {
+    if (rows == 0) return GCGCN_OK;
+    const int blocks = min(ceil_div(rows, 8), sm_count() * 8);
+    csr_gather_kernel<<<blocks, 256, 0, st>>>(src, ptr, idx, w, rows, out);
+    GCGCN_CHECK_LAUNCH("csr_gather");
+    return GCGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair gather forward: one warp per (pair, side) output row of feat_w + dis_w floats
+__global__ void __launch_bounds__(256)
+pair_gather_fwd_kernel(const float4* __restrict__ feat, int fw4, const float4* __restrict__ dis, int dw4,
+                       const int* __restrict__ h_idx, const int* __restrict__ t_idx,
+                       const int* __restrict__ dis_h, const int* __restrict__ dis_t,
+                       float* __restrict__ out_h, float* __restrict__ out_t, long long total_pairs) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int ow4 = fw4 + dw4;
+    for (long long item = warp; item < 2 * total_pairs; item += nwarps) {
+        const bool tail = item >= total_pairs;
+        const long long p = tail ? item - total_pairs : item;
+        const int node = tail ? t_idx[p] : h_idx[p];
+        const float4* frow = feat + static_cast<size_t>(node) * fw4;
+        const float4* drow = nullptr;
+        if (dw4 > 0) drow = dis + static_cast<size_t>(tail ? dis_t[p] : dis_h[p]) * dw4;
+        float* orow = (tail ? out_t : out_h) + static_cast<size_t>(p) * ow4 * 4;
+        for (int q = lane; q < ow4; q += WARP) {
+            const float4 v = q < fw4 ? frow[q] : drow[q - fw4];
+            Vec4<float>::store(orow + q * 4, v);
+        }
+    }
+}
+
+// pair gather backward, feature part: node row (b,k) was gathered by the "h" side of every pair
+// (i,k) and by the "t" side of every pair (k,j)  (G:351-352: h gathers column j, t gathers row i).
+__global__ void __launch_bounds__(128)
+pair_gather_bwd_feat_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                            const int* __restrict__ row_doc, const float* __restrict__ dout_h,
+                            const float* __restrict__ dout_t, int fw4, int ow4,
+                            float* __restrict__ dfeat) {
+    const int r = blockIdx.x;
+    const int b = row_doc[r];
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    const int k = r - node0;
+    const long long p0 = pair_ptr[b];
+    for (int q = threadIdx.x; q < fw4; q += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < n; ++i) {
+            const float4 v = Vec4<float>::load(dout_h + (static_cast<size_t>(p0 + static_cast<long long>(i) * n + k) * ow4 + q) * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        for (int j = 0; j < n; ++j) {
+            const float4 v = Vec4<float>::load(dout_t + (static_cast<size_t>(p0 + static_cast<long long>(k) * n + j) * ow4 + q) * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(dfeat + (static_cast<size_t>(r) * fw4 + q) * 4) = acc;
+    }
+}
+
+// pair gather backward, distance-table part: every warp owns a contiguous chunk of pairs and a
+// private [dis_rows][dis_w] accumulator in shared memory (lane = column), walked sequentially so
+// the summation order is fixed; per-warp partials are reduced by reduce_partials.
+constexpr int DIS_BWD_THREADS = 128;
+__global__ void __launch_bounds__(DIS_BWD_THREADS)
+pair_gather_bwd_dis_kernel(const float* __restrict__ dout_h, const float* __restrict__ dout_t, int fw,
+                           int dw, int dis_rows, const int* __restrict__ dis_h,
+                           const int* __restrict__ dis_t, long long total_pairs,
+                           long long pairs_per_warp, float* __restrict__ partial) {
+    extern __shared__ float acc_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cells = dis_rows * dw;
+    float* acc = acc_all + warp * cells;
+    for (int t = lane; t < cells; t += WARP) acc[t] = 0.f;
+    __syncwarp();
+    const long long gw = static_cast<long long>(blockIdx.x) * (DIS_BWD_THREADS / WARP) + warp;
+    const long long p0 = gw * pairs_per_warp;
+    const long long p1 = min(total_pairs, p0 + pairs_per_warp);
+    const int ow = fw + dw;
+    for (long long p = p0; p < p1; ++p) {
+        const int kh = dis_h[p], kt = dis_t[p];
+        for (int c = lane; c < dw; c += WARP) {
+            acc[kh * dw + c] += dout_h[static_cast<size_t>(p) * ow + fw + c];
+            acc[kt * dw + c] += dout_t[static_cast<size_t>(p) * ow + fw + c];
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < cells; t += WARP) partial[static_cast<size_t>(gw) * cells + t] = acc[t];
+}
+
+int launch_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int feat_w, const float* dis,
+                           int dis_w, const int* h_idx, const int* t_idx, const int* dis_h,
+                           const int* dis_t, float* out_h, float* out_t, cudaStream_t st) {
+    if (bt->total_pairs == 0) return GCGCN_OK;
+    const long long warps = 2 * bt->total_pairs;
+    const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, static_cast<long long>(sm_count()) * 16));
+    pair_gather_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(feat), feat_w / 4,
+                                                   reinterpret_cast<const float4*>(dis), dis_w / 4, h_idx,
+                                                   t_idx, dis_h, dis_t, out_h, out_t, bt->total_pairs);
+    GCGCN_CHECK_LAUNCH("pair_gather_fwd");
+    return GCGCN_OK;
+}
+
+int pair_dis_warps() { return sm_count() * 16; }
+
+int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, int feat_w,
+                           int dis_w, int dis_rows, const int* dis_h, const int* dis_t, float* dfeat,
+                           float* ddis, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    const int ow4 = (feat_w + dis_w) / 4;
+    pair_gather_bwd_feat_kernel<<<bt->total_nodes, 128, 0, st>>>(
+        bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), bt->row_doc, dout_h, dout_t,
+        feat_w / 4, ow4, dfeat);
+    GCGCN_CHECK_LAUNCH("pair_gather_bwd_feat");
+    if (dis_w > 0 && ddis != nullptr) {
+        const int cells = dis_rows * dis_w;
+        long long warps = std::min<long long>(pair_dis_warps(), std::max<long long>(1, bt->total_pairs / 64));
+        const int wpb = DIS_BWD_THREADS / WARP;
+        const int blocks = ceil_div(warps, wpb);
+        warps = static_cast<long long>(blocks) * wpb;
+        const long long ppw = (bt->total_pairs + warps - 1) / warps;
+        const size_t need = static_cast<size_t>(warps) * cells * sizeof(float);
+        if (ws == nullptr || ws_bytes < need)
+            return fail(GCGCN_ERR_WORKSPACE, "pair_gather_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+        const size_t smem = static_cast<size_t>(wpb) * cells * sizeof(float);
+        if (smem > 48 * 1024)
+            return fail(GCGCN_ERR_UNSUPPORTED, "pair_gather_bwd: distance table %d x %d too large", dis_rows, dis_w);
+        pair_gather_bwd_dis_kernel<<<blocks, DIS_BWD_THREADS, smem, st>>>(
+            dout_h, dout_t, feat_w, dis_w, dis_rows, dis_h, dis_t, bt->total_pairs, ppw,
+            static_cast<float*>(ws));
+        GCGCN_CHECK_LAUNCH("pair_gather_bwd_dis");
+        GCGCN_TRY(launch_reduce_partials(static_cast<const float*>(ws), static_cast<int>(warps), cells,
+                                         ddis, cells, nullptr, st));
+    }
+    return GCGCN_OK;
+}
+
+}  // namespace gcgcn

@@ -1,0 +1,289 @@
+"""torch.autograd bindings of the C ABI (include/gcgcn_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current CUDA stream and the autograd
+tape.  Every numerical operation of the hot path is one of this package's own CUDA kernels,
+reached through ``_lib.call``.  CPU tensors are rejected -- there is no fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .batch import PairTables, PoolTable, RaggedBatch
+
+D = 128
+
+_WS: dict = {}
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch arena handed to the library (it never allocates)."""
+    key = (device.index, _stream(device))
+    t = _WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes) + (1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = t
+    return t
+
+
+def _ws_for(batch: RaggedBatch, heads: int, device):
+    n = _lib.load().gcgcn_workspace_bytes(batch.total_nodes, batch.total_pairs, heads)
+    t = workspace(device, n)
+    return t.data_ptr(), t.numel()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.GcgcnError(f"{name} is a CPU tensor: gcgcn_b200 runs on CUDA only (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _edge(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.GcgcnError(f"{name} is a CPU tensor: gcgcn_b200 runs on CUDA only (no CPU fallback)")
+    if t.dtype == torch.float32:
+        return t.contiguous(), _lib.F32
+    if t.dtype == torch.bfloat16:
+        return t.contiguous(), _lib.BF16
+    raise _lib.GcgcnError(f"{name}: edge features must be float32 or bfloat16, got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------- a1 pooling
+class PoolFn(Function):
+    """x0 = node_pos @ ctx as a CSR gather (replaces G:297-298)."""
+
+    @staticmethod
+    def forward(ctx, context: torch.Tensor, table: PoolTable):
+        context = _cuda(context, "context_output")
+        if context.shape != (table.total_tokens, D):
+            raise _lib.GcgcnError(f"context must be [{table.total_tokens}, {D}], got {tuple(context.shape)}")
+        x0 = torch.empty(table.total_nodes, D, device=context.device, dtype=torch.float32)
+        _lib.call("gcgcn_pool_fwd", _p(context), _p(table.ent_ptr), _p(table.tok_idx), _p(table.w),
+                  table.total_nodes, _p(x0), _stream(context.device))
+        ctx.table = table
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        t = ctx.table
+        dx0 = _cuda(dx0, "dx0")
+        dctx = torch.empty(t.total_tokens, D, device=dx0.device, dtype=torch.float32)
+        _lib.call("gcgcn_pool_bwd", _p(dx0), _p(t.tok_ptr), _p(t.ent_idx), _p(t.w_t), t.total_tokens,
+                  _p(dctx), _stream(dx0.device))
+        return dctx, None
+
+
+# ------------------------------------------------------------------------------- edge mean
+class EdgeMeanFn(Function):
+    """ebar_i = mean_j e_ij -- all GraphConv needs from the edge tensor (G:40-41 collapsed)."""
+
+    @staticmethod
+    def forward(ctx, e: torch.Tensor, batch: RaggedBatch):
+        e, dt = _edge(e, "edge_feat")
+        ebar = torch.empty(batch.total_nodes, D, device=e.device, dtype=torch.float32)
+        _lib.call("gcgcn_edge_mean_fwd", batch.ref, _p(e), dt, _p(ebar), _stream(e.device))
+        ctx.batch, ctx.dt, ctx.shape, ctx.edtype = batch, dt, e.shape, e.dtype
+        return ebar
+
+    @staticmethod
+    def backward(ctx, debar):
+        debar = _cuda(debar, "debar")
+        de = torch.empty(ctx.shape, device=debar.device, dtype=ctx.edtype)
+        _lib.call("gcgcn_edge_mean_bwd", ctx.batch.ref, _p(debar), ctx.dt, _p(de), _stream(debar.device))
+        return de, None
+
+
+# ------------------------------------------------------------------------------- a2 GAT
+class GatFn(Function):
+    """GATAttention.forward (G:154-168) + the edge mean of the same pass.  Returns (A, ebar)."""
+
+    @staticmethod
+    def forward(ctx, x, e, u, v, c, batch: RaggedBatch, mask_u8, apply_mask: bool, keep):
+        x = _cuda(x, "node_feat")
+        e, dt = _edge(e, "edge_feat")
+        u, v, c = _cuda(u, "u"), _cuda(v, "v"), _cuda(c, "c")
+        dev = x.device
+        P = torch.empty(batch.total_pairs, device=dev, dtype=torch.float32)
+        A = P if keep is None else torch.empty_like(P)
+        ebar = torch.empty(batch.total_nodes, D, device=dev, dtype=torch.float32)
+        if keep is not None:
+            keep = _cuda(keep, "keep")
+        if mask_u8 is not None:
+            mask_u8 = _cuda(mask_u8, "mask", torch.uint8)
+        ws, wsb = _ws_for(batch, 1, dev)
+        _lib.call("gcgcn_gat_fwd", batch.ref, _p(x), _p(e), dt, _p(u), _p(v), _p(c), _p(mask_u8),
+                  int(bool(apply_mask)), _p(keep), _p(P), _p(A), _p(ebar), ws, wsb, _stream(dev))
+        ctx.save_for_backward(x, e, u, v, P, keep, mask_u8)
+        ctx.batch, ctx.dt, ctx.apply_mask = batch, dt, bool(apply_mask)
+        return A, ebar
+
+    @staticmethod
+    def backward(ctx, dA, debar):
+        x, e, u, v, P, keep, mask_u8 = ctx.saved_tensors
+        bt, dev = ctx.batch, x.device
+        dA = torch.zeros_like(P) if dA is None else _cuda(dA, "dA")
+        debar = None if debar is None else _cuda(debar, "debar")
+        dx = torch.empty_like(x)
+        de = torch.empty_like(e)
+        du = torch.empty(D, device=dev)
+        dv = torch.empty(D, device=dev)
+        dc = torch.empty(1, device=dev)
+        ws, wsb = _ws_for(bt, 1, dev)
+        _lib.call("gcgcn_gat_bwd", bt.ref, _p(x), _p(e), ctx.dt, _p(u), _p(v), _p(mask_u8),
+                  int(ctx.apply_mask), _p(keep), _p(P), _p(dA), _p(debar), _p(dx), _p(de), _p(du),
+                  _p(dv), _p(dc), ws, wsb, _stream(dev))
+        return dx, de, du, dv, dc.reshape(()), None, None, None, None
+
+
+# ------------------------------------------------------------------------------- a5 MHA
+class MhaFn(Function):
+    """MultiHeadAttention.forward (G:133-142).  Returns A [H, total_pairs]."""
+
+    @staticmethod
+    def forward(ctx, x, Wq, bq, batch: RaggedBatch, heads: int, keep):
+        x, Wq, bq = _cuda(x, "node_feat"), _cuda(Wq, "Wq"), _cuda(bq, "bq")
+        dev = x.device
+        q = torch.empty(batch.total_nodes, D, device=dev, dtype=torch.float32)
+        P = torch.empty(heads, batch.total_pairs, device=dev, dtype=torch.float32)
+        A = P if keep is None else torch.empty_like(P)
+        if keep is not None:
+            keep = _cuda(keep, "keep")
+        ws, wsb = _ws_for(batch, heads, dev)
+        _lib.call("gcgcn_mha_fwd", batch.ref, heads, _p(x), _p(Wq), _p(bq), _p(keep), _p(q), _p(P), _p(A),
+                  ws, wsb, _stream(dev))
+        ctx.save_for_backward(x, Wq, q, P, keep)
+        ctx.batch, ctx.heads = batch, heads
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        x, Wq, q, P, keep = ctx.saved_tensors
+        bt, dev = ctx.batch, x.device
+        dA = _cuda(dA, "dA")
+        dx = torch.empty_like(x)
+        dWq = torch.empty_like(Wq)
+        dbq = torch.empty(D, device=dev)
+        ws, wsb = _ws_for(bt, ctx.heads, dev)
+        _lib.call("gcgcn_mha_bwd", bt.ref, ctx.heads, _p(x), _p(Wq), _p(q), _p(keep), _p(P), _p(dA),
+                  _p(dx), _p(dWq), _p(dbq), ws, wsb, _stream(dev))
+        return dx, dWq, dbq, None, None, None
+
+
+# ------------------------------------------------------------------------------- a3/a4/a6 stack
+class StackFn(Function):
+    """Dense-connected GraphConv stack + output linear (G:36-50, 63-80, 97-120)."""
+
+    @staticmethod
+    def forward(ctx, x, ebar, A, WnX, We, Winner, Wout, bout, batch: RaggedBatch, heads: int,
+                layers: int, in_dim: int, slab: int, flags: int, keep):
+        x, ebar, A = _cuda(x, "node_feat"), _cuda(ebar, "ebar"), _cuda(A, "adj_matrix")
+        WnX, We = _cuda(WnX, "WnX"), _cuda(We, "We")
+        Winner = None if Winner is None else _cuda(Winner, "Winner")
+        linear = bool(flags & _lib.STACK_LINEAR)
+        if linear:
+            Wout, bout = _cuda(Wout, "Wout"), _cuda(bout, "bout")
+        if keep is not None:
+            keep = _cuda(keep, "keep")
+        dev, M, HD = x.device, batch.total_nodes, heads * slab
+        if A.numel() != heads * batch.total_pairs:
+            raise _lib.GcgcnError(f"attention has {A.numel()} entries, expected {heads} x {batch.total_pairs}")
+        Z = torch.empty(M, HD, device=dev)
+        G = torch.empty(M, HD, device=dev)
+        F = torch.empty(M, HD, device=dev) if linear else None
+        y = torch.empty(M, D if linear else slab, device=dev)
+        ws, wsb = _ws_for(batch, heads, dev)
+        _lib.call("gcgcn_graphconv_stack_fwd", batch.ref, heads, layers, in_dim, slab, flags, _p(x), _p(ebar),
+                  _p(A), _p(WnX), _p(We), _p(Winner), _p(Wout), _p(bout), _p(keep), _p(Z), _p(G), _p(F),
+                  _p(y), ws, wsb, _stream(dev))
+        ctx.save_for_backward(x, ebar, A, WnX, We, Winner, Wout, keep, Z, G, F)
+        ctx.cfg = (batch, heads, layers, in_dim, slab, flags)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ebar, A, WnX, We, Winner, Wout, keep, Z, G, F = ctx.saved_tensors
+        batch, heads, layers, in_dim, slab, flags = ctx.cfg
+        dev = x.device
+        dy = _cuda(dy, "dy")
+        linear = bool(flags & _lib.STACK_LINEAR)
+        dx = torch.empty_like(x)
+        debar = torch.empty_like(ebar)
+        dA = torch.empty_like(A)
+        dWnX, dWe = torch.empty_like(WnX), torch.empty_like(We)
+        dWinner = None if Winner is None else torch.empty_like(Winner)
+        dWout = torch.empty_like(Wout) if linear else None
+        dbout = torch.empty(D, device=dev) if linear else None
+        ws, wsb = _ws_for(batch, heads, dev)
+        _lib.call("gcgcn_graphconv_stack_bwd", batch.ref, heads, layers, in_dim, slab, flags, _p(x), _p(ebar),
+                  _p(A), _p(WnX), _p(We), _p(Winner), _p(Wout), _p(keep), _p(Z), _p(G), _p(F), _p(dy),
+                  _p(dx), _p(debar), _p(dA), _p(dWnX), _p(dWe), _p(dWinner), _p(dWout), _p(dbout),
+                  ws, wsb, _stream(dev))
+        return (dx, debar, dA, dWnX, dWe, dWinner, dWout, dbout, None, None, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------- a8 pair gathers
+class PairGatherFn(Function):
+    """P_h[p] = cat(feat[h_idx[p]], dis[dis_h[p]]), P_t likewise (G:306-307, 351-352)."""
+
+    @staticmethod
+    def forward(ctx, feat, dis, tables: PairTables, batch: RaggedBatch):
+        feat = _cuda(feat, "node_feats")
+        fw = feat.shape[1]
+        dw = 0
+        if dis is not None:
+            dis = _cuda(dis, "dis_embed")
+            dw = dis.shape[1]
+            if not tables.has_dis:
+                raise _lib.GcgcnError("PairTables were built without node_relative_pos")
+        dev = feat.device
+        out_h = torch.empty(batch.total_pairs, fw + dw, device=dev)
+        out_t = torch.empty(batch.total_pairs, fw + dw, device=dev)
+        _lib.call("gcgcn_pair_gather_fwd", batch.ref, _p(feat), fw, _p(dis), dw, _p(tables.h_idx),
+                  _p(tables.t_idx), _p(tables.dis_h) if dw else None, _p(tables.dis_t) if dw else None,
+                  _p(out_h), _p(out_t), _stream(dev))
+        ctx.cfg = (tables, batch, fw, dw, 0 if dis is None else dis.shape[0], feat.shape[0])
+        return out_h, out_t
+
+    @staticmethod
+    def backward(ctx, dh, dt):
+        tables, batch, fw, dw, rows, nrows = ctx.cfg
+        dev = dh.device if dh is not None else dt.device
+        shape = (batch.total_pairs, fw + dw)
+        dh = torch.zeros(shape, device=dev) if dh is None else _cuda(dh, "dout_h")
+        dt = torch.zeros(shape, device=dev) if dt is None else _cuda(dt, "dout_t")
+        dfeat = torch.empty(nrows, fw, device=dev)
+        ddis = torch.empty(rows, dw, device=dev) if dw else None
+        ws, wsb = _ws_for(batch, 1, dev)
+        _lib.call("gcgcn_pair_gather_bwd", batch.ref, _p(dh), _p(dt), fw, dw, rows,
+                  _p(tables.dis_h) if dw else None, _p(tables.dis_t) if dw else None, _p(dfeat), _p(ddis),
+                  ws, wsb, _stream(dev))
+        return dfeat, ddis, None, None
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, trans_a=False, trans_b=False, bias=None,
+         out: Optional[torch.Tensor] = None, alpha=1.0, beta=0.0) -> torch.Tensor:
+    """Thin test hook over gcgcn_gemm (row-major fp32)."""
+    a, b = _cuda(a, "A"), _cuda(b, "B")
+    M = a.shape[1] if trans_a else a.shape[0]
+    K = a.shape[0] if trans_a else a.shape[1]
+    N = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.zeros(M, N, device=a.device)
+    ws = workspace(a.device, 32 << 20)
+    _lib.call("gcgcn_gemm", int(trans_a), int(trans_b), M, N, K, float(alpha), _p(a), a.shape[1], _p(b),
+              b.shape[1], float(beta), _p(out), out.shape[1], _p(bias), ws.data_ptr(), ws.numel(),
+              _stream(a.device))
+    return out

@@ -1,0 +1,217 @@
+/*
+ * gcgcn_b200 -- C ABI of the B200-native (sm_100a) entity-graph convolution hot path of GCGCN.
+ *
+ * The reference (Huiweizhou/GCGCN) has no FFI: its boundary for this path is the Python
+ * nn.Module surface in models/GCGCN_glove.py (G) and
+ * models/GraphCNN_multihead_bert_gate_cls.py (B; graph classes byte-identical to G).  Every
+ * entry point below therefore cites the reference *method* it replaces.  The Python drop-in
+ * modules in gcgcn_b200/modules.py bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host"; a CPU buffer is an
+ *     error, never a fallback;
+ *   - the library never allocates or frees: outputs, saved-for-backward buffers and
+ *     workspaces are caller-owned (sizes via the *_workspace_bytes functions);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - return value: 0 = ok, negative = error (see codes); gcgcn_last_error() gives the text
+ *     for the calling thread;
+ *   - node-sized tensors ([total_nodes, *]) and attention maps are float32; the n x n x 128
+ *     edge tensors (the bytes that matter) are float32 or bfloat16, selected by `edge_dtype`;
+ *     accumulation is always float32;
+ *   - hidden width d = 128 (G:234) is a compile-time constant of the kernels.
+ *
+ * Ragged batches: B document graphs are concatenated.  Node rows of document b live at
+ * [node_ptr[b], node_ptr[b+1]); its n_b x n_b pair grid (edge features, attention maps,
+ * masks) starts at pair offset pair_ptr[b] (= sum of n^2 of earlier documents) and is
+ * row-major [i][j].  B = 1 reproduces the reference's un-batched call.
+ */
+#ifndef GCGCN_B200_H
+#define GCGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCGCN_HIDDEN 128
+
+#define GCGCN_OK 0
+#define GCGCN_ERR_INVALID_ARG (-1)
+#define GCGCN_ERR_UNSUPPORTED (-2)
+#define GCGCN_ERR_CUDA (-3)
+#define GCGCN_ERR_WORKSPACE (-4)
+
+#define GCGCN_F32 0
+#define GCGCN_BF16 1
+
+/* flags of gcgcn_graphconv_stack_{fwd,bwd} */
+#define GCGCN_STACK_RELU 1       /* relu after every sub-layer (G:71, G:108)                    */
+#define GCGCN_STACK_RESIDUAL 2   /* F_h = cat_l drop(g_l) + x  (G:75-76, G:112-113)             */
+#define GCGCN_STACK_LINEAR 4     /* y = Linear(cat_h F_h)      (G:78, G:117-118)                */
+
+typedef struct gcgcn_batch {
+    int32_t num_docs;        /* B                                                        */
+    int32_t total_nodes;     /* sum_b n_b                                                */
+    int64_t total_pairs;     /* sum_b n_b^2                                              */
+    int32_t max_nodes;       /* max_b n_b                                                */
+    int32_t reserved;
+    const int32_t* node_ptr; /* [B+1] device                                             */
+    const int64_t* pair_ptr; /* [B+1] device                                             */
+    const int32_t* row_doc;  /* [total_nodes] device: document of each node row          */
+} gcgcn_batch;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* gcgcn_version(void);
+const char* gcgcn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t gcgcn_launch_count(void);
+/* fills SM count and compute capability of the current device */
+int gcgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* upper bound, in bytes, of the workspace any entry point below needs for this batch shape */
+size_t gcgcn_workspace_bytes(int32_t total_nodes, int64_t total_pairs, int32_t heads);
+
+/* ---- a1: mention->entity pooling, replaces G:297-298 (= B:287-288) ------------------------
+ * x0[e,:] = sum_k w[k] * ctx[tok_idx[k],:] for k in [ent_ptr[e], ent_ptr[e+1]).
+ * The CSR table is built on the host bit-exactly from the reference's node_pos weights
+ * (config/Config.py:169-176, 223) by gcgcn_b200.batch.PoolTable.
+ * bwd uses the transposed table (token -> entities) so it is a deterministic gather too.   */
+int gcgcn_pool_fwd(const float* ctx, const int32_t* ent_ptr, const int32_t* tok_idx, const float* w,
+                   int32_t total_nodes, float* x0, void* stream);
+int gcgcn_pool_bwd(const float* dx0, const int32_t* tok_ptr, const int32_t* ent_idx, const float* w_t,
+                   int32_t total_tokens, float* dctx, void* stream);
+
+/* ---- shared edge pass ("K_edge_reduce"), the n^2*d stream of G:40-41 and G:161 ----------
+ * mean only (what GraphConv needs from the edge tensor, G:40-41 collapsed):
+ *   ebar[r,:] = mean_j e[i,j,:]                      r = node row of (b,i)
+ * bwd: de[i,j,:] = debar[r,:] / n_b                                                        */
+int gcgcn_edge_mean_fwd(const gcgcn_batch* bt, const void* e, int32_t edge_dtype, float* ebar,
+                        void* stream);
+int gcgcn_edge_mean_bwd(const gcgcn_batch* bt, const float* debar, int32_t edge_dtype, void* de,
+                        void* stream);
+
+/* ---- a2: GATAttention.forward(node_feat, edge_feat, mask), replaces G:154-168 -------------
+ * energy_ij = u.x_j + v.e_ij + c  with  u = Wh^T w1 + Wt^T w2, v = Wr^T w3,
+ * c = w1.bh + w2.bt + w3.br + b (exact collapse of G:156-162; built from the reference-named
+ * parameters on the host side); P = softmax_j(energy); A = P * keep.
+ * mask: uint8 [total_pairs], honoured only if apply_mask != 0 (the reference ignores it,
+ * G:163-164).  keep: keep-scale dropout mask [total_pairs] (0 or 1/(1-p)) or NULL (eval).
+ * The same pass over e also yields ebar for the following GraphConvolution.
+ * fwd outputs: P (softmax), A (post-dropout; may alias P when keep == NULL), ebar.
+ * ws: >= total_nodes floats.                                                               */
+int gcgcn_gat_fwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype,
+                  const float* u, const float* v, const float* c, const uint8_t* mask,
+                  int32_t apply_mask, const float* keep, float* P, float* A, float* ebar,
+                  void* ws, size_t ws_bytes, void* stream);
+/* bwd inputs: dA (grad of A), debar (grad of ebar, may be NULL).
+ * outputs: dx [total_nodes,128], de (edge_dtype) [total_pairs,128], du[128], dv[128], dc[1]. */
+int gcgcn_gat_bwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype,
+                  const float* u, const float* v, const uint8_t* mask, int32_t apply_mask,
+                  const float* keep, const float* P, const float* dA, const float* debar,
+                  float* dx, void* de, float* du, float* dv, float* dc,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a5: MultiHeadAttention.forward(node_feat, mask=None), replaces G:133-142 -------------
+ * q = x Wq^T + bq (Wq = the H linears_q weights stacked to [128,128], G:129);
+ * P_h = softmax(q_h q_h^T / sqrt(d_h)) -- the key uses linears_q too (G:137);
+ * A_h = P_h * keep_h.  Attention maps are head-major: [H][total_pairs].
+ * q [total_nodes,128] is an output saved for backward.                                     */
+int gcgcn_mha_fwd(const gcgcn_batch* bt, int32_t heads, const float* x, const float* Wq,
+                  const float* bq, const float* keep, float* q, float* P, float* A,
+                  void* ws, size_t ws_bytes, void* stream);
+int gcgcn_mha_bwd(const gcgcn_batch* bt, int32_t heads, const float* x, const float* Wq,
+                  const float* q, const float* keep, const float* P, const float* dA,
+                  float* dx, float* dWq, float* dbq, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a3/a4/a6: GraphConv / GraphConvolution / MultiGraphConvolution .forward -------------
+ * replaces G:36-50, G:63-80, G:97-120.  For head h and sub-layer l (g = 128 / layers):
+ *   Z_hl = x WnX[:, h,l] + sum_{m<l} g_hm Winner[h,l,m]        (node projection, dense connect)
+ *   out  = ( ebar We[:, h,l] + A_h Z_hl ) / r_h ,  r = rowsum(A_h) + [rowsum == 0]  (G:43-50)
+ *   g_hl = relu(out);  F_h = cat_l(keep * g_hl) + x;  y = cat_h(F_h) Wout^T + bout
+ * Packed weights (built by the drop-in modules from the reference-named parameters):
+ *   WnX  [128, H*128]  column h*128 + l*g + c  = graphconv[h*L+l].weights_node[0:128, c]
+ *   We   [128, H*128]  column h*128 + l*g + c  = graphconv[h*L+l].weights_edge[:, c]
+ *   Winner [H][L][128][g]  row m*g + k (m < l) = graphconv[h*L+l].weights_node[128 + m*g + k, :]
+ *   Wout [128, H*128], bout [128]              = linear_layer.{weight,bias}
+ * A: [H][total_pairs]; keep: [total_nodes, H*128] or NULL.
+ * Saved for backward (caller-owned, float32): Z, G, F -- each [total_nodes, H*128].
+ * flags: GCGCN_STACK_*; without GCGCN_STACK_LINEAR, y receives F (H must be 1 then).
+ * in_dim = width of x (rows of WnX), slab = per-head output width = layers * g.  Inside the two
+ * conv blocks both are 128; a stand-alone GraphConv(input_dim, 128, output_dim) (G:19) is
+ * layers = 1, in_dim = input_dim, slab = output_dim in {16,32,64,128}, flags = 0, and every
+ * "H*128" above reads "H*slab".                                                            */
+int gcgcn_graphconv_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim,
+                              int32_t slab, int32_t flags,
+                              const float* x, const float* ebar, const float* A,
+                              const float* WnX, const float* We, const float* Winner,
+                              const float* Wout, const float* bout, const float* keep,
+                              float* Z, float* G, float* F, float* y,
+                              void* ws, size_t ws_bytes, void* stream);
+int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim,
+                              int32_t slab, int32_t flags,
+                              const float* x, const float* ebar, const float* A,
+                              const float* WnX, const float* We, const float* Winner,
+                              const float* Wout, const float* keep,
+                              const float* Z, const float* G, const float* F, const float* dy,
+                              float* dx, float* debar, float* dA,
+                              float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
+                              void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a8: pair gathers, replaces G:351-352 (+ G:306-307) -----------------------------------
+ * out_h[p,:] = cat(feat[h_idx[p],:], dis[dis_h[p],:]),  out_t[p,:] = cat(feat[t_idx[p],:], dis[dis_t[p],:])
+ * for every pair p of the batch.  Index tables are int32 [total_pairs] holding *global* node
+ * rows (h_idx[i,j] = node_ptr[b]+j, t_idx[i,j] = node_ptr[b]+i, quirk 6) and distance rows
+ * (dis_plus +/- node_relative_pos), built by gcgcn_b200.batch.PairTables.
+ * feat_w and dis_w must be multiples of 4; dis_w may be 0 (in-loop gathers, G:321-322).
+ * bwd: dfeat[r,:] = sum over pairs that gathered row r (segmented, deterministic);
+ *      ddis[k,:]  = sum over pairs that gathered distance row k.                           */
+int gcgcn_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int32_t feat_w,
+                          const float* dis, int32_t dis_w, const int32_t* h_idx,
+                          const int32_t* t_idx, const int32_t* dis_h, const int32_t* dis_t,
+                          float* out_h, float* out_t, void* stream);
+int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t,
+                          int32_t feat_w, int32_t dis_w, int32_t dis_rows,
+                          const int32_t* dis_h, const int32_t* dis_t,
+                          float* dfeat, float* ddis, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- block-level composites (SURVEY.md section 8b minimum set) ---------------------------
+ * CAGGC = a2 + a4 sharing one pass over e0 (G:330-333); MAGGC = a5 + a6 (G:336-337).
+ * They call the entry points above in order with buffers carved from `ws`; `saved` is a
+ * caller-owned arena of gcgcn_block_saved_bytes(...) bytes that bwd reads back.            */
+size_t gcgcn_block_saved_bytes(int32_t total_nodes, int64_t total_pairs, int32_t heads);
+int gcgcn_caggc_fwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e,
+                    int32_t edge_dtype, const float* u, const float* v, const float* c,
+                    const float* WnX, const float* We, const float* Winner, const float* Wout,
+                    const float* bout, float* y, void* saved, void* ws, size_t ws_bytes,
+                    void* stream);
+int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e,
+                    int32_t edge_dtype, const float* u, const float* v,
+                    const float* WnX, const float* We, const float* Winner, const float* Wout,
+                    const float* dy, const void* saved, float* dx, void* de,
+                    float* du, float* dv, float* dc, float* dWnX, float* dWe, float* dWinner,
+                    float* dWout, float* dbout, void* ws, size_t ws_bytes, void* stream);
+int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x,
+                    const void* e, int32_t edge_dtype, const float* Wq, const float* bq,
+                    const float* WnX, const float* We, const float* Winner, const float* Wout,
+                    const float* bout, float* y, void* saved, void* ws, size_t ws_bytes,
+                    void* stream);
+int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x,
+                    int32_t edge_dtype, const float* Wq,
+                    const float* WnX, const float* We, const float* Winner, const float* Wout,
+                    const float* dy, const void* saved, float* dx, void* de,
+                    float* dWq, float* dbq, float* dWnX, float* dWe, float* dWinner,
+                    float* dWout, float* dbout, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- dense projection used by the entry points above (exported for tests) ----------------
+ * C = alpha * op(A) op(B) + beta * C (+ bias broadcast over rows), row-major float32.
+ * trans_a / trans_b: 0 = as stored, 1 = transposed.  K may be huge (weight gradients reduce
+ * over every node row of the batch); the split-K partials live in ws.                      */
+int gcgcn_gemm(int32_t trans_a, int32_t trans_b, int32_t M, int32_t N, int32_t K, float alpha,
+               const float* A, int32_t lda, const float* B, int32_t ldb, float beta, float* C,
+               int32_t ldc, const float* bias, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCGCN_B200_H */

@@ -1,0 +1,116 @@
+"""Host-side index builders and batch descriptors vs the oracle's literal restatement of
+config/Config.py (C:169-176, 207-217, 223) and G:351-352.  Integer work: bit-exact."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import gcgcn_oracle as O
+from gcgcn_b200 import synthetic as S
+from gcgcn_b200.batch import (PairTables, PoolTable, RaggedBatch, make_dis2idx, node_relative_pos,
+                              shard_documents)
+
+
+def test_ragged_batch_offsets():
+    bt = RaggedBatch([3, 1, 5, 0, 2], "cpu")
+    assert bt.node_ptr_host.tolist() == [0, 3, 4, 9, 9, 11]
+    assert bt.pair_ptr_host.tolist() == [0, 9, 10, 35, 35, 39]
+    assert bt.row_doc_host.tolist() == [0, 0, 0, 1, 2, 2, 2, 2, 2, 4, 4]
+    assert (bt.total_nodes, bt.total_pairs, bt.max_nodes, bt.num_docs) == (11, 39, 5, 5)
+    # algorithmic bytes formula of SURVEY.md 8d: s*d*(5 n^2 + 8 n)
+    one = RaggedBatch([42], "cpu")
+    assert one.algorithmic_bytes(4, backward=True) == 4 * 128 * (5 * 42 * 42 + 8 * 42)
+    assert one.algorithmic_bytes(4, backward=False) == 4 * 128 * (2 * 42 * 42 + 3 * 42)
+    assert round(one.algorithmic_bytes() / 1e6, 2) == 4.69
+
+
+def test_empty_batch():
+    bt = RaggedBatch([], "cpu")
+    assert (bt.total_nodes, bt.total_pairs, bt.max_nodes) == (0, 0, 0)
+
+
+def _check_pool_table(spans_list, lens):
+    tab = PoolTable.from_spans(spans_list, lens)
+    node0, tok0 = 0, 0
+    for spans, L in zip(spans_list, lens):
+        dense_ref = O.build_node_pos(spans, L)                      # [n, min(L,512)] float32
+        Lt = dense_ref.shape[1]
+        got = tab.dense(slice(node0, node0 + len(spans)), tok0, Lt)
+        assert torch.equal(got, dense_ref)                          # bit-exact weights and positions
+        node0 += len(spans)
+        tok0 += Lt
+    assert tab.total_tokens == tok0 and tab.total_nodes == node0
+    # the table from the dense matrices is the same table
+    tab2 = PoolTable.from_node_pos([O.build_node_pos(s, L) for s, L in zip(spans_list, lens)])
+    for name in ("ent_ptr_host", "tok_idx_host", "w_host", "tok_ptr_host", "ent_idx_host", "w_t_host"):
+        assert np.array_equal(getattr(tab, name), getattr(tab2, name)), name
+    # transpose really is the transpose
+    dense = np.zeros((tab.total_nodes, tab.total_tokens), np.float32)
+    for e in range(tab.total_nodes):
+        for k in range(tab.ent_ptr_host[e], tab.ent_ptr_host[e + 1]):
+            dense[e, tab.tok_idx_host[k]] = tab.w_host[k]
+    dense_t = np.zeros_like(dense)
+    for t in range(tab.total_tokens):
+        for k in range(tab.tok_ptr_host[t], tab.tok_ptr_host[t + 1]):
+            dense_t[tab.ent_idx_host[k], t] = tab.w_t_host[k]
+    assert np.array_equal(dense, dense_t)
+
+
+def test_pool_table_matches_reference_weights_on_synthetic_batch():
+    docs = S.make_batch()
+    _check_pool_table([d.spans for d in docs], [d.L for d in docs])
+
+
+def test_pool_table_overlap_overwrite_and_truncation():
+    # overlapping mentions: the later span overwrites (C:174); tokens >= 512 are cut (C:223)
+    spans = [[[0, 4], [2, 5]], [[510, 514]], [[600, 603], [7, 8]], [[3, 4], [3, 4], [3, 4]]]
+    _check_pool_table([spans], [700])
+    tab = PoolTable.from_spans([spans], [700])
+    assert tab.total_tokens == 512
+    # entity 1 keeps only tokens 510, 511 with weight 1/4 each; entity 2 loses its first mention
+    assert tab.tok_idx_host[tab.ent_ptr_host[1]:tab.ent_ptr_host[2]].tolist() == [510, 511]
+    assert tab.tok_idx_host[tab.ent_ptr_host[2]:tab.ent_ptr_host[3]].tolist() == [7]
+    assert tab.w_host[tab.ent_ptr_host[2]] == np.float32(0.5)
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.lists(st.lists(st.tuples(st.integers(0, 560), st.integers(1, 6)), min_size=1, max_size=4),
+                min_size=1, max_size=9), st.integers(520, 640))
+def test_pool_table_property(entities, L):
+    spans = [[[s, min(s + ln, L)] for s, ln in ms if s < L] or [[0, 1]] for ms in entities]
+    spans = [[m for m in ms if m[1] > m[0]] or [[0, 1]] for ms in spans]
+    _check_pool_table([spans], [L])
+
+
+def test_dis2idx_and_relative_pos():
+    assert np.array_equal(make_dis2idx(), O.make_dis2idx())
+    for d in S.make_batch():
+        assert np.array_equal(node_relative_pos(d.first_pos), O.build_node_relative_pos(d.first_pos).numpy())
+    rp = node_relative_pos([0, 1, 3, 700, 90])
+    assert rp[0, 3] == -10 and rp[3, 0] == 10 and rp[1, 0] == 1 and rp[0, 2] == -2 and rp[4, 0] == 7
+
+
+def test_pair_tables_orientation_and_distance_rows():
+    docs = S.make_batch((0, 5, 11))
+    bt = RaggedBatch([d.n for d in docs], "cpu")
+    rps = [node_relative_pos(d.first_pos) for d in docs]
+    tabs = PairTables(bt, rps)
+    for b, d in enumerate(docs):
+        lo, hi = bt.pair_ptr_host[b], bt.pair_ptr_host[b + 1]
+        h_ref, t_ref, dh_ref, dt_ref = O.pair_index_tables(torch.from_numpy(rps[b]))
+        base = bt.node_ptr_host[b]
+        assert np.array_equal(tabs.h_idx_host[lo:hi] - base, h_ref.reshape(-1).numpy())   # h_idx[i,j] = j
+        assert np.array_equal(tabs.t_idx_host[lo:hi] - base, t_ref.reshape(-1).numpy())   # t_idx[i,j] = i
+        assert np.array_equal(tabs.dis_h_host[lo:hi], dh_ref.reshape(-1).numpy())
+        assert np.array_equal(tabs.dis_t_host[lo:hi], dt_ref.reshape(-1).numpy())
+        assert tabs.dis_h_host[lo:hi].min() >= 0 and tabs.dis_h_host[lo:hi].max() <= 20
+    assert tabs.h_idx_host.dtype == np.int32
+
+
+def test_shard_documents_balances_pair_counts():
+    sizes = S.shard_doc_sizes(1200)
+    for world in (1, 2, 4, 8):
+        shards = shard_documents(sizes, world)
+        assert sorted(i for s in shards for i in s) == list(range(1200))
+        loads = [int((sizes[s] ** 2).sum()) for s in shards]
+        assert max(loads) - min(loads) <= 42 * 42
