@@ -72,6 +72,8 @@ SIGNATURES = {
     "gcgcn_last_error": (c_char_p, []),
     "gcgcn_launch_count": (c_uint64, []),
     "gcgcn_device_info": (c_int32, [POINTER(c_int32)] * 3),
+    "gcgcn_timing_begin": (c_int32, [_P]),
+    "gcgcn_timing_end": (c_int32, [_P, c_char_p, c_size_t]),
     "gcgcn_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "gcgcn_pool_fwd": (c_int32, [_P, _P, _P, _P, c_int32, _P, _P]),
     "gcgcn_pool_bwd": (c_int32, [_P, _P, _P, _P, c_int32, _P, _P]),
@@ -137,6 +139,21 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().gcgcn_launch_count())
+
+
+def timing_begin(stream: int) -> None:
+    call("gcgcn_timing_begin", stream)
+
+
+def timing_end(stream: int) -> dict:
+    """{kernel name: (launches, total_ms)} since timing_begin."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    call("gcgcn_timing_end", stream, buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def version() -> str:

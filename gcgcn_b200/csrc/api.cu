@@ -1,6 +1,10 @@
 // extern "C" surface of libgcgcn_b200.so (declared in include/gcgcn_b200.h).
 // Host-side orchestration only: argument checks, workspace carving and kernel sequencing.
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -45,6 +49,28 @@ int pair_dis_warps();
 
 // ---- error text, launch counter, device cache --------------------------------------------------
 std::atomic<uint64_t> g_launches{0};
+std::atomic<bool> g_timing{false};
+
+namespace {
+struct Mark { const char* name; cudaEvent_t ev; };
+std::mutex g_tmutex;
+std::vector<Mark> g_marks;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+void timing_mark(const char* name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_tmutex);
+    cudaEvent_t e = take_event();
+    if (e == nullptr) return;
+    cudaEventRecord(e, st);
+    g_marks.push_back({name, e});
+}
 
 char* error_buffer() {
     static thread_local char buf[512] = "";
@@ -175,9 +201,51 @@ size_t gcgcn_workspace_bytes(int32_t total_nodes, int64_t total_pairs, int32_t h
     return b;
 }
 
+// ---- per-kernel timing (bench.py's roofline section) ----------------------------------------
+int gcgcn_timing_begin(void* stream) {
+    std::lock_guard<std::mutex> lk(g_tmutex);
+    for (auto& m : g_marks) g_event_pool.push_back(m.ev);
+    g_marks.clear();
+    cudaEvent_t e = take_event();
+    if (e == nullptr) return fail(GCGCN_ERR_CUDA, "timing_begin: cannot create an event");
+    GCGCN_TRY(cuda_ok(cudaEventRecord(e, static_cast<cudaStream_t>(stream)), "timing_begin"));
+    g_marks.push_back({"(begin)", e});
+    g_timing.store(true);
+    return GCGCN_OK;
+}
+
+// writes one line per kernel name: "<name>\t<launches>\t<total milliseconds>\n"
+int gcgcn_timing_end(void* stream, char* buf, size_t cap) {
+    g_timing.store(false);
+    std::lock_guard<std::mutex> lk(g_tmutex);
+    (void)stream;
+    if (buf == nullptr || cap == 0) return fail(GCGCN_ERR_INVALID_ARG, "timing_end: no buffer");
+    buf[0] = 0;
+    if (g_marks.empty()) return GCGCN_OK;
+    GCGCN_TRY(cuda_ok(cudaEventSynchronize(g_marks.back().ev), "timing_end"));
+    std::map<std::string, std::pair<long, double>> acc;
+    for (size_t i = 1; i < g_marks.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto& slot = acc[g_marks[i].name];
+        slot.first += 1;
+        slot.second += ms;
+    }
+    size_t off = 0;
+    for (auto& kv : acc) {
+        int w = snprintf(buf + off, cap - off, "%s\t%ld\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        if (w < 0 || static_cast<size_t>(w) >= cap - off) break;
+        off += static_cast<size_t>(w);
+    }
+    for (auto& m : g_marks) g_event_pool.push_back(m.ev);
+    g_marks.clear();
+    return GCGCN_OK;
+}
+
 // ---- a1 pooling ------------------------------------------------------------------------------
 int gcgcn_pool_fwd(const float* ctx, const int32_t* ent_ptr, const int32_t* tok_idx, const float* w,
                    int32_t total_nodes, float* x0, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_REQUIRE(total_nodes >= 0, "pool_fwd: total_nodes < 0");
     if (total_nodes == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(ctx, "ctx"));
@@ -188,6 +256,7 @@ int gcgcn_pool_fwd(const float* ctx, const int32_t* ent_ptr, const int32_t* tok_
 
 int gcgcn_pool_bwd(const float* dx0, const int32_t* tok_ptr, const int32_t* ent_idx, const float* w_t,
                    int32_t total_tokens, float* dctx, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_REQUIRE(total_tokens >= 0, "pool_bwd: total_tokens < 0");
     if (total_tokens == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(dx0, "dx0"));
@@ -198,6 +267,7 @@ int gcgcn_pool_bwd(const float* dx0, const int32_t* tok_ptr, const int32_t* ent_
 
 // ---- shared edge pass ------------------------------------------------------------------------
 int gcgcn_edge_mean_fwd(const gcgcn_batch* bt, const void* e, int32_t edge_dtype, float* ebar, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     if (bt->total_nodes == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(e, "edge_feat"));
@@ -207,6 +277,7 @@ int gcgcn_edge_mean_fwd(const gcgcn_batch* bt, const void* e, int32_t edge_dtype
 }
 
 int gcgcn_edge_mean_bwd(const gcgcn_batch* bt, const float* debar, int32_t edge_dtype, void* de, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     if (bt->total_nodes == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(debar, "debar"));
@@ -219,6 +290,7 @@ int gcgcn_edge_mean_bwd(const gcgcn_batch* bt, const float* debar, int32_t edge_
 int gcgcn_gat_fwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype, const float* u,
                   const float* v, const float* c, const uint8_t* mask, int32_t apply_mask, const float* keep,
                   float* P, float* A, float* ebar, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     if (bt->total_nodes == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(x, "node_feat"));
@@ -241,6 +313,7 @@ int gcgcn_gat_bwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t 
                   const float* v, const uint8_t* mask, int32_t apply_mask, const float* keep, const float* P,
                   const float* dA, const float* debar, float* dx, void* de, float* du, float* dv, float* dc,
                   void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     if (bt->total_nodes == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(x, "node_feat"));
@@ -268,6 +341,7 @@ int gcgcn_gat_bwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t 
 // ---- a5 MultiHeadAttention -------------------------------------------------------------------
 int gcgcn_mha_fwd(const gcgcn_batch* bt, int32_t heads, const float* x, const float* Wq, const float* bq,
                   const float* keep, float* q, float* P, float* A, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     GCGCN_REQUIRE(heads >= 1 && D % heads == 0, "mha_fwd: head_num %d must divide %d", heads, D);
     if (bt->total_nodes == 0) return GCGCN_OK;
@@ -285,6 +359,7 @@ int gcgcn_mha_fwd(const gcgcn_batch* bt, int32_t heads, const float* x, const fl
 int gcgcn_mha_bwd(const gcgcn_batch* bt, int32_t heads, const float* x, const float* Wq, const float* q,
                   const float* keep, const float* P, const float* dA, float* dx, float* dWq, float* dbq,
                   void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     GCGCN_REQUIRE(heads >= 1 && D % heads == 0, "mha_bwd: head_num %d must divide %d", heads, D);
     if (bt->total_nodes == 0) return GCGCN_OK;
@@ -315,6 +390,7 @@ int gcgcn_graphconv_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
                               const float* WnX, const float* We, const float* Winner, const float* Wout,
                               const float* bout, const float* keep, float* Z, float* G, float* F, float* y,
                               void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     GCGCN_REQUIRE(heads >= 1 && layers >= 1 && in_dim >= 1 && slab >= 1, "stack_fwd: bad heads/layers/widths");
     const bool linear = flags & GCGCN_STACK_LINEAR;
@@ -353,6 +429,7 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
                               const float* dy, float* dx, float* debar, float* dA, float* dWnX, float* dWe,
                               float* dWinner, float* dWout, float* dbout, void* ws, size_t ws_bytes,
                               void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     GCGCN_REQUIRE(heads >= 1 && layers >= 1 && in_dim >= 1 && slab >= 1 && slab % layers == 0,
                   "stack_bwd: bad heads/layers/widths");
@@ -417,6 +494,7 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
 int gcgcn_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int32_t feat_w, const float* dis,
                           int32_t dis_w, const int32_t* h_idx, const int32_t* t_idx, const int32_t* dis_h,
                           const int32_t* dis_t, float* out_h, float* out_t, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     GCGCN_REQUIRE(feat_w > 0 && feat_w % 4 == 0 && dis_w >= 0 && dis_w % 4 == 0,
                   "pair_gather: widths must be multiples of 4 (feat_w=%d, dis_w=%d)", feat_w, dis_w);
@@ -438,6 +516,7 @@ int gcgcn_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int32_t feat
 int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, int32_t feat_w,
                           int32_t dis_w, int32_t dis_rows, const int32_t* dis_h, const int32_t* dis_t,
                           float* dfeat, float* ddis, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
     GCGCN_REQUIRE(feat_w > 0 && feat_w % 4 == 0 && dis_w >= 0 && dis_w % 4 == 0,
                   "pair_gather: widths must be multiples of 4 (feat_w=%d, dis_w=%d)", feat_w, dis_w);
@@ -453,6 +532,7 @@ int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const floa
 int gcgcn_gemm(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A,
                int32_t lda, const float* B, int32_t ldb, float beta, float* C, int32_t ldc, const float* bias,
                void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
     GCGCN_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
     if (M == 0 || N == 0) return GCGCN_OK;
     GCGCN_TRY(check_device_ptr(C, "C"));

@@ -21,6 +21,10 @@ constexpr int WARP = 32;
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+// optional per-kernel timing (gcgcn_timing_begin/end): one CUDA event after every launch and at
+// every API entry; a kernel's time is the gap to the previous event on the same stream.
+extern std::atomic<bool> g_timing;
+void timing_mark(const char* name, cudaStream_t st);
 
 inline int cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return GCGCN_OK;
@@ -30,8 +34,15 @@ inline int cuda_ok(cudaError_t e, const char* what) {
 #define GCGCN_CHECK_LAUNCH(name)                                        \
     do {                                                                \
         ::gcgcn::g_launches.fetch_add(1, std::memory_order_relaxed);    \
+        if (::gcgcn::g_timing.load(std::memory_order_relaxed)) ::gcgcn::timing_mark(name, st); \
         int rc__ = ::gcgcn::cuda_ok(cudaPeekAtLastError(), name);       \
         if (rc__ != GCGCN_OK) return rc__;                              \
+    } while (0)
+
+#define GCGCN_API_ENTER(stream)                                                          \
+    do {                                                                                 \
+        if (::gcgcn::g_timing.load(std::memory_order_relaxed))                           \
+            ::gcgcn::timing_mark("(between calls)", static_cast<cudaStream_t>(stream));  \
     } while (0)
 
 #define GCGCN_TRY(expr)                    \

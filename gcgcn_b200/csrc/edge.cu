@@ -330,12 +330,13 @@ static int edge_fwd_t(const gcgcn_batch* bt, const T* e, const float* v, const f
         edge_row_fwd_kernel<T, true><<<bt->total_nodes, EDGE_THREADS, smem, st>>>(
             e, bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), bt->row_doc, v, ux,
             mask, keep, P, A, ebar);
+        GCGCN_CHECK_LAUNCH("edge_row_fwd<score+mean>");
     } else {
         edge_row_fwd_kernel<T, false><<<bt->total_nodes, EDGE_THREADS, EDGE_WARPS * D * sizeof(float), st>>>(
             e, bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), bt->row_doc, nullptr,
             nullptr, nullptr, nullptr, nullptr, nullptr, ebar);
+        GCGCN_CHECK_LAUNCH("edge_row_fwd<mean>");
     }
-    GCGCN_CHECK_LAUNCH("edge_row_fwd");
     return GCGCN_OK;
 }
 
@@ -358,16 +359,18 @@ static int edge_bwd_t(const gcgcn_batch* bt, const T* e, const float* v, const f
                       const float* debar, T* de, float* dv_partial, cudaStream_t st) {
     int grid = min(edge_bwd_grid(), bt->total_nodes);
     const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
-    if (dS != nullptr)
+    if (dS != nullptr) {
         edge_row_bwd_kernel<T, true><<<grid, EDGE_THREADS, 0, st>>>(e, bt->node_ptr, pp, bt->row_doc, v,
                                                                     dS, debar, de, dv_partial,
                                                                     bt->total_nodes);
-    else
+        GCGCN_CHECK_LAUNCH("edge_row_bwd<score+mean>");
+    } else {
         edge_row_bwd_kernel<T, false><<<grid, EDGE_THREADS, 0, st>>>(nullptr, bt->node_ptr, pp,
                                                                      bt->row_doc, nullptr, nullptr,
                                                                      debar, de, nullptr,
                                                                      bt->total_nodes);
-    GCGCN_CHECK_LAUNCH("edge_row_bwd");
+        GCGCN_CHECK_LAUNCH("edge_row_bwd<mean>");
+    }
     return GCGCN_OK;
 }
 

@@ -202,7 +202,7 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
     else if (ta && !tb) GCGCN_GEMM(true, false);
     else GCGCN_GEMM(true, true);
 #undef GCGCN_GEMM
-    GCGCN_CHECK_LAUNCH("gemm");
+    GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tt" : "gemm_tn") : (tb ? "gemm_nt" : "gemm_nn"));
     if (splits > 1) {
         const size_t total = static_cast<size_t>(M) * N;
         splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(partial, splits, M, N, alpha, beta, C,

@@ -69,6 +69,10 @@ const char* gcgcn_last_error(void);
 uint64_t gcgcn_launch_count(void);
 /* fills SM count and compute capability of the current device */
 int gcgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* per-kernel timing for bench.py: begin() starts recording one CUDA event after every launch on
+ * `stream`; end() synchronises and writes "<kernel>\t<launches>\t<total ms>\n" lines into buf. */
+int gcgcn_timing_begin(void* stream);
+int gcgcn_timing_end(void* stream, char* buf, size_t cap);
 /* upper bound, in bytes, of the workspace any entry point below needs for this batch shape */
 size_t gcgcn_workspace_bytes(int32_t total_nodes, int64_t total_pairs, int32_t heads);
 

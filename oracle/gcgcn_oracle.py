@@ -42,6 +42,12 @@ Params = Dict[str, Tensor]
 
 HIDDEN = 128  # G:234
 
+# Test hook: when set to a list, every relu of the dense stack appends the smallest |pre-activation|
+# it saw.  relu'(x) jumps at 0, so a document whose margin is within float rounding of 0 has
+# ill-conditioned gradients (any re-implementation may land on the other side of the kink); the
+# tests use this to pick well-conditioned documents for gradient comparisons.
+RELU_MARGIN_PROBE = None
+
 
 def _sub(params: Params, prefix: str) -> Params:
     """Select ``prefix.*`` entries and strip the prefix."""
@@ -89,9 +95,11 @@ def _dense_stack(x: Tensor, edge: Tensor, att: Tensor, p: Params, first: int, la
     cur = x
     for l in range(layers):
         k = first + l
-        g = torch.relu(graph_conv(cur, edge, att,
-                                  p[f"graphconv.{k}.weights_edge"],
-                                  p[f"graphconv.{k}.weights_node"]))       # G:71 / G:108
+        pre = graph_conv(cur, edge, att, p[f"graphconv.{k}.weights_edge"],
+                         p[f"graphconv.{k}.weights_node"])
+        if RELU_MARGIN_PROBE is not None:
+            RELU_MARGIN_PROBE.append(float(pre.detach().abs().min()))
+        g = torch.relu(pre)                                                # G:71 / G:108
         cache.append(g)                                                    # G:72
         cur = torch.cat(cache, dim=-1)                                     # G:73
         m = None if keep is None else keep[l]

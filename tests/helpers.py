@@ -67,6 +67,16 @@ def oracle_blocks(doc, state, layers, heads, keep=None, backward=True, apply_mas
     return out
 
 
+def relu_margin(doc, state, layers, heads) -> float:
+    """Smallest |pre-activation| over every relu of the two blocks (oracle, eval mode)."""
+    O.RELU_MARGIN_PROBE = []
+    try:
+        oracle_blocks(doc, state, layers, heads, backward=False)
+        return min(O.RELU_MARGIN_PROBE)
+    finally:
+        O.RELU_MARGIN_PROBE = None
+
+
 def maxdiff(a, b) -> float:
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     assert a.shape == b.shape, (a.shape, b.shape)
