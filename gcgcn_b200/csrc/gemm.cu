@@ -170,11 +170,26 @@ colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ldx, int ro
 int launch_reduce_partials(const float* partial, int parts, int width, float* out0, int width0,
                            float* out1, cudaStream_t st);
 
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, float alpha, float beta, float* C,
+                         int ldc, const float* bias, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(M) * N;
+    splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias);
+    GCGCN_CHECK_LAUNCH("splitk_reduce");
+    return GCGCN_OK;
+}
+
+int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                   int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
+                   cudaStream_t st, int* taken);
+
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
     if (M <= 0 || N <= 0) return GCGCN_OK;
     if (K < 0) return fail(GCGCN_ERR_INVALID_ARG, "gemm: K < 0");
+    int taken = 0;
+    GCGCN_TRY(launch_gemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ws, ws_bytes, st, &taken));
+    if (taken) return GCGCN_OK;
     const int tiles = ceil_div(M, GM) * ceil_div(N, GN);
     int splits = 1;
     const int target = 2 * sm_count();
@@ -203,12 +218,7 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
     else GCGCN_GEMM(true, true);
 #undef GCGCN_GEMM
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tt" : "gemm_tn") : (tb ? "gemm_nt" : "gemm_nn"));
-    if (splits > 1) {
-        const size_t total = static_cast<size_t>(M) * N;
-        splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(partial, splits, M, N, alpha, beta, C,
-                                                                    ldc, bias);
-        GCGCN_CHECK_LAUNCH("splitk_reduce");
-    }
+    if (splits > 1) GCGCN_TRY(launch_splitk_reduce(partial, splits, M, N, alpha, beta, C, ldc, bias, st));
     return GCGCN_OK;
 }
 

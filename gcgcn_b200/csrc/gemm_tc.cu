@@ -1,0 +1,446 @@
+// tcgen05 / TMEM projection GEMM with fp32-accurate "3xTF32" operand splitting (sm_100a).
+//
+//   C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias          (row-major fp32 in HBM)
+//
+// Why this shape of kernel: the dense contractions of the path are (all node rows of the batch) x
+// (128..1024)-wide projections and their transposes.  fp32 parity with the reference (<= 1e-4 abs)
+// rules out single-pass TF32 (10-bit mantissa), so every fp32 operand value a is split on the fly into
+//   a_hi = a with the low 13 mantissa bits cleared (exactly representable in TF32)
+//   a_lo = a - a_hi                                  (exact in fp32; the MMA keeps its top 11 bits)
+// and the product is accumulated as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (error ~2^-20 relative) by
+// three tcgen05.mma.kind::tf32 instructions per K-step into one fp32 accumulator in TMEM.
+//
+// Structure (one CTA per SM, persistent over 128x128 output tiles):
+//   warps 0-7  producers: global -> registers -> {hi,lo} split -> shared memory in the UMMA
+//              canonical K-major no-swizzle layout ([K/4][128 rows][16 B]); operands stored
+//              "transposed" in HBM (MN-contiguous) are transposed in registers on the way, so the
+//              tensor core always sees K-major tiles.  TMA cannot be used for this stage because the
+//              split is arithmetic on every element.
+//   warp 8     allocates TMEM, then one elected lane issues the MMAs and commits them to mbarriers
+//   warps 9-12 epilogue: tcgen05.ld the 128x128 fp32 accumulator, apply alpha/beta/bias, store
+// Pipelines: 3 shared-memory stages (full/empty mbarriers), 2 TMEM accumulators (tile i+1 is
+// multiplied while tile i is stored).  K may be split across CTAs (weight gradients reduce over all
+// node rows); partials go to the workspace and are reduced by splitk_reduce (deterministic).
+#include "common.cuh"
+
+namespace gcgcn {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_PART_BYTES = 128 * TC_BK * 4;              // one 128 x 32 fp32 operand part: 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_PART_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_PRODUCER_WARPS = 8;                        // two groups of 4
+constexpr int TC_MMA_WARP = 8;
+constexpr int TC_THREADS = 13 * 32;                         // 8 producer + 1 MMA + 4 epilogue warps
+constexpr int TC_TMEM_COLS = 256;                           // 2 accumulators x 128 fp32 columns
+constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcArgs {
+    int M, N, K, lda, ldb, ldc;
+    const float* A;
+    const float* B;
+    const float* bias;
+    float* C;
+    float* partial;     // != nullptr -> split-K partial output [k_splits][M][N]
+    float alpha, beta;
+    int tiles_m, tiles_n, k_splits, k_per_split;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], 128 x 128 x 8 TF32
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8-row x 16-byte core matrices are 128 contiguous
+// bytes; the next core matrix along M/N is 128 B away (SBO), the next along K is 128 rows * 16 B away (LBO).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = (smem_addr >> 4) & 0x3FFFu;
+    d |= static_cast<uint64_t>((128 * 16) >> 4) << 16;   // leading (K) byte offset
+    d |= static_cast<uint64_t>(128 >> 4) << 32;          // stride (M/N) byte offset
+    d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (Blackwell)
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, N = 128, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void split_store(float* hi_base, float* lo_base, int chunk, int row, float4 a) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u);
+    h.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u);
+    l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+    const int off = (chunk * 128 + row) * 4;
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+// One 128(rows) x 32(k) operand tile = 1024 float4; each of the 128 threads of a producer group moves 8.
+// Thread -> (row, 16-byte K chunk) assignment of its i-th float4:
+//   K-contiguous source: a warp instruction covers 8 consecutive rows x 4 consecutive chunks, so global
+//     loads touch 8 rows x 64 contiguous bytes and the shared-memory stores (rows 16 B apart, chunks
+//     2 KB apart) are bank-conflict free;
+//   MN-contiguous source (transposed in registers): lanes walk rows, so the 4-byte global loads coalesce
+//     into 128-byte lines and each store instruction writes 512 contiguous bytes.
+template <bool KCONTIG>
+__device__ __forceinline__ void tile_coord(int tid, int i, int& row, int& chunk) {
+    if (KCONTIG) {
+        const int w = tid >> 5, l = tid & 31;
+        row = 32 * w + 8 * (i >> 1) + (l & 7);
+        chunk = 4 * (i & 1) + (l >> 3);
+    } else {
+        row = tid;
+        chunk = i;
+    }
+}
+
+// KCONTIG: element (row, k) at src[row*ld + k]; otherwise at src[k*ld + row].  Out of range -> 0.
+template <bool KCONTIG>
+__device__ __forceinline__ void fetch_operand(const float* __restrict__ src, int ld, int row0, int rows_total,
+                                              int k0, int kend, bool vec_ok, int tid, float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int r, c;
+        tile_coord<KCONTIG>(tid, i, r, c);
+        const int row = row0 + r, k = k0 + 4 * c;
+        const bool row_ok = row < rows_total;
+        if (KCONTIG) {
+            const float* p = src + static_cast<size_t>(row) * ld + k;
+            if (row_ok && vec_ok && k + 4 <= kend) {
+                v[i] = *reinterpret_cast<const float4*>(p);
+            } else {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = (row_ok && k + q < kend) ? p[q] : 0.f;
+                v[i] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        } else {
+            float t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                t[q] = (row_ok && k + q < kend) ? src[static_cast<size_t>(k + q) * ld + row] : 0.f;
+            v[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    }
+}
+
+template <bool KCONTIG>
+__device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, const float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int r, c;
+        tile_coord<KCONTIG>(tid, i, r, c);
+        split_store(hi, lo, c, r, v[i]);
+    }
+}
+
+template <bool A_KCONTIG, bool B_KCONTIG>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(TC_STAGES) * TC_STAGE_BYTES);
+    // bars: full[3], empty[3], tmem_full[2], tmem_empty[2], then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * TC_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * TC_STAGES + 2 + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full_bar(s), 4);    // one arrive per producer warp
+            mbar_init(empty_bar(s), 1);   // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);   // tcgen05.commit
+            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_mn = args.tiles_m * args.tiles_n;
+    const int total_tiles = tiles_mn * args.k_splits;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        // ===== producers: two groups of 4 warps take alternate K blocks, so two blocks' loads are in flight
+        const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
+        const bool b_vec = (args.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.B) & 15) == 0);
+        const int group = warp >> 2, tid = threadIdx.x & 127;
+        int j = 0;                                   // running K-block index of this CTA
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int ks = t / tiles_mn, rem = t - ks * tiles_mn;
+            const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
+            const int kbeg = ks * args.k_per_split;
+            const int kend = min(args.K, kbeg + args.k_per_split);
+            for (int k0 = kbeg; k0 < kend; k0 += TC_BK, ++j) {
+                if ((j & 1) != group) continue;
+                const int stage = j % TC_STAGES;
+                const uint32_t phase = (j / TC_STAGES) & 1;
+                float4 va[8], vb[8];
+                fetch_operand<A_KCONTIG>(args.A, args.lda, m0, args.M, k0, kend, a_vec, tid, va);
+                fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, k0, kend, b_vec, tid, vb);
+                mbar_wait(empty_bar(stage), phase ^ 1);      // the MMAs that read this stage have retired
+                float* st = reinterpret_cast<float*>(smem + size_t(stage) * TC_STAGE_BYTES);
+                store_operand<A_KCONTIG>(st, st + TC_PART_BYTES / 4, tid, va);
+                store_operand<B_KCONTIG>(st + 2 * (TC_PART_BYTES / 4), st + 3 * (TC_PART_BYTES / 4), tid, vb);
+                fence_proxy_async();          // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(stage));
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int ks = t / tiles_mn;
+                const int kbeg = ks * args.k_per_split;
+                const int kend = min(args.K, kbeg + args.k_per_split);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * TC_BN);
+                uint32_t accumulate = 0;
+                for (int k0 = kbeg; k0 < kend; k0 += TC_BK) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + size_t(stage) * TC_STAGE_BYTES);
+                    const uint32_t a_hi = sa, a_lo = sa + TC_PART_BYTES;
+                    const uint32_t b_hi = sa + 2 * TC_PART_BYTES, b_lo = sa + 3 * TC_PART_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        const uint32_t koff = kk * 2 * (128 * 16);   // two 16-byte K chunks per MMA
+                        umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), TC_IDESC, accumulate);
+                        umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), TC_IDESC, 1u);
+                        umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), TC_IDESC, 1u);
+                        accumulate = 1u;
+                    }
+                    umma_commit(empty_bar(stage));             // stage is free once these MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));                   // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warps 9..12 own TMEM lane quarters (warp % 4) =====
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool c_vec = (args.partial != nullptr ? (args.N % 4 == 0)
+                                                    : (args.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(args.C) & 15) == 0));
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int ks = t / tiles_mn, rem = t - ks * tiles_mn;
+            const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
+            const int kbeg = ks * args.k_per_split;
+            const bool has_k = kbeg < args.K;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < args.M;
+            float* out_row;
+            int ldo;
+            if (args.partial != nullptr) {
+                out_row = args.partial + (static_cast<size_t>(ks) * args.M + (row_ok ? row : 0)) * args.N;
+                ldo = args.N;
+            } else {
+                out_row = args.C + static_cast<size_t>(row_ok ? row : 0) * args.ldc;
+                ldo = args.ldc;
+            }
+            (void)ldo;
+#pragma unroll 1
+            for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                       static_cast<uint32_t>(acc * TC_BN + chunk * 32);
+                tmem_ld32(taddr, v);
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = n0 + chunk * 32 + j;
+                    if (col >= args.N) break;
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = has_k ? __uint_as_float(v[j + q]) : 0.f;
+                    if (args.partial == nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            o[q] *= args.alpha;
+                            if (args.bias != nullptr && col + q < args.N) o[q] += args.bias[col + q];
+                        }
+                    }
+                    if (c_vec && col + 4 <= args.N) {
+                        float4* p = reinterpret_cast<float4*>(out_row + col);
+                        if (args.partial == nullptr && args.beta != 0.f) {
+                            const float4 c = *p;
+                            o[0] += args.beta * c.x; o[1] += args.beta * c.y;
+                            o[2] += args.beta * c.z; o[3] += args.beta * c.w;
+                        }
+                        *p = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (col + q >= args.N) break;
+                            float val = o[q];
+                            if (args.partial == nullptr && args.beta != 0.f) val += args.beta * out_row[col + q];
+                            out_row[col + q] = val;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, float alpha, float beta, float* C,
+                         int ldc, const float* bias, cudaStream_t st);
+
+bool gemm_tc_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GCGCN_GEMM");
+        cached = (e != nullptr && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;   // GCGCN_GEMM=simt disables
+    }
+    return cached == 1;
+}
+
+// returns 1 if the launch was taken by the tensor-core path, 0 if the caller should use the SIMT kernel
+int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                   int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
+                   cudaStream_t st, int* taken) {
+    *taken = 0;
+    if (!gemm_tc_enabled() || K < 1) return GCGCN_OK;
+    if (static_cast<double>(M) * N * K < 2.0e6) return GCGCN_OK;       // tiny: not worth a 128x128 tile
+    TcArgs a;
+    a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+    a.A = A; a.B = B; a.bias = bias; a.C = C; a.alpha = alpha; a.beta = beta;
+    a.tiles_m = ceil_div(M, TC_BM);
+    a.tiles_n = ceil_div(N, TC_BN);
+    const int tiles = a.tiles_m * a.tiles_n;
+    const int sms = sm_count();
+    int splits = 1;
+    if (tiles < sms && K >= 4096) {
+        splits = std::min(ceil_div(2 * sms, tiles), ceil_div(K, 512));
+        const size_t per = static_cast<size_t>(M) * N * sizeof(float);
+        if (ws == nullptr) splits = 1;
+        else splits = static_cast<int>(std::min<size_t>(splits, ws_bytes / per));
+        if (splits < 2) splits = 1;
+    }
+    a.k_per_split = K;
+    a.partial = nullptr;
+    if (splits > 1) {
+        a.k_per_split = ceil_div(ceil_div(K, splits), TC_BK) * TC_BK;
+        splits = ceil_div(K, a.k_per_split);
+        a.partial = static_cast<float*>(ws);
+    }
+    a.k_splits = splits;
+    const int grid = std::min(sms, tiles * splits);
+    // op(A)[m,k]: stored [M][K] (K contiguous) when !ta, [K][M] when ta.
+    // op(B)[k,n] as the N x K operand: stored [N][K] (K contiguous) when tb, [K][N] when !tb.
+    const bool a_kc = !ta, b_kc = (tb != 0);
+#define GCGCN_TC_LAUNCH(AK, BK)                                                                          \
+    do {                                                                                                 \
+        static bool attr_done = false;                                                                   \
+        if (!attr_done) {                                                                                \
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>,                               \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                                   static_cast<int>(TC_SMEM_BYTES)), "gemm_tc smem"));   \
+            attr_done = true;                                                                            \
+        }                                                                                                \
+        gemm_tc_kernel<AK, BK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);                              \
+    } while (0)
+    if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true);
+    else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false);
+    else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true);
+    else GCGCN_TC_LAUNCH(false, false);
+#undef GCGCN_TC_LAUNCH
+    GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
+    if (splits > 1) GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st));
+    *taken = 1;
+    return GCGCN_OK;
+}
+
+}  // namespace gcgcn

@@ -172,9 +172,10 @@ def test_full_size_shard_properties():
     de0s = bt.split_pairs(res["de0"])
     for i in sample:
         alone = run_blocks(gb, [docs[i]])
-        assert_close(alone["y1"], y1s[i], 1e-6, "batch invariance y1")
-        assert_close(alone["y2"], y2s[i], 1e-6, "batch invariance y2")
-        assert_close(alone["dx0"], dxs[i], 1e-6, "batch invariance dx0")
+        # (not bit-identical: tiny products take the CUDA-core GEMM, large ones the tcgen05 3xTF32 GEMM)
+        assert_close(alone["y1"], y1s[i], 2e-5, "batch invariance y1")
+        assert_close(alone["y2"], y2s[i], 2e-5, "batch invariance y2")
+        assert_close(alone["dx0"], dxs[i], 2e-5, "batch invariance dx0")
         r = oracle_blocks(docs[i], state, 2, 8)
         assert_close(y1s[i], r["y1"], FP32_TOL, "y1")
         assert_close(y2s[i], r["y2"], FP32_TOL, "y2")
