@@ -408,10 +408,21 @@ static int prep_smem(K kernel, size_t bytes, const char* name) {
     return GCGCN_OK;
 }
 
+// tensor-core (mma.sync 3xTF32) versions for n <= 64, gcn_stack_mma.cu
+bool stack_mma_usable(const gcgcn_batch* bt, int layers, int slab);
+int launch_stack_fwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                         float* Z, const float* E, const float* Winner, const float* keep, const float* x,
+                         float* G, float* F, cudaStream_t st);
+int launch_stack_bwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                         const float* Z, const float* G, const float* Winner, const float* keep, const float* dF,
+                         float* dZ, float* dE, float* dA, cudaStream_t st);
+
 int launch_stack_fwd(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A, float* Z,
                      const float* E, const float* Winner, const float* keep, const float* x, float* G,
                      float* F, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
+    if (stack_mma_usable(bt, layers, slab))
+        return launch_stack_fwd_mma(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, F, st);
     if (layers < 1 || slab % layers != 0)
         return fail(GCGCN_ERR_UNSUPPORTED, "layer_num %d must divide the output width %d", layers, slab);
     const int gd = slab / layers;
@@ -443,6 +454,8 @@ int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
                      const float* Z, const float* G, const float* Winner, const float* keep,
                      const float* dF, float* dZ, float* dE, float* dA, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
+    if (stack_mma_usable(bt, layers, slab))
+        return launch_stack_bwd_mma(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, dA, st);
     if (layers < 1 || slab % layers != 0)
         return fail(GCGCN_ERR_UNSUPPORTED, "layer_num %d must divide the output width %d", layers, slab);
     const int gd = slab / layers;

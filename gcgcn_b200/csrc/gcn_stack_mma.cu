@@ -1,0 +1,442 @@
+// Dense-connected GraphConv stack for DocRED-sized graphs (n <= 64), warp-level tensor-core version.
+//
+// Same contract as gcn_stack.cu (one CTA per (document, head); see that file for the math), but every
+// small per-document product -- A Z_l, g_{<l} Winner, and in backward dN Z^T, A^T dN, dZ Winner^T --
+// runs on the tensor cores with mma.sync.m16n8k8 TF32.  fp32 parity (<= 1e-4 abs vs the reference) is
+// kept by the same 3xTF32 operand split as the tcgen05 projection GEMM: x = hi + lo with hi exactly
+// representable in TF32, and  a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b.
+//
+// Why mma.sync and not tcgen05 here: the matrices belong to ONE document (16..64 rows); a tcgen05 tile
+// is 128 rows and would have to be built from several documents' block-diagonal attention maps.  The
+// document-batched projections (where M is every node row of the batch) are the tcgen05 kernel's job.
+//
+// Operands live in shared memory as fp32 and are split in registers after the fragment loads.  Row
+// strides are chosen so that both fragment access patterns (lanes = 8 rows x 4 k, or 4 k x 8 cols) are
+// bank-conflict free or at worst 2-way.
+#include "common.cuh"
+
+namespace gcgcn {
+
+constexpr int SM_THREADS = 128;
+constexpr int SM_WARPS = SM_THREADS / WARP;
+
+__device__ __forceinline__ float4 ld4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 ld2g(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// One warp: C[16 x 8*NT] += A[16 x 8*ksteps] * B[8*ksteps x 8*NT] with fp32-accurate 3xTF32.
+//   fa(m, k): element of A, m in [0,16);  fb(k, n): element of B, n in [0, 8*NT).
+// Fragment layout (PTX m16n8k8): g = lane/4, t = lane%4
+//   a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);  b0=(t,g) b1=(t+4,g);  c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)
+template <int NT, class FA, class FB>
+__device__ __forceinline__ void warp_gemm(float (&c)[NT][4], int ksteps, FA fa, FB fb) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int k0 = ks * 8;
+        uint32_t ah[4], al[4];
+        split_tf32(fa(g, k0 + t), ah[0], al[0]);
+        split_tf32(fa(g + 8, k0 + t), ah[1], al[1]);
+        split_tf32(fa(g, k0 + t + 4), ah[2], al[2]);
+        split_tf32(fa(g + 8, k0 + t + 4), ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t bh[2], bl[2];
+            split_tf32(fb(k0 + t, 8 * nt + g), bh[0], bl[0]);
+            split_tf32(fb(k0 + t + 4, 8 * nt + g), bh[1], bl[1]);
+            mma_tf32(c[nt], al, bh);
+            mma_tf32(c[nt], ah, bl);
+            mma_tf32(c[nt], ah, bh);
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_frag(float (&c)[NT][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[nt][q] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int GD>
+__global__ void __launch_bounds__(SM_THREADS)
+stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                     const float* __restrict__ A, float* __restrict__ Z, const float* __restrict__ E,
+                     const float* __restrict__ Winner, const float* __restrict__ keep,
+                     const float* __restrict__ x, float* __restrict__ G, float* __restrict__ F, int layers,
+                     int heads, int flags, long long total_pairs) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    if (n == 0) return;
+    const int S = layers * GD, HD = heads * S, KI = (layers - 1) * GD;
+    const int NP = (n + 15) & ~15;
+    const int LDA = NP + 4, LDG = KI + 4;
+    constexpr int LDZ = GD + 8, LDW = GD + 8, NG = GD / 32;
+
+    float* As = smem;                 // [NP][LDA]  attention map, zero padded
+    float* Zs = As + NP * LDA;        // [NP][LDZ]  Z_l
+    float* Gs = Zs + NP * LDZ;        // [NP][LDG]  g_0 .. g_{L-2}
+    float* Ws = Gs + NP * LDG;        // [KI][LDW]  dense-connect weights of the current sub-layer
+    float* rs = Ws + KI * LDW;        // [NP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const float* Ab = A + static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const bool relu = flags & GCGCN_STACK_RELU, resid = flags & GCGCN_STACK_RESIDUAL;
+
+    for (int idx = tid; idx < NP * NP; idx += SM_THREADS) {
+        const int i = idx / NP, j = idx - i * NP;
+        As[i * LDA + j] = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
+    }
+    for (int idx = tid; idx < NP * LDG; idx += SM_THREADS) Gs[idx] = 0.f;
+    __syncthreads();
+    for (int i = warp; i < NP; i += SM_WARPS) {          // r = rowsum + [rowsum == 0]   (G:47-49)
+        float s = 0.f;
+        for (int j = lane; j < NP; j += WARP) s += As[i * LDA + j];
+        s = warp_sum(s);
+        if (lane == 0) rs[i] = s + (s == 0.f ? 1.f : 0.f);
+    }
+
+    const int MT = NP / 16;
+    for (int l = 0; l < layers; ++l) {
+        const int kin = l * GD;
+        const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+        if (l > 0) {
+            const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
+            for (int idx = tid; idx < kin * (GD / 4); idx += SM_THREADS) {
+                const int k = idx / (GD / 4), c4 = (idx - k * (GD / 4)) * 4;
+                *reinterpret_cast<float4*>(Ws + k * LDW + c4) = ld4g(wsrc + static_cast<size_t>(k) * GD + c4);
+            }
+        }
+        for (int idx = tid; idx < NP * (GD / 4); idx += SM_THREADS) {
+            const int i = idx / (GD / 4), c4 = (idx - i * (GD / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n) v = ld4g(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4);
+            *reinterpret_cast<float4*>(Zs + i * LDZ + c4) = v;
+        }
+        __syncthreads();
+        if (l > 0) {
+            // Z_l += g_{<l} Winner_l   (dense connection, row-local in the reference: G:72-73)
+            for (int u = warp; u < MT * NG; u += SM_WARPS) {
+                const int mt = u / NG, ng = u - mt * NG;
+                float c[4][4];
+                float* zc = Zs + (16 * mt) * LDZ + 32 * ng;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float2 lo = *reinterpret_cast<const float2*>(zc + g * LDZ + 8 * nt + 2 * t);
+                    const float2 hi = *reinterpret_cast<const float2*>(zc + (g + 8) * LDZ + 8 * nt + 2 * t);
+                    c[nt][0] = lo.x; c[nt][1] = lo.y; c[nt][2] = hi.x; c[nt][3] = hi.y;
+                }
+                const float* ga = Gs + (16 * mt) * LDG;
+                const float* wb = Ws + 32 * ng;
+                warp_gemm<4>(c, kin / 8, [&](int m, int k) { return ga[m * LDG + k]; },
+                             [&](int k, int nn) { return wb[k * LDW + nn]; });
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    *reinterpret_cast<float2*>(zc + g * LDZ + 8 * nt + 2 * t) = make_float2(c[nt][0], c[nt][1]);
+                    *reinterpret_cast<float2*>(zc + (g + 8) * LDZ + 8 * nt + 2 * t) = make_float2(c[nt][2], c[nt][3]);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < n * (GD / 4); idx += SM_THREADS) {   // final Z_l, saved for backward
+                const int i = idx / (GD / 4), c4 = (idx - i * (GD / 4)) * 4;
+                *reinterpret_cast<float4*>(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4) =
+                    *reinterpret_cast<const float4*>(Zs + i * LDZ + c4);
+            }
+        }
+        // out = (E + A Z_l) / r ; g_l = relu(out) ; F = keep * g_l + x
+        for (int u = warp; u < MT * NG; u += SM_WARPS) {
+            const int mt = u / NG, ng = u - mt * NG;
+            float c[4][4];
+            zero_frag<4>(c);
+            const float* aa = As + (16 * mt) * LDA;
+            const float* zb = Zs + 32 * ng;
+            warp_gemm<4>(c, NP / 8, [&](int m, int k) { return aa[m * LDA + k]; },
+                         [&](int k, int nn) { return zb[k * LDZ + nn]; });
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = 16 * mt + g + 8 * half;
+                if (i >= n) continue;
+                const float r = rs[i];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int col = 32 * ng + 8 * nt + 2 * t;
+                    const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + col;
+                    const float2 e2 = ld2g(E + off);
+                    float2 o;
+                    o.x = (e2.x + c[nt][2 * half]) / r;
+                    o.y = (e2.y + c[nt][2 * half + 1]) / r;
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                    *reinterpret_cast<float2*>(G + off) = o;
+                    if (l < layers - 1) *reinterpret_cast<float2*>(Gs + i * LDG + kin + col) = o;
+                    float2 f = o;
+                    if (keep != nullptr) { const float2 k2 = ld2g(keep + off); f.x *= k2.x; f.y *= k2.y; }
+                    if (resid) {
+                        const float2 x2 = ld2g(x + static_cast<size_t>(node0 + i) * S + l * GD + col);
+                        f.x += x2.x; f.y += x2.y;
+                    }
+                    *reinterpret_cast<float2*>(F + off) = f;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int GD>
+__global__ void __launch_bounds__(SM_THREADS)
+stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                     const float* __restrict__ A, const float* __restrict__ Z, const float* __restrict__ G,
+                     const float* __restrict__ Winner, const float* __restrict__ keep,
+                     const float* __restrict__ dF, float* __restrict__ dZ, float* __restrict__ dE,
+                     float* __restrict__ dA, int layers, int heads, int flags, long long total_pairs) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    if (n == 0) return;
+    const int S = layers * GD, HD = heads * S, KI = (layers - 1) * GD;
+    const int NP = (n + 15) & ~15;
+    const int LDA = NP + 4;
+    constexpr int LDN = GD + 12, NG = GD / 32, CG = GD / 4, RPP = SM_THREADS / CG;
+
+    float* Ats = smem;                 // [NP][LDA]  A transposed: Ats[j][i] = A[i][j]
+    float* dNs = Ats + NP * LDA;       // [NP][LDN]  dN_l = dOut_l / r
+    float* Ts = dNs + NP * LDN;        // [NP][LDN]  Z_l, later dZ_l
+    float* Wl = Ts + NP * LDN;         // [KI][LDN]  rows [0, l*GD) of Winner[h][l]
+    float* rs = Wl + KI * LDN;         // [NP]
+    float* drs = rs + NP;              // [NP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const float* Ab = A + abase;
+    float* dAb = dA + abase;
+    const bool relu = flags & GCGCN_STACK_RELU;
+
+    for (int idx = tid; idx < NP * NP; idx += SM_THREADS) {
+        const int i = idx / NP, j = idx - i * NP;
+        Ats[j * LDA + i] = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
+    }
+    for (int i = warp; i < NP; i += SM_WARPS) {
+        float s = 0.f;
+        if (i < n)
+            for (int j = lane; j < n; j += WARP) s += Ab[static_cast<size_t>(i) * n + j];
+        s = warp_sum(s);
+        if (lane == 0) { rs[i] = s + (s == 0.f ? 1.f : 0.f); drs[i] = 0.f; }
+    }
+    __syncthreads();
+
+    const int MT = NP / 16;
+    const int cg = tid % CG, rg = tid / CG, c0 = cg * 4;
+    for (int l = layers - 1; l >= 0; --l) {
+        const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+        if (l > 0) {
+            const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
+            for (int idx = tid; idx < l * GD * CG; idx += SM_THREADS) {
+                const int k = idx / CG, c4 = (idx - k * CG) * 4;
+                *reinterpret_cast<float4*>(Wl + k * LDN + c4) = ld4g(wsrc + static_cast<size_t>(k) * GD + c4);
+            }
+        }
+        // (a) row-local: dG_l -> dOut -> dN_l (shared), dE_l (global), dr (shared)
+        for (int i = rg; i < NP; i += RPP) {
+            float4 dn = make_float4(0.f, 0.f, 0.f, 0.f), zl = dn;
+            float drp = 0.f;
+            if (i < n) {
+                const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + c0;
+                float4 dg = ld4g(dF + off);
+                if (keep != nullptr) {
+                    const float4 k4 = ld4g(keep + off);
+                    dg.x *= k4.x; dg.y *= k4.y; dg.z *= k4.z; dg.w *= k4.w;
+                }
+                if (l < layers - 1) {
+                    const float4 s4 = ld4g(dZ + off);      // dense-connect gradient parked in slab l
+                    dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
+                }
+                const float4 g4 = ld4g(G + off);
+                if (relu) {
+                    dg.x = g4.x > 0.f ? dg.x : 0.f; dg.y = g4.y > 0.f ? dg.y : 0.f;
+                    dg.z = g4.z > 0.f ? dg.z : 0.f; dg.w = g4.w > 0.f ? dg.w : 0.f;
+                }
+                const float r = rs[i];
+                dn.x = dg.x / r; dn.y = dg.y / r; dn.z = dg.z / r; dn.w = dg.w / r;
+                *reinterpret_cast<float4*>(dE + off) = dn;
+                drp = -(dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
+                zl = ld4g(Z + off);
+            }
+            *reinterpret_cast<float4*>(dNs + i * LDN + c0) = dn;
+            *reinterpret_cast<float4*>(Ts + i * LDN + c0) = zl;
+#pragma unroll
+            for (int o = CG / 2; o > 0; o >>= 1) drp += __shfl_xor_sync(0xffffffffu, drp, o);
+            if (cg == 0 && i < n) drs[i] += drp;
+        }
+        __syncthreads();
+        // (c) dA += dN_l Z_l^T  (+ dr on the last processed sub-layer)
+        for (int u = warp; u < MT * MT; u += SM_WARPS) {
+            const int mt = u / MT, jt = u - mt * MT;
+            float c[2][4];
+            zero_frag<2>(c);
+            const float* da = dNs + (16 * mt) * LDN;
+            const float* zb = Ts + (16 * jt) * LDN;
+            warp_gemm<2>(c, GD / 8, [&](int m, int k) { return da[m * LDN + k]; },
+                         [&](int k, int nn) { return zb[nn * LDN + k]; });
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = 16 * mt + g + 8 * half;
+                if (i >= n) continue;
+                const float dr = (l == 0) ? drs[i] : 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 16 * jt + 8 * nt + 2 * t + e;
+                        if (j >= n) continue;
+                        float* p = dAb + static_cast<size_t>(i) * n + j;
+                        float val = c[nt][2 * half + e] + dr;
+                        if (l != layers - 1) val += *p;
+                        *p = val;
+                    }
+            }
+        }
+        __syncthreads();
+        // (b) dZ_l = A^T dN_l  -> Ts (for the dense-connect push-down) and global
+        for (int u = warp; u < MT * NG; u += SM_WARPS) {
+            const int jt = u / NG, ng = u - jt * NG;
+            float c[4][4];
+            zero_frag<4>(c);
+            const float* at = Ats + (16 * jt) * LDA;
+            const float* db = dNs + 32 * ng;
+            warp_gemm<4>(c, NP / 8, [&](int m, int k) { return at[m * LDA + k]; },
+                         [&](int k, int nn) { return db[k * LDN + nn]; });
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int j = 16 * jt + g + 8 * half;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int col = 32 * ng + 8 * nt + 2 * t;
+                    const float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+                    *reinterpret_cast<float2*>(Ts + j * LDN + col) = v;
+                    if (j < n)
+                        *reinterpret_cast<float2*>(dZ + static_cast<size_t>(node0 + j) * HD + colbase + col) = v;
+                }
+            }
+        }
+        __syncthreads();
+        // push dZ_l through the dense connection: dG_m[j][c'] += sum_c dZ_l[j][c] * Wn_l[128 + m*GD + c'][c]
+        for (int u = warp; u < l * MT * NG; u += SM_WARPS) {
+            const int m = u / (MT * NG), rem = u - m * (MT * NG);
+            const int jt = rem / NG, ng = rem - jt * NG;
+            float c[4][4];
+            zero_frag<4>(c);
+            const float* ta = Ts + (16 * jt) * LDN;
+            const float* wb = Wl + (m * GD + 32 * ng) * LDN;
+            warp_gemm<4>(c, GD / 8, [&](int mm, int k) { return ta[mm * LDN + k]; },
+                         [&](int k, int nn) { return wb[nn * LDN + k]; });
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int j = 16 * jt + g + 8 * half;
+                if (j >= n) continue;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int col = 32 * ng + 8 * nt + 2 * t;
+                    float* p = dZ + static_cast<size_t>(node0 + j) * HD + static_cast<size_t>(h) * S + m * GD + col;
+                    float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+                    if (l != layers - 1) {
+                        const float2 cur = *reinterpret_cast<const float2*>(p);
+                        v.x += cur.x; v.y += cur.y;
+                    }
+                    *reinterpret_cast<float2*>(p) = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static size_t fwd_mma_smem(int n, int layers, int gd) {
+    const int np = (n + 15) & ~15, ki = (layers - 1) * gd;
+    return (static_cast<size_t>(np) * (np + 4) + static_cast<size_t>(np) * (gd + 8) +
+            static_cast<size_t>(np) * (ki + 4) + static_cast<size_t>(ki) * (gd + 8) + np) * sizeof(float);
+}
+static size_t bwd_mma_smem(int n, int layers, int gd) {
+    const int np = (n + 15) & ~15, ki = (layers - 1) * gd;
+    return (static_cast<size_t>(np) * (np + 4) + 2 * static_cast<size_t>(np) * (gd + 12) +
+            static_cast<size_t>(ki) * (gd + 12) + 2 * np) * sizeof(float);
+}
+
+bool stack_mma_usable(const gcgcn_batch* bt, int layers, int slab) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("GCGCN_STACK");
+        enabled = (e != nullptr && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;    // GCGCN_STACK=simt disables
+    }
+    if (!enabled || layers < 1 || slab % layers != 0) return false;
+    const int gd = slab / layers;
+    return bt->max_nodes <= 64 && (gd == 32 || gd == 64);
+}
+
+template <typename K>
+static int set_dyn_smem(K kernel, size_t bytes, const char* name) {
+    if (bytes > 48 * 1024)
+        return cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(bytes)), name);
+    return GCGCN_OK;
+}
+
+int launch_stack_fwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                         float* Z, const float* E, const float* Winner, const float* keep, const float* x,
+                         float* G, float* F, cudaStream_t st) {
+    const int gd = slab / layers;
+    const size_t smem = fwd_mma_smem(bt->max_nodes, layers, gd);
+    dim3 grid(bt->num_docs, heads);
+    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
+    if (gd == 64) {
+        GCGCN_TRY(set_dyn_smem(stack_fwd_mma_kernel<64>, smem, "stack_fwd_mma"));
+        stack_fwd_mma_kernel<64><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F,
+                                                                 layers, heads, flags, bt->total_pairs);
+    } else {
+        GCGCN_TRY(set_dyn_smem(stack_fwd_mma_kernel<32>, smem, "stack_fwd_mma"));
+        stack_fwd_mma_kernel<32><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F,
+                                                                 layers, heads, flags, bt->total_pairs);
+    }
+    GCGCN_CHECK_LAUNCH("gcn_stack_fwd_mma");
+    return GCGCN_OK;
+}
+
+int launch_stack_bwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                         const float* Z, const float* G, const float* Winner, const float* keep, const float* dF,
+                         float* dZ, float* dE, float* dA, cudaStream_t st) {
+    const int gd = slab / layers;
+    const size_t smem = bwd_mma_smem(bt->max_nodes, layers, gd);
+    dim3 grid(bt->num_docs, heads);
+    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
+    if (gd == 64) {
+        GCGCN_TRY(set_dyn_smem(stack_bwd_mma_kernel<64>, smem, "stack_bwd_mma"));
+        stack_bwd_mma_kernel<64><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, G, Winner, keep, dF, dZ, dE,
+                                                                 dA, layers, heads, flags, bt->total_pairs);
+    } else {
+        GCGCN_TRY(set_dyn_smem(stack_bwd_mma_kernel<32>, smem, "stack_bwd_mma"));
+        stack_bwd_mma_kernel<32><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, G, Winner, keep, dF, dZ, dE,
+                                                                 dA, layers, heads, flags, bt->total_pairs);
+    }
+    GCGCN_CHECK_LAUNCH("gcn_stack_bwd_mma");
+    return GCGCN_OK;
+}
+
+}  // namespace gcgcn
