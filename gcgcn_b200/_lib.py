@@ -37,6 +37,7 @@ class Batch(ctypes.Structure):
         ("num_docs", c_int32), ("total_nodes", c_int32), ("total_pairs", c_int64),
         ("max_nodes", c_int32), ("reserved", c_int32),
         ("node_ptr", c_void_p), ("pair_ptr", c_void_p), ("row_doc", c_void_p),
+        ("doc_order", c_void_p), ("class_end", c_int32 * 4),
     ]
 
 

@@ -47,10 +47,16 @@ class RaggedBatch:
         self.node_ptr = torch.from_numpy(self.node_ptr_host).to(self.device)
         self.pair_ptr = torch.from_numpy(self.pair_ptr_host).to(self.device)
         self.row_doc = torch.from_numpy(self.row_doc_host).to(self.device)
+        # scheduling hint: documents by descending size + size-class boundaries (n > 48, 32, 16, 0)
+        self.doc_order_host = np.argsort(-ns, kind="stable").astype(np.int32)
+        self.class_end_host = [int((ns > t).sum()) for t in (48, 32, 16, 0)]
+        self.doc_order = torch.from_numpy(self.doc_order_host).to(self.device)
         self.c_struct = _lib.Batch(
             self.num_docs, self.total_nodes, self.total_pairs, self.max_nodes, 0,
             self.node_ptr.data_ptr(), self.pair_ptr.data_ptr(),
-            self.row_doc.data_ptr() if self.total_nodes else None)
+            self.row_doc.data_ptr() if self.total_nodes else None,
+            self.doc_order.data_ptr() if self.num_docs else None,
+            (ctypes.c_int32 * 4)(*self.class_end_host))
 
     @property
     def ref(self):

@@ -76,22 +76,25 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
                      const float* __restrict__ A, float* __restrict__ Z, const float* __restrict__ E,
                      const float* __restrict__ Winner, const float* __restrict__ keep,
                      const float* __restrict__ x, float* __restrict__ G, float* __restrict__ F, int layers,
-                     int heads, int flags, long long total_pairs) {
+                     int heads, int flags, long long total_pairs, const int* __restrict__ doc_order, int first) {
     extern __shared__ __align__(16) float smem[];
-    const int b = blockIdx.x, h = blockIdx.y;
+    const int b = doc_order != nullptr ? doc_order[first + blockIdx.x] : blockIdx.x;
+    const int h = blockIdx.y;
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
     const int S = layers * GD, HD = heads * S, KI = (layers - 1) * GD;
     const int NP = (n + 15) & ~15;
     const int LDA = NP + 4, LDG = KI + 4;
-    constexpr int LDZ = GD + 8, LDW = GD + 8, NG = GD / 32;
+    constexpr int LDZ = GD + 8, NG = GD / 32;
 
     float* As = smem;                 // [NP][LDA]  attention map, zero padded
     float* Zs = As + NP * LDA;        // [NP][LDZ]  Z_l
     float* Gs = Zs + NP * LDZ;        // [NP][LDG]  g_0 .. g_{L-2}
-    float* Ws = Gs + NP * LDG;        // [KI][LDW]  dense-connect weights of the current sub-layer
-    float* rs = Ws + KI * LDW;        // [NP]
+    float* rs = Gs + NP * LDG;        // [NP]
+    // The dense-connect weights (16 KB per head) are read as MMA fragments straight from global memory:
+    // co-resident CTAs work on the same head, so they stay L1-resident, and leaving them out of shared
+    // memory raises occupancy (the kernel is latency-, not bandwidth-bound).
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -115,13 +118,7 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
     for (int l = 0; l < layers; ++l) {
         const int kin = l * GD;
         const size_t colbase = static_cast<size_t>(h) * S + l * GD;
-        if (l > 0) {
-            const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
-            for (int idx = tid; idx < kin * (GD / 4); idx += SM_THREADS) {
-                const int k = idx / (GD / 4), c4 = (idx - k * (GD / 4)) * 4;
-                *reinterpret_cast<float4*>(Ws + k * LDW + c4) = ld4g(wsrc + static_cast<size_t>(k) * GD + c4);
-            }
-        }
+        const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
         for (int idx = tid; idx < NP * (GD / 4); idx += SM_THREADS) {
             const int i = idx / (GD / 4), c4 = (idx - i * (GD / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -142,9 +139,9 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
                     c[nt][0] = lo.x; c[nt][1] = lo.y; c[nt][2] = hi.x; c[nt][3] = hi.y;
                 }
                 const float* ga = Gs + (16 * mt) * LDG;
-                const float* wb = Ws + 32 * ng;
+                const float* wb = wsrc + 32 * ng;
                 warp_gemm<4>(c, kin / 8, [&](int m, int k) { return ga[m * LDG + k]; },
-                             [&](int k, int nn) { return wb[k * LDW + nn]; });
+                             [&](int k, int nn) { return __ldg(wb + k * GD + nn); });
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     *reinterpret_cast<float2*>(zc + g * LDZ + 8 * nt + 2 * t) = make_float2(c[nt][0], c[nt][1]);
@@ -204,13 +201,15 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
                      const float* __restrict__ A, const float* __restrict__ Z, const float* __restrict__ G,
                      const float* __restrict__ Winner, const float* __restrict__ keep,
                      const float* __restrict__ dF, float* __restrict__ dZ, float* __restrict__ dE,
-                     float* __restrict__ dA, int layers, int heads, int flags, long long total_pairs) {
+                     float* __restrict__ dA, int layers, int heads, int flags, long long total_pairs,
+                     const int* __restrict__ doc_order, int first) {
     extern __shared__ __align__(16) float smem[];
-    const int b = blockIdx.x, h = blockIdx.y;
+    const int b = doc_order != nullptr ? doc_order[first + blockIdx.x] : blockIdx.x;
+    const int h = blockIdx.y;
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
-    const int S = layers * GD, HD = heads * S, KI = (layers - 1) * GD;
+    const int S = layers * GD, HD = heads * S;
     const int NP = (n + 15) & ~15;
     const int LDA = NP + 4;
     constexpr int LDN = GD + 12, NG = GD / 32, CG = GD / 4, RPP = SM_THREADS / CG;
@@ -218,8 +217,7 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
     float* Ats = smem;                 // [NP][LDA]  A transposed: Ats[j][i] = A[i][j]
     float* dNs = Ats + NP * LDA;       // [NP][LDN]  dN_l = dOut_l / r
     float* Ts = dNs + NP * LDN;        // [NP][LDN]  Z_l, later dZ_l
-    float* Wl = Ts + NP * LDN;         // [KI][LDN]  rows [0, l*GD) of Winner[h][l]
-    float* rs = Wl + KI * LDN;         // [NP]
+    float* rs = Ts + NP * LDN;         // [NP]   (dense-connect weights: fragments from global, see fwd)
     float* drs = rs + NP;              // [NP]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -246,13 +244,7 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
     const int cg = tid % CG, rg = tid / CG, c0 = cg * 4;
     for (int l = layers - 1; l >= 0; --l) {
         const size_t colbase = static_cast<size_t>(h) * S + l * GD;
-        if (l > 0) {
-            const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
-            for (int idx = tid; idx < l * GD * CG; idx += SM_THREADS) {
-                const int k = idx / CG, c4 = (idx - k * CG) * 4;
-                *reinterpret_cast<float4*>(Wl + k * LDN + c4) = ld4g(wsrc + static_cast<size_t>(k) * GD + c4);
-            }
-        }
+        const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
         // (a) row-local: dG_l -> dOut -> dN_l (shared), dE_l (global), dr (shared)
         for (int i = rg; i < NP; i += RPP) {
             float4 dn = make_float4(0.f, 0.f, 0.f, 0.f), zl = dn;
@@ -344,9 +336,9 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
             float c[4][4];
             zero_frag<4>(c);
             const float* ta = Ts + (16 * jt) * LDN;
-            const float* wb = Wl + (m * GD + 32 * ng) * LDN;
+            const float* wb = wsrc + static_cast<size_t>(m * GD + 32 * ng) * GD;
             warp_gemm<4>(c, GD / 8, [&](int mm, int k) { return ta[mm * LDN + k]; },
-                         [&](int k, int nn) { return wb[nn * LDN + k]; });
+                         [&](int k, int nn) { return __ldg(wb + nn * GD + k); });
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int j = 16 * jt + g + 8 * half;
@@ -372,12 +364,12 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
 static size_t fwd_mma_smem(int n, int layers, int gd) {
     const int np = (n + 15) & ~15, ki = (layers - 1) * gd;
     return (static_cast<size_t>(np) * (np + 4) + static_cast<size_t>(np) * (gd + 8) +
-            static_cast<size_t>(np) * (ki + 4) + static_cast<size_t>(ki) * (gd + 8) + np) * sizeof(float);
+            static_cast<size_t>(np) * (ki + 4) + np) * sizeof(float);
 }
 static size_t bwd_mma_smem(int n, int layers, int gd) {
-    const int np = (n + 15) & ~15, ki = (layers - 1) * gd;
-    return (static_cast<size_t>(np) * (np + 4) + 2 * static_cast<size_t>(np) * (gd + 12) +
-            static_cast<size_t>(ki) * (gd + 12) + 2 * np) * sizeof(float);
+    const int np = (n + 15) & ~15;
+    (void)layers;
+    return (static_cast<size_t>(np) * (np + 4) + 2 * static_cast<size_t>(np) * (gd + 12) + 2 * np) * sizeof(float);
 }
 
 bool stack_mma_usable(const gcgcn_batch* bt, int layers, int slab) {
@@ -399,44 +391,61 @@ static int set_dyn_smem(K kernel, size_t bytes, const char* name) {
     return GCGCN_OK;
 }
 
+// One launch per size class (padded n = 64, 48, 32, 16) when the batch carries the doc_order hint, so
+// that small documents do not reserve the shared memory of the largest one.
+template <class LaunchFn>
+static int for_each_class(const gcgcn_batch* bt, LaunchFn fn) {
+    if (bt->doc_order == nullptr) return fn(bt->num_docs, 0, bt->max_nodes, static_cast<const int*>(nullptr));
+    static const int cap[4] = {64, 48, 32, 16};
+    int first = 0;
+    for (int c = 0; c < 4; ++c) {
+        const int count = bt->class_end[c] - first;
+        if (count > 0) GCGCN_TRY(fn(count, first, cap[c] < bt->max_nodes ? cap[c] : bt->max_nodes, bt->doc_order));
+        first = bt->class_end[c] > first ? bt->class_end[c] : first;
+    }
+    return GCGCN_OK;
+}
+
 int launch_stack_fwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
                          float* Z, const float* E, const float* Winner, const float* keep, const float* x,
                          float* G, float* F, cudaStream_t st) {
     const int gd = slab / layers;
-    const size_t smem = fwd_mma_smem(bt->max_nodes, layers, gd);
-    dim3 grid(bt->num_docs, heads);
     const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
-    if (gd == 64) {
-        GCGCN_TRY(set_dyn_smem(stack_fwd_mma_kernel<64>, smem, "stack_fwd_mma"));
-        stack_fwd_mma_kernel<64><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F,
-                                                                 layers, heads, flags, bt->total_pairs);
-    } else {
-        GCGCN_TRY(set_dyn_smem(stack_fwd_mma_kernel<32>, smem, "stack_fwd_mma"));
-        stack_fwd_mma_kernel<32><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F,
-                                                                 layers, heads, flags, bt->total_pairs);
-    }
-    GCGCN_CHECK_LAUNCH("gcn_stack_fwd_mma");
-    return GCGCN_OK;
+    GCGCN_TRY(set_dyn_smem(stack_fwd_mma_kernel<64>, fwd_mma_smem(64, layers, 64), "stack_fwd_mma"));
+    GCGCN_TRY(set_dyn_smem(stack_fwd_mma_kernel<32>, fwd_mma_smem(64, layers, 32), "stack_fwd_mma"));
+    return for_each_class(bt, [&](int count, int first, int nmax, const int* order) -> int {
+        const size_t smem = fwd_mma_smem(nmax, layers, gd);
+        dim3 grid(count, heads);
+        if (gd == 64)
+            stack_fwd_mma_kernel<64><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F,
+                                                                     layers, heads, flags, bt->total_pairs, order, first);
+        else
+            stack_fwd_mma_kernel<32><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F,
+                                                                     layers, heads, flags, bt->total_pairs, order, first);
+        GCGCN_CHECK_LAUNCH("gcn_stack_fwd_mma");
+        return GCGCN_OK;
+    });
 }
 
 int launch_stack_bwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
                          const float* Z, const float* G, const float* Winner, const float* keep, const float* dF,
                          float* dZ, float* dE, float* dA, cudaStream_t st) {
     const int gd = slab / layers;
-    const size_t smem = bwd_mma_smem(bt->max_nodes, layers, gd);
-    dim3 grid(bt->num_docs, heads);
     const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
-    if (gd == 64) {
-        GCGCN_TRY(set_dyn_smem(stack_bwd_mma_kernel<64>, smem, "stack_bwd_mma"));
-        stack_bwd_mma_kernel<64><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, G, Winner, keep, dF, dZ, dE,
-                                                                 dA, layers, heads, flags, bt->total_pairs);
-    } else {
-        GCGCN_TRY(set_dyn_smem(stack_bwd_mma_kernel<32>, smem, "stack_bwd_mma"));
-        stack_bwd_mma_kernel<32><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, G, Winner, keep, dF, dZ, dE,
-                                                                 dA, layers, heads, flags, bt->total_pairs);
-    }
-    GCGCN_CHECK_LAUNCH("gcn_stack_bwd_mma");
-    return GCGCN_OK;
+    GCGCN_TRY(set_dyn_smem(stack_bwd_mma_kernel<64>, bwd_mma_smem(64, layers, 64), "stack_bwd_mma"));
+    GCGCN_TRY(set_dyn_smem(stack_bwd_mma_kernel<32>, bwd_mma_smem(64, layers, 32), "stack_bwd_mma"));
+    return for_each_class(bt, [&](int count, int first, int nmax, const int* order) -> int {
+        const size_t smem = bwd_mma_smem(nmax, layers, gd);
+        dim3 grid(count, heads);
+        if (gd == 64)
+            stack_bwd_mma_kernel<64><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, G, Winner, keep, dF, dZ, dE,
+                                                                     dA, layers, heads, flags, bt->total_pairs, order, first);
+        else
+            stack_bwd_mma_kernel<32><<<grid, SM_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, G, Winner, keep, dF, dZ, dE,
+                                                                     dA, layers, heads, flags, bt->total_pairs, order, first);
+        GCGCN_CHECK_LAUNCH("gcn_stack_bwd_mma");
+        return GCGCN_OK;
+    });
 }
 
 }  // namespace gcgcn

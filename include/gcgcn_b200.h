@@ -60,6 +60,11 @@ typedef struct gcgcn_batch {
     const int32_t* node_ptr; /* [B+1] device                                             */
     const int64_t* pair_ptr; /* [B+1] device                                             */
     const int32_t* row_doc;  /* [total_nodes] device: document of each node row          */
+    /* optional scheduling hint (may be NULL / zeros): documents sorted by n descending, and how
+     * many of them have n > 48, n > 32, n > 16 and n > 0.  Lets the per-document kernels launch one
+     * grid per size class with right-sized shared memory instead of sizing every CTA for max_nodes. */
+    const int32_t* doc_order; /* [B] device                                              */
+    int32_t class_end[4];     /* cumulative counts in doc_order: n>48, n>32, n>16, n>0   */
 } gcgcn_batch;
 
 /* ---- library ---------------------------------------------------------------------------- */
