@@ -324,7 +324,10 @@ def run_gpu_arm(args):
     total_k = sum(v[1] for v in kern.values()) or 1.0
     ranked = sorted(((k, v) for k, v in kern.items() if not k.startswith("(")), key=lambda kv: -kv[1][1])
     breakdown = [{"kernel": k, "launches": v[0], "ms_per_step": v[1] / args.steps, "share": v[1] / total_k}
-                 for k, v in ranked[:12]]
+                 for k, v in ranked[:30]]
+    gaps = kern.get("(between calls)", (0, 0.0))
+    breakdown.append({"kernel": "(time between C-ABI calls: torch packing/autograd glue)", "launches": gaps[0],
+                      "ms_per_step": gaps[1] / args.steps, "share": gaps[1] / total_k})
     if ranked:
         name, (cnt, tot_ms) = ranked[0]
         per_launch_s = tot_ms * 1e-3 / cnt
