@@ -11,13 +11,13 @@
 // three tcgen05.mma.kind::tf32 instructions per K-step into one fp32 accumulator in TMEM.
 //
 // Structure (one CTA per SM, persistent over 128x128 output tiles):
-//   warps 0-7  producers: global -> registers -> {hi,lo} split -> shared memory in the UMMA
+//   warps 0-15 producers (4 groups of 4 warps, one K block each in flight): global -> registers -> {hi,lo} split -> shared memory in the UMMA
 //              canonical K-major no-swizzle layout ([K/4][128 rows][16 B]); operands stored
 //              "transposed" in HBM (MN-contiguous) are transposed in registers on the way, so the
 //              tensor core always sees K-major tiles.  TMA cannot be used for this stage because the
 //              split is arithmetic on every element.
-//   warp 8     allocates TMEM, then one elected lane issues the MMAs and commits them to mbarriers
-//   warps 9-12 epilogue: tcgen05.ld the 128x128 fp32 accumulator, apply alpha/beta/bias, store
+//   warp 16    allocates TMEM, then one elected lane issues the MMAs and commits them to mbarriers
+//   warps 17-20 epilogue: tcgen05.ld the 128x128 fp32 accumulator, apply alpha/beta/bias, store
 // Pipelines: 3 shared-memory stages (full/empty mbarriers), 2 TMEM accumulators (tile i+1 is
 // multiplied while tile i is stored).  K may be split across CTAs (weight gradients reduce over all
 // node rows); partials go to the workspace and are reduced by splitk_reduce (deterministic).
@@ -26,13 +26,20 @@
 namespace gcgcn {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
-constexpr int TC_PART_BYTES = 128 * TC_BK * 4;              // one 128 x 32 fp32 operand part: 16 KB
+// One operand part = 8 K-chunk planes of [128 rows][16 B]; each plane is padded by 16 B so that a quarter
+// warp storing the 8 chunks of one row (lanes = chunks) hits 8 different 16-byte bank groups.
+constexpr int TC_PLANE_BYTES = 128 * 16 + 16;               // UMMA leading (K) byte offset (odd multiple of 16 B)
+constexpr int TC_PART_BYTES = (TC_BK / 4) * TC_PLANE_BYTES; // one 128 x 32 fp32 operand part
 constexpr int TC_STAGE_BYTES = 4 * TC_PART_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_PRODUCER_WARPS = 8;                        // two groups of 4
-constexpr int TC_MMA_WARP = 8;
-constexpr int TC_THREADS = 13 * 32;                         // 8 producer + 1 MMA + 4 epilogue warps
+constexpr int TC_EPI_LD = 36;                               // epilogue transpose buffer: [32][36] floats per warp (144 B rows)
+constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;
+// GROUPS producer groups of 4 warps (one K block of global loads in flight each), then 1 MMA warp, then 4
+// epilogue warps (warp index 4*GROUPS+1.. so that warp % 4 covers the TMEM lane quarters 1,2,3,0).
+// Three groups for K-contiguous operands; two when both operands are transposed on the way in (the scalar
+// loads of that path need more registers per thread than a 17-warp CTA leaves).
+constexpr int tc_threads(int groups) { return (4 * groups + 5) * 32; }
 constexpr int TC_TMEM_COLS = 256;                           // 2 accumulators x 128 fp32 columns
-constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + TC_EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcArgs {
     int M, N, K, lda, ldb, ldc;
@@ -116,10 +123,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // UMMA shared-memory descriptor, K-major, no swizzle: 8-row x 16-byte core matrices are 128 contiguous
-// bytes; the next core matrix along M/N is 128 B away (SBO), the next along K is 128 rows * 16 B away (LBO).
+// bytes; the next core matrix along M/N is 128 B away (SBO), the next along K is one padded chunk plane
+// (TC_PLANE_BYTES) away (LBO).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = (smem_addr >> 4) & 0x3FFFu;
-    d |= static_cast<uint64_t>((128 * 16) >> 4) << 16;   // leading (K) byte offset
+    d |= static_cast<uint64_t>(TC_PLANE_BYTES >> 4) << 16;   // leading (K) byte offset
     d |= static_cast<uint64_t>(128 >> 4) << 32;          // stride (M/N) byte offset
     d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (Blackwell)
     return d;
@@ -134,24 +142,24 @@ __device__ __forceinline__ void split_store(float* hi_base, float* lo_base, int 
     h.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u);
     h.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u);
     l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-    const int off = (chunk * 128 + row) * 4;
+    const int off = chunk * (TC_PLANE_BYTES / 4) + row * 4;
     *reinterpret_cast<float4*>(hi_base + off) = h;
     *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
 // One 128(rows) x 32(k) operand tile = 1024 float4; each of the 128 threads of a producer group moves 8.
 // Thread -> (row, 16-byte K chunk) assignment of its i-th float4:
-//   K-contiguous source: a warp instruction covers 8 consecutive rows x 4 consecutive chunks, so global
-//     loads touch 8 rows x 64 contiguous bytes and the shared-memory stores (rows 16 B apart, chunks
-//     2 KB apart) are bank-conflict free;
+//   K-contiguous source: a warp instruction covers 4 consecutive rows x all 8 chunks, so global loads
+//     are 4 fully used 128-byte lines and the shared-memory stores (rows 16 B apart, chunk planes
+//     2 KB + 16 B apart) spread over all 32 banks (4 wavefronts for 512 B, the minimum);
 //   MN-contiguous source (transposed in registers): lanes walk rows, so the 4-byte global loads coalesce
 //     into 128-byte lines and each store instruction writes 512 contiguous bytes.
 template <bool KCONTIG>
 __device__ __forceinline__ void tile_coord(int tid, int i, int& row, int& chunk) {
     if (KCONTIG) {
         const int w = tid >> 5, l = tid & 31;
-        row = 32 * w + 8 * (i >> 1) + (l & 7);
-        chunk = 4 * (i & 1) + (l >> 3);
+        row = 32 * w + 4 * i + (l >> 3);
+        chunk = l & 7;
     } else {
         row = tid;
         chunk = i;
@@ -198,11 +206,14 @@ __device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, con
     }
 }
 
-template <bool A_KCONTIG, bool B_KCONTIG>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcArgs args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(TC_STAGES) * TC_STAGE_BYTES);
+template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS>
+__global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const TcArgs args) {
+    constexpr int TC_PRODUCER_WARPS = 4 * GROUPS, TC_MMA_WARP = 4 * GROUPS, TC_GROUPS = GROUPS;
+    // (no integer round trip on this pointer: the compiler must keep seeing shared memory, or every
+    //  operand store degrades to a generic ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* epi_stage = reinterpret_cast<float*>(smem + size_t(TC_STAGES) * TC_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(TC_STAGES) * TC_STAGE_BYTES + TC_EPI_BYTES);
     // bars: full[3], empty[3], tmem_full[2], tmem_empty[2], then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
     const uint32_t bar0 = smem_u32(bars);
@@ -234,7 +245,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcArgs arg
     const int total_tiles = tiles_mn * args.k_splits;
 
     if (warp < TC_PRODUCER_WARPS) {
-        // ===== producers: two groups of 4 warps take alternate K blocks, so two blocks' loads are in flight
+        // ===== producers: TC_GROUPS groups of 4 warps take K blocks round-robin; a group issues its loads
+        // before it waits for its shared-memory stage, so TC_GROUPS blocks of global loads are in flight
         const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
         const bool b_vec = (args.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.B) & 15) == 0);
         const int group = warp >> 2, tid = threadIdx.x & 127;
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcArgs arg
             const int kbeg = ks * args.k_per_split;
             const int kend = min(args.K, kbeg + args.k_per_split);
             for (int k0 = kbeg; k0 < kend; k0 += TC_BK, ++j) {
-                if ((j & 1) != group) continue;
+                if ((j % TC_GROUPS) != group) continue;
                 const int stage = j % TC_STAGES;
                 const uint32_t phase = (j / TC_STAGES) & 1;
                 float4 va[8], vb[8];
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcArgs arg
                     const uint32_t b_hi = sa + 2 * TC_PART_BYTES, b_lo = sa + 3 * TC_PART_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                        const uint32_t koff = kk * 2 * (128 * 16);   // two 16-byte K chunks per MMA
+                        const uint32_t koff = kk * 2 * TC_PLANE_BYTES;   // two 16-byte K chunks per MMA
                         umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), TC_IDESC, accumulate);
                         umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), TC_IDESC, 1u);
                         umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), TC_IDESC, 1u);
@@ -298,74 +310,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcArgs arg
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 9..12 own TMEM lane quarters (warp % 4) =====
+        // ===== epilogue: warps 17..20 own TMEM lane quarters (warp % 4) =====
+        // tcgen05.ld gives lane = row, register = column.  A 32x32 block is transposed through a padded
+        // per-warp shared buffer so that every global store instruction writes one contiguous 128-byte
+        // row segment (lane = column) instead of 32 scattered 16-byte pieces.
         const int quarter = warp & 3;
+        float* stg = epi_stage + quarter * 32 * TC_EPI_LD;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool c_vec = (args.partial != nullptr ? (args.N % 4 == 0)
-                                                    : (args.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(args.C) & 15) == 0));
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int ks = t / tiles_mn, rem = t - ks * tiles_mn;
             const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
-            const int kbeg = ks * args.k_per_split;
-            const bool has_k = kbeg < args.K;
+            const bool has_k = ks * args.k_per_split < args.K;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < args.M;
-            float* out_row;
+            const int row_base = m0 + quarter * 32;
+            float* out_base;
             int ldo;
             if (args.partial != nullptr) {
-                out_row = args.partial + (static_cast<size_t>(ks) * args.M + (row_ok ? row : 0)) * args.N;
+                out_base = args.partial + static_cast<size_t>(ks) * args.M * args.N;
                 ldo = args.N;
             } else {
-                out_row = args.C + static_cast<size_t>(row_ok ? row : 0) * args.ldc;
+                out_base = args.C;
                 ldo = args.ldc;
             }
-            (void)ldo;
+            const int rows_valid = min(32, args.M - row_base);      // may be <= 0 for padding tiles
+            const bool final_out = args.partial == nullptr;
+            const bool vec = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_base) & 15) == 0) && (n0 + TC_BN <= args.N);
 #pragma unroll 1
             for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(acc * TC_BN + chunk * 32);
                 tmem_ld32(taddr, v);
-                if (!row_ok) continue;
+                if (chunk == TC_BN / 32 - 1) {
+                    // the accumulator is in registers now: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = n0 + chunk * 32 + j;
-                    if (col >= args.N) break;
-                    float o[4];
+                for (int j = 0; j < 32; j += 4)          // lane = row: 144-byte row pitch -> conflict-free float4 stores
+                    *reinterpret_cast<float4*>(stg + lane * TC_EPI_LD + j) =
+                        has_k ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                            __uint_as_float(v[j + 3]))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                if (vec) {
+                    // lane -> (row = 4*it + lane/8, float4 column = lane%8): 4 rows x 128 contiguous bytes per store
+                    const int c4 = (lane & 7) * 4, col = n0 + chunk * 32 + c4;
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (final_out && args.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(args.bias + col);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = has_k ? __uint_as_float(v[j + q]) : 0.f;
-                    if (args.partial == nullptr) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            o[q] *= args.alpha;
-                            if (args.bias != nullptr && col + q < args.N) o[q] += args.bias[col + q];
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = 4 * it + (lane >> 3);
+                        if (rr < rows_valid) {
+                            float4 val = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_LD + c4);
+                            float4* p = reinterpret_cast<float4*>(out_base + static_cast<size_t>(row_base + rr) * ldo + col);
+                            if (final_out) {
+                                val.x = val.x * args.alpha + bias4.x; val.y = val.y * args.alpha + bias4.y;
+                                val.z = val.z * args.alpha + bias4.z; val.w = val.w * args.alpha + bias4.w;
+                                if (args.beta != 0.f) {
+                                    const float4 c = *p;
+                                    val.x += args.beta * c.x; val.y += args.beta * c.y;
+                                    val.z += args.beta * c.z; val.w += args.beta * c.w;
+                                }
+                            }
+                            *p = val;
                         }
                     }
-                    if (c_vec && col + 4 <= args.N) {
-                        float4* p = reinterpret_cast<float4*>(out_row + col);
-                        if (args.partial == nullptr && args.beta != 0.f) {
-                            const float4 c = *p;
-                            o[0] += args.beta * c.x; o[1] += args.beta * c.y;
-                            o[2] += args.beta * c.z; o[3] += args.beta * c.w;
-                        }
-                        *p = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (col + q >= args.N) break;
-                            float val = o[q];
-                            if (args.partial == nullptr && args.beta != 0.f) val += args.beta * out_row[col + q];
-                            out_row[col + q] = val;
+                } else {
+                    const int col = n0 + chunk * 32 + lane;
+                    if (col < args.N) {
+                        const float bias = (final_out && args.bias != nullptr) ? args.bias[col] : 0.f;
+                        for (int rr = 0; rr < rows_valid; ++rr) {
+                            float val = stg[rr * TC_EPI_LD + lane];
+                            float* p = out_base + static_cast<size_t>(row_base + rr) * ldo + col;
+                            if (final_out) {
+                                val = val * args.alpha + bias;
+                                if (args.beta != 0.f) val += args.beta * (*p);
+                            }
+                            *p = val;
                         }
                     }
                 }
+                __syncwarp();
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -421,21 +451,21 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     // op(A)[m,k]: stored [M][K] (K contiguous) when !ta, [K][M] when ta.
     // op(B)[k,n] as the N x K operand: stored [N][K] (K contiguous) when tb, [K][N] when !tb.
     const bool a_kc = !ta, b_kc = (tb != 0);
-#define GCGCN_TC_LAUNCH(AK, BK)                                                                          \
+#define GCGCN_TC_LAUNCH(AK, BK, G)                                                                       \
     do {                                                                                                 \
         static bool attr_done = false;                                                                   \
         if (!attr_done) {                                                                                \
-            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>,                               \
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, G>,                            \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                                    static_cast<int>(TC_SMEM_BYTES)), "gemm_tc smem"));   \
             attr_done = true;                                                                            \
         }                                                                                                \
-        gemm_tc_kernel<AK, BK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);                              \
+        gemm_tc_kernel<AK, BK, G><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);                        \
     } while (0)
-    if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true);
-    else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false);
-    else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true);
-    else GCGCN_TC_LAUNCH(false, false);
+    if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3);
+    else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3);
+    else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3);
+    else GCGCN_TC_LAUNCH(false, false, 2);
 #undef GCGCN_TC_LAUNCH
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1) GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st));
