@@ -52,7 +52,7 @@ std::atomic<uint64_t> g_launches{0};
 std::atomic<bool> g_timing{false};
 
 namespace {
-struct Mark { const char* name; cudaEvent_t ev; };
+struct Mark { const char* name; cudaEvent_t ev; cudaStream_t st; };
 std::mutex g_tmutex;
 std::vector<Mark> g_marks;
 std::vector<cudaEvent_t> g_event_pool;
@@ -69,7 +69,7 @@ void timing_mark(const char* name, cudaStream_t st) {
     cudaEvent_t e = take_event();
     if (e == nullptr) return;
     cudaEventRecord(e, st);
-    g_marks.push_back({name, e});
+    g_marks.push_back({name, e, st});
 }
 
 char* error_buffer() {
@@ -209,7 +209,7 @@ int gcgcn_timing_begin(void* stream) {
     cudaEvent_t e = take_event();
     if (e == nullptr) return fail(GCGCN_ERR_CUDA, "timing_begin: cannot create an event");
     GCGCN_TRY(cuda_ok(cudaEventRecord(e, static_cast<cudaStream_t>(stream)), "timing_begin"));
-    g_marks.push_back({"(begin)", e});
+    g_marks.push_back({"(begin)", e, static_cast<cudaStream_t>(stream)});
     g_timing.store(true);
     return GCGCN_OK;
 }
@@ -223,13 +223,26 @@ int gcgcn_timing_end(void* stream, char* buf, size_t cap) {
     buf[0] = 0;
     if (g_marks.empty()) return GCGCN_OK;
     GCGCN_TRY(cuda_ok(cudaEventSynchronize(g_marks.back().ev), "timing_end"));
+    GCGCN_TRY(cuda_ok(cudaDeviceSynchronize(), "timing_end"));
     std::map<std::string, std::pair<long, double>> acc;
-    for (size_t i = 1; i < g_marks.size(); ++i) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) { cudaGetLastError(); continue; }
-        auto& slot = acc[g_marks[i].name];
-        slot.first += 1;
-        slot.second += ms;
+    std::map<cudaStream_t, cudaEvent_t> last;          // a kernel's time = gap to the previous mark on ITS stream
+    for (size_t i = 0; i < g_marks.size(); ++i) {
+        auto it = last.find(g_marks[i].st);
+        if (it != last.end()) {
+            float ms = 0.f;
+            // host-side gaps are only meaningful on the stream timing_begin was called on
+            const bool gap_mark = g_marks[i].name[0] == '(';
+            if (gap_mark && g_marks[i].st != g_marks[0].st) {
+                // chain reset only
+            } else if (cudaEventElapsedTime(&ms, it->second, g_marks[i].ev) == cudaSuccess) {
+                auto& slot = acc[g_marks[i].name];
+                slot.first += 1;
+                slot.second += ms;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        last[g_marks[i].st] = g_marks[i].ev;
     }
     size_t off = 0;
     for (auto& kv : acc) {

@@ -226,7 +226,7 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
 int launch_colsum(const float* X, int M, int N, int ldx, float* out, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
     if (N <= 0) return GCGCN_OK;
-    int parts = max(1, min(ceil_div(M, 256), sm_count() * 2));
+    int parts = max(1, min(ceil_div(M, 64), sm_count() * 16));
     const size_t need = static_cast<size_t>(parts) * N * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return fail(GCGCN_ERR_WORKSPACE, "colsum: workspace too small");
     const int rows_per_block = max(1, ceil_div(M, parts));

@@ -305,8 +305,12 @@ class GraphBlocks(nn.Module, _KeepMixin):
     layer_num/head_num: 2/8 for GCGCN_glove (G:250-251), 4/4 for the BERT variant (B:247-248).
     """
 
-    def __init__(self, layer_num=2, head_num=8, alpha=1.0, hidden_size=HIDDEN, graph_hop=2):
+    def __init__(self, layer_num=2, head_num=8, alpha=1.0, hidden_size=HIDDEN, graph_hop=2, overlap=True):
         super().__init__()
+        # overlap: stream the hop-1 edge tensor (mean forward, broadcast-write backward: pure HBM work)
+        # on a side stream while the CAGGC block (tensor-core / latency-bound work) runs on the main one
+        self.overlap = overlap
+        self._side = {}
         if graph_hop != 2:
             raise _lib.GcgcnError("graph_hop = 2 (config/Config.py:71) is the only supported depth")
         self.layerNum, self.headNum, self.alpha = layer_num, head_num, alpha
@@ -325,11 +329,24 @@ class GraphBlocks(nn.Module, _KeepMixin):
         """x0 [total_nodes,128]; e0, e1 [total_pairs,128] (fp32 or bf16); adj [total_pairs] or None.
         Returns y1, y2 and node_feats = cat[x0, x0, y1] (append-before-update, G:338)."""
         mask = None if adj is None else torch.eq(adj, 0)                                # G:330
+        ebar1 = None
+        if self.overlap and e1.is_cuda:
+            main = torch.cuda.current_stream(e1.device)
+            side = self._side.get(e1.device)
+            if side is None:
+                side = self._side[e1.device] = torch.cuda.Stream(e1.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ebar1 = EdgeMeanFn.apply(e1, batch)
+            ebar1.record_stream(main)
         a0, ebar0 = self.get_weighted_adj_matrix.forward_batched(x0, e0, batch, mask)   # G:332
         new = self.graphcnn[0].forward_batched(x0, ebar0, a0.view(1, -1), batch)        # G:333
         y1 = self._blend(new, x0)
         a1 = self.get_adj_matrix[0].forward_batched(y1, batch)                          # G:336
-        ebar1 = EdgeMeanFn.apply(e1, batch)
+        if ebar1 is None:
+            ebar1 = EdgeMeanFn.apply(e1, batch)
+        else:
+            torch.cuda.current_stream(e1.device).wait_stream(self._side[e1.device])
         new = self.graphcnn[1].forward_batched(y1, ebar1, a1, batch)                    # G:337
         y2 = self._blend(new, y1)
         return {"y1": y1, "y2": y2, "a0": a0, "a1": a1, "node_feats": torch.cat([x0, x0, y1], 1)}
