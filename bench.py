@@ -214,6 +214,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG=VERSION
+        os.environ["NCCL_DEBUG"] = os.environ.get("GCGCN_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -363,7 +365,8 @@ def run_gpu_arm(args):
                    "collective": "none" if world == 1 else f"one NCCL all-reduce of {bucket.nbytes} B per step"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": top, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
