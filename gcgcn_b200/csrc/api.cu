@@ -46,6 +46,10 @@ int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const flo
                            int dis_w, int dis_rows, const int* dis_h, const int* dis_t, float* dfeat,
                            float* ddis, void* ws, size_t ws_bytes, cudaStream_t st);
 int pair_dis_warps();
+int launch_pack_stack(const float* const* wn_ptrs, const float* const* we_ptrs, int heads, int layers, int slab,
+                      float* WnX, float* We, float* Winner, cudaStream_t st);
+int launch_unpack_stack(const float* dWnX, const float* dWe, const float* dWinner, int heads, int layers, int slab,
+                        float* dwn_flat, float* dwe_flat, cudaStream_t st);
 
 // ---- error text, launch counter, device cache --------------------------------------------------
 std::atomic<uint64_t> g_launches{0};
@@ -501,6 +505,33 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
                                       gws, GEMM_WS_BYTES, st));
     }
     return GCGCN_OK;
+}
+
+// ---- parameter packing -----------------------------------------------------------------------
+int gcgcn_pack_stack_weights(const void* wn_ptrs, const void* we_ptrs, int32_t heads, int32_t layers, int32_t slab,
+                             float* WnX, float* We, float* Winner, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(heads >= 1 && layers >= 1 && slab >= 1 && slab % layers == 0, "pack_stack: bad heads/layers/slab");
+    GCGCN_REQUIRE(layers == 1 || Winner != nullptr, "pack_stack: Winner is required when layers > 1");
+    GCGCN_TRY(check_device_ptr(wn_ptrs, "wn_ptrs"));
+    GCGCN_TRY(check_device_ptr(we_ptrs, "we_ptrs"));
+    GCGCN_TRY(check_device_ptr(WnX, "WnX"));
+    GCGCN_TRY(check_device_ptr(We, "We"));
+    return launch_pack_stack(static_cast<const float* const*>(wn_ptrs), static_cast<const float* const*>(we_ptrs),
+                             heads, layers, slab, WnX, We, Winner, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_unpack_stack_grads(const float* dWnX, const float* dWe, const float* dWinner, int32_t heads,
+                             int32_t layers, int32_t slab, float* dwn_flat, float* dwe_flat, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(heads >= 1 && layers >= 1 && slab >= 1 && slab % layers == 0, "unpack_stack: bad heads/layers/slab");
+    GCGCN_REQUIRE(layers == 1 || dWinner != nullptr, "unpack_stack: dWinner is required when layers > 1");
+    GCGCN_TRY(check_device_ptr(dWnX, "dWnX"));
+    GCGCN_TRY(check_device_ptr(dWe, "dWe"));
+    GCGCN_TRY(check_device_ptr(dwn_flat, "dwn_flat"));
+    GCGCN_TRY(check_device_ptr(dwe_flat, "dwe_flat"));
+    return launch_unpack_stack(dWnX, dWe, dWinner, heads, layers, slab, dwn_flat, dwe_flat,
+                               static_cast<cudaStream_t>(stream));
 }
 
 // ---- a8 pair gathers -------------------------------------------------------------------------

@@ -234,6 +234,63 @@ class StackFn(Function):
         return (dx, debar, dA, dWnX, dWe, dWinner, dWout, dbout, None, None, None, None, None, None, None)
 
 
+# ------------------------------------------------------------------------------- parameter packing
+_PTR_TABLES: dict = {}
+
+
+def _ptr_table(tensors, device) -> torch.Tensor:
+    key = tuple(t.data_ptr() for t in tensors)
+    tab = _PTR_TABLES.get(key)
+    if tab is None:
+        if len(_PTR_TABLES) > 64:
+            _PTR_TABLES.clear()
+        tab = _PTR_TABLES[key] = torch.tensor(key, dtype=torch.int64, device=device)
+    return tab
+
+
+class PackStackFn(Function):
+    """(weights_node_k, weights_edge_k for k = h*L + l) -> WnX, We, Winner in one launch; the backward
+    scatters the packed gradients into per-parameter views of two flat buffers in one launch."""
+
+    @staticmethod
+    def forward(ctx, heads: int, layers: int, *params):
+        wn = [_cuda(p, "weights_node") for p in params[0::2]]
+        we = [_cuda(p, "weights_edge") for p in params[1::2]]
+        dev = wn[0].device
+        slab = layers * we[0].shape[1]
+        g = slab // layers
+        WnX = torch.empty(D, heads * slab, device=dev)
+        We = torch.empty(D, heads * slab, device=dev)
+        Winner = torch.empty(heads, layers, slab, g, device=dev) if layers > 1 else None
+        _lib.call("gcgcn_pack_stack_weights", _p(_ptr_table(wn, dev)), _p(_ptr_table(we, dev)), heads, layers, slab,
+                  _p(WnX), _p(We), _p(Winner), _stream(dev))
+        ctx.cfg = (heads, layers, slab, [tuple(t.shape) for t in wn], [tuple(t.shape) for t in we])
+        ctx._keepalive = (wn, we)
+        if Winner is None:
+            ctx.mark_non_differentiable()
+            return WnX, We
+        return WnX, We, Winner
+
+    @staticmethod
+    def backward(ctx, dWnX, dWe, dWinner=None):
+        heads, layers, slab, wn_shapes, we_shapes = ctx.cfg
+        dev = dWnX.device
+        dWnX, dWe = _cuda(dWnX, "dWnX"), _cuda(dWe, "dWe")
+        if layers > 1:
+            dWinner = torch.zeros(heads, layers, slab, slab // layers, device=dev) if dWinner is None \
+                else _cuda(dWinner, "dWinner")
+        dwn_flat = torch.empty(sum(a * b for a, b in wn_shapes), device=dev)
+        dwe_flat = torch.empty(sum(a * b for a, b in we_shapes), device=dev)
+        _lib.call("gcgcn_unpack_stack_grads", _p(dWnX), _p(dWe), _p(dWinner), heads, layers, slab, _p(dwn_flat),
+                  _p(dwe_flat), _stream(dev))
+        gn = [v.view(s) for v, s in zip(torch.split(dwn_flat, [a * b for a, b in wn_shapes]), wn_shapes)]
+        ge = [v.view(s) for v, s in zip(torch.split(dwe_flat, [a * b for a, b in we_shapes]), we_shapes)]
+        out = [None, None]
+        for a, b in zip(gn, ge):
+            out += [a, b]
+        return tuple(out)
+
+
 # ------------------------------------------------------------------------------- a8 pair gathers
 class PairGatherFn(Function):
     """P_h[p] = cat(feat[h_idx[p]], dis[dis_h[p]]), P_t likewise (G:306-307, 351-352)."""

@@ -25,7 +25,7 @@ from torch import nn
 
 from . import _lib
 from .batch import PairTables, PoolTable, RaggedBatch, single_doc_batch
-from .functional import EdgeMeanFn, GatFn, MhaFn, PairGatherFn, PoolFn, StackFn
+from .functional import EdgeMeanFn, GatFn, MhaFn, PackStackFn, PairGatherFn, PoolFn, StackFn
 
 HIDDEN = 128
 
@@ -114,6 +114,12 @@ class GraphConv(nn.Module, _KeepMixin):
 def _pack_stack(convs: Sequence[GraphConv], heads: int, layers: int, g: int):
     """Pack per-GraphConv parameters into the layouts of gcgcn_graphconv_stack_* (autograd-visible,
     so gradients land on the reference-named parameters)."""
+    if convs[0].weights_node.is_cuda:
+        flat = []
+        for c in convs:
+            flat += [c.weights_node, c.weights_edge]
+        packed = PackStackFn.apply(heads, layers, *flat)
+        return (packed[0], packed[1], packed[2] if layers > 1 else None)
     wn_x = torch.cat([c.weights_node[:HIDDEN] for c in convs], dim=1)          # [128, H*128]
     w_e = torch.cat([c.weights_edge for c in convs], dim=1)                    # [128, H*128]
     if layers == 1:

@@ -167,6 +167,16 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
                               float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
                               void* ws, size_t ws_bytes, void* stream);
 
+/* ---- parameter packing for the stack entry points ----------------------------------------
+ * The reference keeps one weights_node [128 + l*g, g] and one weights_edge [128, g] per GraphConv
+ * (G:24-25, heads*layers of them).  pack gathers them (device arrays of heads*layers device pointers,
+ * GraphConv index k = h*layers + l) into WnX / We / Winner in one launch; unpack scatters the packed
+ * gradients into two flat buffers holding the per-GraphConv gradients back to back in index order.   */
+int gcgcn_pack_stack_weights(const void* wn_ptrs, const void* we_ptrs, int32_t heads, int32_t layers,
+                             int32_t slab, float* WnX, float* We, float* Winner, void* stream);
+int gcgcn_unpack_stack_grads(const float* dWnX, const float* dWe, const float* dWinner, int32_t heads,
+                             int32_t layers, int32_t slab, float* dwn_flat, float* dwe_flat, void* stream);
+
 /* ---- a8: pair gathers, replaces G:351-352 (+ G:306-307) -----------------------------------
  * out_h[p,:] = cat(feat[h_idx[p],:], dis[dis_h[p],:]),  out_t[p,:] = cat(feat[t_idx[p],:], dis[dis_t[p],:])
  * for every pair p of the batch.  Index tables are int32 [total_pairs] holding *global* node
