@@ -36,28 +36,40 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // One warp: C[16 x 8*NT] += A[16 x 8*ksteps] * B[8*ksteps x 8*NT] with fp32-accurate 3xTF32.
-//   fa(m, k): element of A, m in [0,16);  fb(k, n): element of B, n in [0, 8*NT).
+//   A(m,k) = pa[m*lda + k]                       (m in [0,16))
+//   B(k,n) = pb[k*ldb + n]  (BT = false)  or  pb[n*ldb + k]  (BT = true)          (n in [0, 8*NT))
 // Fragment layout (PTX m16n8k8): g = lane/4, t = lane%4
 //   a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);  b0=(t,g) b1=(t+4,g);  c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)
-template <int NT, class FA, class FB>
-__device__ __forceinline__ void warp_gemm(float (&c)[NT][4], int ksteps, FA fa, FB fb) {
+// All per-lane addresses are formed once; the K loop only bumps two pointers.
+template <int NT, bool BT>
+__device__ __forceinline__ void warp_gemm(float (&c)[NT][4], int ksteps, const float* __restrict__ pa, int lda,
+                                          const float* __restrict__ pb, int ldb) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* a_lo = pa + g * lda + t;            // row g
+    const float* a_hi = a_lo + 8 * lda;              // row g + 8
+    const float* b0 = BT ? pb + g * ldb + t : pb + t * ldb + g;
+    const int b_k4 = BT ? 4 : 4 * ldb;               // k -> k + 4
+    const int b_n8 = BT ? 8 * ldb : 8;               // next 8-column tile
+    const int b_step = BT ? 8 : 8 * ldb;             // next K step
+#pragma unroll 2
     for (int ks = 0; ks < ksteps; ++ks) {
-        const int k0 = ks * 8;
         uint32_t ah[4], al[4];
-        split_tf32(fa(g, k0 + t), ah[0], al[0]);
-        split_tf32(fa(g + 8, k0 + t), ah[1], al[1]);
-        split_tf32(fa(g, k0 + t + 4), ah[2], al[2]);
-        split_tf32(fa(g + 8, k0 + t + 4), ah[3], al[3]);
+        split_tf32(a_lo[0], ah[0], al[0]);
+        split_tf32(a_hi[0], ah[1], al[1]);
+        split_tf32(a_lo[4], ah[2], al[2]);
+        split_tf32(a_hi[4], ah[3], al[3]);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             uint32_t bh[2], bl[2];
-            split_tf32(fb(k0 + t, 8 * nt + g), bh[0], bl[0]);
-            split_tf32(fb(k0 + t + 4, 8 * nt + g), bh[1], bl[1]);
+            split_tf32(b0[nt * b_n8], bh[0], bl[0]);
+            split_tf32(b0[nt * b_n8 + b_k4], bh[1], bl[1]);
             mma_tf32(c[nt], al, bh);
             mma_tf32(c[nt], ah, bl);
             mma_tf32(c[nt], ah, bh);
         }
+        a_lo += 8;
+        a_hi += 8;
+        b0 += b_step;
     }
 }
 
@@ -91,7 +103,7 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
     float* As = smem;                 // [NP][LDA]  attention map, zero padded
     float* Zs = As + NP * LDA;        // [NP][LDZ]  Z_l
     float* Gs = Zs + NP * LDZ;        // [NP][LDG]  g_0 .. g_{L-2}
-    float* rs = Gs + NP * LDG;        // [NP]
+    float* rs = Gs + NP * LDG;        // [NP]  reciprocal row normalisers
     // The dense-connect weights (16 KB per head) are read as MMA fragments straight from global memory:
     // co-resident CTAs work on the same head, so they stay L1-resident, and leaving them out of shared
     // memory raises occupancy (the kernel is latency-, not bandwidth-bound).
@@ -101,18 +113,18 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
     const float* Ab = A + static_cast<long long>(h) * total_pairs + pair_ptr[b];
     const bool relu = flags & GCGCN_STACK_RELU, resid = flags & GCGCN_STACK_RESIDUAL;
 
-    for (int idx = tid; idx < NP * NP; idx += SM_THREADS) {
-        const int i = idx / NP, j = idx - i * NP;
-        As[i * LDA + j] = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
+    // attention map -> shared (zero padded), one warp per row, and 1 / (rowsum + [rowsum == 0])   (G:47-49)
+    for (int i = warp; i < NP; i += SM_WARPS) {
+        float s = 0.f;
+        for (int j = lane; j < NP; j += WARP) {
+            const float v = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
+            As[i * LDA + j] = v;
+            s += v;
+        }
+        s = warp_sum(s);
+        if (lane == 0) rs[i] = 1.0f / (s + (s == 0.f ? 1.f : 0.f));
     }
     for (int idx = tid; idx < NP * LDG; idx += SM_THREADS) Gs[idx] = 0.f;
-    __syncthreads();
-    for (int i = warp; i < NP; i += SM_WARPS) {          // r = rowsum + [rowsum == 0]   (G:47-49)
-        float s = 0.f;
-        for (int j = lane; j < NP; j += WARP) s += As[i * LDA + j];
-        s = warp_sum(s);
-        if (lane == 0) rs[i] = s + (s == 0.f ? 1.f : 0.f);
-    }
 
     const int MT = NP / 16;
     for (int l = 0; l < layers; ++l) {
@@ -140,8 +152,7 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
                 }
                 const float* ga = Gs + (16 * mt) * LDG;
                 const float* wb = wsrc + 32 * ng;
-                warp_gemm<4>(c, kin / 8, [&](int m, int k) { return ga[m * LDG + k]; },
-                             [&](int k, int nn) { return __ldg(wb + k * GD + nn); });
+                warp_gemm<4, false>(c, kin / 8, ga, LDG, wb, GD);
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     *reinterpret_cast<float2*>(zc + g * LDZ + 8 * nt + 2 * t) = make_float2(c[nt][0], c[nt][1]);
@@ -162,21 +173,20 @@ stack_fwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
             zero_frag<4>(c);
             const float* aa = As + (16 * mt) * LDA;
             const float* zb = Zs + 32 * ng;
-            warp_gemm<4>(c, NP / 8, [&](int m, int k) { return aa[m * LDA + k]; },
-                         [&](int k, int nn) { return zb[k * LDZ + nn]; });
+            warp_gemm<4, false>(c, NP / 8, aa, LDA, zb, LDZ);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int i = 16 * mt + g + 8 * half;
                 if (i >= n) continue;
-                const float r = rs[i];
+                const float rinv = rs[i];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const int col = 32 * ng + 8 * nt + 2 * t;
                     const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + col;
                     const float2 e2 = ld2g(E + off);
                     float2 o;
-                    o.x = (e2.x + c[nt][2 * half]) / r;
-                    o.y = (e2.y + c[nt][2 * half + 1]) / r;
+                    o.x = (e2.x + c[nt][2 * half]) * rinv;
+                    o.y = (e2.y + c[nt][2 * half + 1]) * rinv;
                     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
                     *reinterpret_cast<float2*>(G + off) = o;
                     if (l < layers - 1) *reinterpret_cast<float2*>(Gs + i * LDG + kin + col) = o;
@@ -227,16 +237,16 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
     float* dAb = dA + abase;
     const bool relu = flags & GCGCN_STACK_RELU;
 
-    for (int idx = tid; idx < NP * NP; idx += SM_THREADS) {
-        const int i = idx / NP, j = idx - i * NP;
-        Ats[j * LDA + i] = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
-    }
+    // attention map -> shared, transposed and zero padded; reciprocal row normalisers (G:47-49)
     for (int i = warp; i < NP; i += SM_WARPS) {
         float s = 0.f;
-        if (i < n)
-            for (int j = lane; j < n; j += WARP) s += Ab[static_cast<size_t>(i) * n + j];
+        for (int j = lane; j < NP; j += WARP) {
+            const float v = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
+            Ats[j * LDA + i] = v;
+            s += v;
+        }
         s = warp_sum(s);
-        if (lane == 0) { rs[i] = s + (s == 0.f ? 1.f : 0.f); drs[i] = 0.f; }
+        if (lane == 0) { rs[i] = 1.0f / (s + (s == 0.f ? 1.f : 0.f)); drs[i] = 0.f; }
     }
     __syncthreads();
 
@@ -265,8 +275,8 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
                     dg.x = g4.x > 0.f ? dg.x : 0.f; dg.y = g4.y > 0.f ? dg.y : 0.f;
                     dg.z = g4.z > 0.f ? dg.z : 0.f; dg.w = g4.w > 0.f ? dg.w : 0.f;
                 }
-                const float r = rs[i];
-                dn.x = dg.x / r; dn.y = dg.y / r; dn.z = dg.z / r; dn.w = dg.w / r;
+                const float rinv = rs[i];
+                dn.x = dg.x * rinv; dn.y = dg.y * rinv; dn.z = dg.z * rinv; dn.w = dg.w * rinv;
                 *reinterpret_cast<float4*>(dE + off) = dn;
                 drp = -(dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
                 zl = ld4g(Z + off);
@@ -285,8 +295,7 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
             zero_frag<2>(c);
             const float* da = dNs + (16 * mt) * LDN;
             const float* zb = Ts + (16 * jt) * LDN;
-            warp_gemm<2>(c, GD / 8, [&](int m, int k) { return da[m * LDN + k]; },
-                         [&](int k, int nn) { return zb[nn * LDN + k]; });
+            warp_gemm<2, true>(c, GD / 8, da, LDN, zb, LDN);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int i = 16 * mt + g + 8 * half;
@@ -313,8 +322,7 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
             zero_frag<4>(c);
             const float* at = Ats + (16 * jt) * LDA;
             const float* db = dNs + 32 * ng;
-            warp_gemm<4>(c, NP / 8, [&](int m, int k) { return at[m * LDA + k]; },
-                         [&](int k, int nn) { return db[k * LDN + nn]; });
+            warp_gemm<4, false>(c, NP / 8, at, LDA, db, LDN);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int j = 16 * jt + g + 8 * half;
@@ -337,8 +345,7 @@ stack_bwd_mma_kernel(const int* __restrict__ node_ptr, const long long* __restri
             zero_frag<4>(c);
             const float* ta = Ts + (16 * jt) * LDN;
             const float* wb = wsrc + static_cast<size_t>(m * GD + 32 * ng) * GD;
-            warp_gemm<4>(c, GD / 8, [&](int mm, int k) { return ta[mm * LDN + k]; },
-                         [&](int k, int nn) { return __ldg(wb + nn * GD + k); });
+            warp_gemm<4, true>(c, GD / 8, ta, LDN, wb, GD);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int j = 16 * jt + g + 8 * half;
