@@ -37,6 +37,9 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
                 int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 int launch_colsum(const float* X, int M, int N, int ldx, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gemm_batched(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                        int ldb, float beta, float* C, int ldc, int batch, long long sA, long long sB, long long sC,
+                        void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_csr_gather(const float* src, const int* ptr, const int* idx, const float* w, int rows, float* out,
                       cudaStream_t st);
 int launch_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int feat_w, const float* dis, int dis_w,
@@ -497,12 +500,11 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
         GCGCN_TRY(cuda_ok(cudaMemsetAsync(dWinner, 0, static_cast<size_t>(heads) * layers * slab * gd * sizeof(float), st),
                           "memset dWinner"));
         // dWinner[h][l][m*g + k][c] = sum_rows G[row][h*S + m*g + k] * dZ[row][h*S + l*g + c],  m < l
-        for (int h = 0; h < heads; ++h)
-            for (int l = 1; l < layers; ++l)
-                GCGCN_TRY(launch_gemm(1, 0, l * gd, gd, M, 1.f, G + static_cast<size_t>(h) * slab, HD,
-                                      dZ + static_cast<size_t>(h) * slab + l * gd, HD, 0.f,
-                                      dWinner + (static_cast<size_t>(h) * layers + l) * slab * gd, gd, nullptr,
-                                      gws, GEMM_WS_BYTES, st));
+        // (all heads of one sub-layer in a single batched launch)
+        for (int l = 1; l < layers; ++l)
+            GCGCN_TRY(launch_gemm_batched(1, 0, l * gd, gd, M, 1.f, G, HD, dZ + l * gd, HD, 0.f,
+                                          dWinner + static_cast<size_t>(l) * slab * gd, gd, heads, slab, slab,
+                                          static_cast<long long>(layers) * slab * gd, gws, GEMM_WS_BYTES, st));
     }
     return GCGCN_OK;
 }

@@ -140,10 +140,12 @@ gemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int l
 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float alpha, float beta,
-                     float* __restrict__ C, int ldc, const float* __restrict__ bias) {
+                     float* __restrict__ C, int ldc, const float* __restrict__ bias, long long batch_stride_c) {
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const size_t total = static_cast<size_t>(M) * N;
     if (idx >= total) return;
+    partial += static_cast<size_t>(blockIdx.y) * splits * total;      // batched: one product per blockIdx.y
+    C += static_cast<size_t>(blockIdx.y) * batch_stride_c;
     float s = 0.f;
     for (int p = 0; p < splits; ++p) s += partial[p * total + idx];
     const int m = static_cast<int>(idx / N), n = static_cast<int>(idx - static_cast<size_t>(m) * N);
@@ -171,16 +173,17 @@ int launch_reduce_partials(const float* partial, int parts, int width, float* ou
                            float* out1, cudaStream_t st);
 
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, float alpha, float beta, float* C,
-                         int ldc, const float* bias, cudaStream_t st) {
+                         int ldc, const float* bias, cudaStream_t st, int batch = 1, long long sC = 0) {
     const size_t total = static_cast<size_t>(M) * N;
-    splitk_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias);
+    dim3 grid(ceil_div(total, 256), batch);
+    splitk_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias, sC);
     GCGCN_CHECK_LAUNCH("splitk_reduce");
     return GCGCN_OK;
 }
 
 int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                    int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
-                   cudaStream_t st, int* taken);
+                   cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC);
 
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
@@ -188,7 +191,8 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
     if (M <= 0 || N <= 0) return GCGCN_OK;
     if (K < 0) return fail(GCGCN_ERR_INVALID_ARG, "gemm: K < 0");
     int taken = 0;
-    GCGCN_TRY(launch_gemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ws, ws_bytes, st, &taken));
+    GCGCN_TRY(launch_gemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ws, ws_bytes, st, &taken,
+                             1, 0, 0, 0));
     if (taken) return GCGCN_OK;
     const int tiles = ceil_div(M, GM) * ceil_div(N, GN);
     int splits = 1;
@@ -219,6 +223,22 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
 #undef GCGCN_GEMM
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tt" : "gemm_tn") : (tb ? "gemm_nt" : "gemm_nn"));
     if (splits > 1) GCGCN_TRY(launch_splitk_reduce(partial, splits, M, N, alpha, beta, C, ldc, bias, st));
+    return GCGCN_OK;
+}
+
+// `batch` independent products with the same shapes and strided operands (the per-head dense-connect
+// weight gradients): one tensor-core launch when possible, else a loop over the single-product path
+int launch_gemm_batched(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                        int ldb, float beta, float* C, int ldc, int batch, long long sA, long long sB, long long sC,
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || batch <= 0) return GCGCN_OK;
+    int taken = 0;
+    GCGCN_TRY(launch_gemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, ws, ws_bytes, st, &taken,
+                             batch, sA, sB, sC));
+    if (taken) return GCGCN_OK;
+    for (int b = 0; b < batch; ++b)
+        GCGCN_TRY(launch_gemm(ta, tb, M, N, K, alpha, A + b * sA, lda, B + b * sB, ldb, beta, C + b * sC, ldc, nullptr,
+                              ws, ws_bytes, st));
     return GCGCN_OK;
 }
 

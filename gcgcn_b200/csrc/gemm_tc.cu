@@ -50,6 +50,8 @@ struct TcArgs {
     float* partial;     // != nullptr -> split-K partial output [k_splits][M][N]
     float alpha, beta;
     int tiles_m, tiles_n, k_splits, k_per_split;
+    int batch;                      // independent products per launch (same shapes, strided operands)
+    long long sA, sB, sC;           // element strides between consecutive products
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -242,27 +244,30 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_mn = args.tiles_m * args.tiles_n;
-    const int total_tiles = tiles_mn * args.k_splits;
+    const int total_tiles = tiles_mn * args.k_splits * args.batch;
 
     if (warp < TC_PRODUCER_WARPS) {
         // ===== producers: TC_GROUPS groups of 4 warps take K blocks round-robin; a group issues its loads
         // before it waits for its shared-memory stage, so TC_GROUPS blocks of global loads are in flight
-        const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
-        const bool b_vec = (args.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.B) & 15) == 0);
+        const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0) && (args.sA % 4 == 0);
+        const bool b_vec = (args.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.B) & 15) == 0) && (args.sB % 4 == 0);
         const int group = warp >> 2, tid = threadIdx.x & 127;
         int j = 0;                                   // running K-block index of this CTA
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int ks = t / tiles_mn, rem = t - ks * tiles_mn;
+            const int bi = t / (tiles_mn * args.k_splits), tb = t - bi * (tiles_mn * args.k_splits);
+            const int ks = tb / tiles_mn, rem = tb - ks * tiles_mn;
             const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
             const int kbeg = ks * args.k_per_split;
             const int kend = min(args.K, kbeg + args.k_per_split);
+            const float* Ab = args.A + bi * args.sA;
+            const float* Bb = args.B + bi * args.sB;
             for (int k0 = kbeg; k0 < kend; k0 += TC_BK, ++j) {
                 if ((j % TC_GROUPS) != group) continue;
                 const int stage = j % TC_STAGES;
                 const uint32_t phase = (j / TC_STAGES) & 1;
                 float4 va[8], vb[8];
-                fetch_operand<A_KCONTIG>(args.A, args.lda, m0, args.M, k0, kend, a_vec, tid, va);
-                fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, k0, kend, b_vec, tid, vb);
+                fetch_operand<A_KCONTIG>(Ab, args.lda, m0, args.M, k0, kend, a_vec, tid, va);
+                fetch_operand<B_KCONTIG>(Bb, args.ldb, n0, args.N, k0, kend, b_vec, tid, vb);
                 mbar_wait(empty_bar(stage), phase ^ 1);      // the MMAs that read this stage have retired
                 float* st = reinterpret_cast<float*>(smem + size_t(stage) * TC_STAGE_BYTES);
                 store_operand<A_KCONTIG>(st, st + TC_PART_BYTES / 4, tid, va);
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int ks = t / tiles_mn;
+                const int ks = (t % (tiles_mn * args.k_splits)) / tiles_mn;
                 const int kbeg = ks * args.k_per_split;
                 const int kend = min(args.K, kbeg + args.k_per_split);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);     // epilogue has drained this accumulator
@@ -319,7 +324,8 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int ks = t / tiles_mn, rem = t - ks * tiles_mn;
+            const int bi = t / (tiles_mn * args.k_splits), tb = t - bi * (tiles_mn * args.k_splits);
+            const int ks = tb / tiles_mn, rem = tb - ks * tiles_mn;
             const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
             const bool has_k = ks * args.k_per_split < args.K;
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -328,10 +334,10 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
             float* out_base;
             int ldo;
             if (args.partial != nullptr) {
-                out_base = args.partial + static_cast<size_t>(ks) * args.M * args.N;
+                out_base = args.partial + (static_cast<size_t>(bi) * args.k_splits + ks) * args.M * args.N;
                 ldo = args.N;
             } else {
-                out_base = args.C;
+                out_base = args.C + bi * args.sC;
                 ldo = args.ldc;
             }
             const int rows_valid = min(32, args.M - row_base);      // may be <= 0 for padding tiles
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
 }
 
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, float alpha, float beta, float* C,
-                         int ldc, const float* bias, cudaStream_t st);
+                         int ldc, const float* bias, cudaStream_t st, int batch, long long sC);
 
 bool gemm_tc_enabled() {
     static int cached = -1;
@@ -420,21 +426,22 @@ bool gemm_tc_enabled() {
 // returns 1 if the launch was taken by the tensor-core path, 0 if the caller should use the SIMT kernel
 int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                    int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
-                   cudaStream_t st, int* taken) {
+                   cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC) {
     *taken = 0;
-    if (!gemm_tc_enabled() || K < 1) return GCGCN_OK;
-    if (static_cast<double>(M) * N * K < 2.0e6) return GCGCN_OK;       // tiny: not worth a 128x128 tile
+    if (!gemm_tc_enabled() || K < 1 || batch < 1) return GCGCN_OK;
+    if (static_cast<double>(M) * N * K * batch < 2.0e6) return GCGCN_OK;   // tiny: not worth a 128x128 tile
     TcArgs a;
     a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
     a.A = A; a.B = B; a.bias = bias; a.C = C; a.alpha = alpha; a.beta = beta;
     a.tiles_m = ceil_div(M, TC_BM);
     a.tiles_n = ceil_div(N, TC_BN);
-    const int tiles = a.tiles_m * a.tiles_n;
+    a.batch = batch; a.sA = sA; a.sB = sB; a.sC = sC;
+    const int tiles = a.tiles_m * a.tiles_n * batch;
     const int sms = sm_count();
     int splits = 1;
     if (tiles < sms && K >= 4096) {
         splits = std::min(ceil_div(2 * sms, tiles), ceil_div(K, 512));
-        const size_t per = static_cast<size_t>(M) * N * sizeof(float);
+        const size_t per = static_cast<size_t>(M) * N * sizeof(float) * batch;
         if (ws == nullptr) splits = 1;
         else splits = static_cast<int>(std::min<size_t>(splits, ws_bytes / per));
         if (splits < 2) splits = 1;
@@ -468,7 +475,8 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     else GCGCN_TC_LAUNCH(false, false, 2);
 #undef GCGCN_TC_LAUNCH
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
-    if (splits > 1) GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st));
+    if (splits > 1)
+        GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));
     *taken = 1;
     return GCGCN_OK;
 }
