@@ -90,6 +90,9 @@ SIGNATURES = {
                                   + [_P] * 13 + [_P, c_size_t, _P]),
     "gcgcn_graphconv_stack_bwd": (c_int32, [_BT, c_int32, c_int32, c_int32, c_int32, c_int32]
                                   + [_P] * 20 + [_P, c_size_t, _P]),
+    "gcgcn_block_supported": (c_int32, [_BT, c_int32, c_int32, c_int32]),
+    "gcgcn_mha_stack_fwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 15 + [_P, c_size_t, _P]),
+    "gcgcn_mha_stack_bwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 22 + [_P, c_size_t, _P]),
     "gcgcn_pack_stack_weights": (c_int32, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "gcgcn_unpack_stack_grads": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "gcgcn_pair_gather_fwd": (c_int32, [_BT, _P, c_int32, _P, c_int32, _P, _P, _P, _P, _P, _P, _P]),

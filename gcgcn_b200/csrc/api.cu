@@ -33,6 +33,14 @@ int launch_stack_fwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
 int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A, const float* Z,
                      const float* G, const float* Winner, const float* keep, const float* dF, float* dZ,
                      float* dE, float* dA, cudaStream_t st);
+bool block_kernels_usable(const gcgcn_batch* bt, int heads, int layers, int slab, bool mha);
+int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
+                     float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
+                     cudaStream_t st);
+int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode, const float* A, const float* q,
+                     const float* Z, const float* G, const float* Winner, const float* dF, float* dZ, float* dE,
+                     float* dOut, cudaStream_t st);
+enum { ATT_GRAD_DA = 0, ATT_GRAD_DS = 1, ATT_GRAD_DQ = 2 };   // == BK_OUT_* of gcn_block.cu
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                 int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
                 cudaStream_t st);
@@ -131,6 +139,7 @@ int check_batch(const gcgcn_batch* bt) {
 }
 
 constexpr size_t GEMM_WS_BYTES = size_t(24) << 20;
+constexpr int BLOCK_FLAGS_ALL = GCGCN_STACK_RELU | GCGCN_STACK_RESIDUAL | GCGCN_STACK_LINEAR;
 
 static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
 
@@ -329,6 +338,21 @@ int gcgcn_gat_fwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t 
     return launch_edge_fwd(bt, e, edge_dtype, v, ux, (apply_mask ? mask : nullptr), keep, P, A, ebar, st);
 }
 
+// GAT backward downstream of the softmax: dS -> dx (node half), du, dc, and the edge pass (de, dv).
+static int gat_bwd_from_ds(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype, const float* u,
+                           const float* v, const float* dS, const float* debar, float* dx, void* de, float* du,
+                           float* dv, float* dc, Arena& ar, cudaStream_t st) {
+    float* node_part = ar.take<float>(static_cast<size_t>(node_bwd_grid()) * (D + 1));
+    float* dv_part = ar.take<float>(static_cast<size_t>(edge_bwd_grid()) * D);
+    if (node_part == nullptr || dv_part == nullptr) return fail(GCGCN_ERR_WORKSPACE, "gat_bwd: workspace too small");
+    int parts = 0;
+    GCGCN_TRY(launch_gat_node_bwd(bt, dS, x, u, dx, node_part, &parts, st));
+    GCGCN_TRY(launch_reduce_partials(node_part, parts, D + 1, du, D, dc, st));
+    GCGCN_TRY(launch_edge_bwd(bt, e, edge_dtype, v, dS, debar, de, dv_part, st));
+    const int grid = edge_bwd_grid() < bt->total_nodes ? edge_bwd_grid() : bt->total_nodes;
+    return launch_reduce_partials(dv_part, grid, D, dv, D, nullptr, st);
+}
+
 int gcgcn_gat_bwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t edge_dtype, const float* u,
                   const float* v, const uint8_t* mask, int32_t apply_mask, const float* keep, const float* P,
                   const float* dA, const float* debar, float* dx, void* de, float* du, float* dv, float* dc,
@@ -345,17 +369,9 @@ int gcgcn_gat_bwd(const gcgcn_batch* bt, const float* x, const void* e, int32_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar(ws, ws_bytes);
     float* dS = ar.take<float>(bt->total_pairs);
-    float* node_part = ar.take<float>(static_cast<size_t>(node_bwd_grid()) * (D + 1));
-    float* dv_part = ar.take<float>(static_cast<size_t>(edge_bwd_grid()) * D);
-    if (dS == nullptr || node_part == nullptr || dv_part == nullptr)
-        return fail(GCGCN_ERR_WORKSPACE, "gat_bwd: workspace too small");
+    if (dS == nullptr) return fail(GCGCN_ERR_WORKSPACE, "gat_bwd: workspace too small");
     GCGCN_TRY(launch_softmax_bwd(bt, 1, P, keep, dA, (apply_mask ? mask : nullptr), dS, st));
-    int parts = 0;
-    GCGCN_TRY(launch_gat_node_bwd(bt, dS, x, u, dx, node_part, &parts, st));
-    GCGCN_TRY(launch_reduce_partials(node_part, parts, D + 1, du, D, dc, st));
-    GCGCN_TRY(launch_edge_bwd(bt, e, edge_dtype, v, dS, debar, de, dv_part, st));
-    const int grid = edge_bwd_grid() < bt->total_nodes ? edge_bwd_grid() : bt->total_nodes;
-    return launch_reduce_partials(dv_part, grid, D, dv, D, nullptr, st);
+    return gat_bwd_from_ds(bt, x, e, edge_dtype, u, v, dS, debar, dx, de, du, dv, dc, ar, st);
 }
 
 // ---- a5 MultiHeadAttention -------------------------------------------------------------------
@@ -405,6 +421,30 @@ int gcgcn_mha_bwd(const gcgcn_batch* bt, int32_t heads, const float* x, const fl
 }
 
 // ---- a3/a4/a6 GraphConv stack ----------------------------------------------------------------
+// q != nullptr: the attention is the MHA map of q's head slices, computed inside the block kernel (P is written).
+static int stack_fwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim, int32_t slab,
+                          int32_t flags, const float* x, const float* ebar, const float* A, const float* q, float* P,
+                          const float* WnX, const float* We, const float* Winner, const float* Wout,
+                          const float* bout, const float* keep, float* Z, float* G, float* F, float* y, void* ws,
+                          size_t ws_bytes, cudaStream_t st) {
+    const bool linear = flags & GCGCN_STACK_LINEAR;
+    const int HD = heads * slab, M = bt->total_nodes;
+    Arena ar(ws, ws_bytes);
+    float* E = ar.take<float>(static_cast<size_t>(M) * HD);
+    float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
+    if (E == nullptr || gws == nullptr) return fail(GCGCN_ERR_WORKSPACE, "stack_fwd: workspace too small");
+    GCGCN_TRY(launch_gemm(0, 0, M, HD, in_dim, 1.f, x, in_dim, WnX, HD, 0.f, Z, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, ebar, D, We, HD, 0.f, E, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    float* Fout = linear ? F : y;
+    if (q != nullptr)
+        GCGCN_TRY(launch_block_fwd(bt, heads, layers, nullptr, q, P, Z, E, Winner, x, G, Fout, st));
+    else
+        GCGCN_TRY(launch_stack_fwd(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, Fout, st));
+    if (linear)
+        GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, F, HD, Wout, HD, 0.f, y, D, bout, gws, GEMM_WS_BYTES, st));
+    return GCGCN_OK;
+}
+
 int gcgcn_graphconv_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim,
                               int32_t slab, int32_t flags, const float* x, const float* ebar, const float* A,
                               const float* WnX, const float* We, const float* Winner, const float* Wout,
@@ -427,18 +467,62 @@ int gcgcn_graphconv_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
     GCGCN_TRY(check_device_ptr(G, "G"));
     GCGCN_TRY(check_device_ptr(y, "y"));
     if (linear) GCGCN_TRY(check_device_ptr(F, "F"));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int HD = heads * slab, M = bt->total_nodes;
+    return stack_fwd_impl(bt, heads, layers, in_dim, slab, flags, x, ebar, A, nullptr, nullptr, WnX, We, Winner, Wout,
+                          bout, keep, Z, G, F, y, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// att_grad: ATT_GRAD_DA -> att_out = dA (any configuration; the caller runs the softmax backward);
+//           ATT_GRAD_DS -> att_out = dS (block kernels, one head, A a softmax output);
+//           ATT_GRAD_DQ -> att_out = dq [rows][128] (block kernels, A = MHA probabilities of q).
+static int stack_bwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t in_dim, int32_t slab,
+                          int32_t flags, int att_grad, const float* x, const float* ebar, const float* A,
+                          const float* q, const float* WnX, const float* We, const float* Winner, const float* Wout,
+                          const float* keep, const float* Z, const float* G, const float* F, const float* dy,
+                          float* dx, float* debar, float* att_out, float* dWnX, float* dWe, float* dWinner,
+                          float* dWout, float* dbout, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const bool linear = flags & GCGCN_STACK_LINEAR;
+    const int HD = heads * slab, M = bt->total_nodes, gd = slab / layers;
     Arena ar(ws, ws_bytes);
-    float* E = ar.take<float>(static_cast<size_t>(M) * HD);
+    float* dFbuf = linear ? ar.take<float>(static_cast<size_t>(M) * HD) : nullptr;
+    float* dZ = ar.take<float>(static_cast<size_t>(M) * HD);
+    float* dE = ar.take<float>(static_cast<size_t>(M) * HD);
     float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
-    if (E == nullptr || gws == nullptr) return fail(GCGCN_ERR_WORKSPACE, "stack_fwd: workspace too small");
-    GCGCN_TRY(launch_gemm(0, 0, M, HD, in_dim, 1.f, x, in_dim, WnX, HD, 0.f, Z, HD, nullptr, gws, GEMM_WS_BYTES, st));
-    GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, ebar, D, We, HD, 0.f, E, HD, nullptr, gws, GEMM_WS_BYTES, st));
-    float* Fout = linear ? F : y;
-    GCGCN_TRY(launch_stack_fwd(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, Fout, st));
-    if (linear)
-        GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, F, HD, Wout, HD, 0.f, y, D, bout, gws, GEMM_WS_BYTES, st));
+    if ((linear && dFbuf == nullptr) || dZ == nullptr || dE == nullptr || gws == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "stack_bwd: workspace too small");
+    const float* dF = dy;
+    if (linear) {
+        GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, dy, D, Wout, HD, 0.f, dFbuf, HD, nullptr, gws, GEMM_WS_BYTES, st));
+        if (dWout != nullptr)
+            GCGCN_TRY(launch_gemm(1, 0, D, HD, M, 1.f, dy, D, F, HD, 0.f, dWout, HD, nullptr, gws, GEMM_WS_BYTES, st));
+        if (dbout != nullptr) GCGCN_TRY(launch_colsum(dy, M, D, D, dbout, gws, GEMM_WS_BYTES, st));
+        dF = dFbuf;
+    }
+    if (att_grad == ATT_GRAD_DA)
+        GCGCN_TRY(launch_stack_bwd(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, att_out, st));
+    else
+        GCGCN_TRY(launch_block_bwd(bt, heads, layers, att_grad, A, q, Z, G, Winner, dF, dZ, dE, att_out, st));
+    // dx = [residual: sum_h dF_h] + dZ WnX^T ; debar = dE We^T
+    float beta = 0.f;
+    if (flags & GCGCN_STACK_RESIDUAL) {
+        GCGCN_TRY(launch_head_sum(dF, heads, M, dx, st));
+        beta = 1.f;
+    }
+    GCGCN_TRY(launch_gemm(0, 1, M, in_dim, HD, 1.f, dZ, HD, WnX, HD, beta, dx, in_dim, nullptr, gws, GEMM_WS_BYTES, st));
+    GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, dE, HD, We, HD, 0.f, debar, D, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWnX != nullptr)
+        GCGCN_TRY(launch_gemm(1, 0, in_dim, HD, M, 1.f, x, in_dim, dZ, HD, 0.f, dWnX, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWe != nullptr)
+        GCGCN_TRY(launch_gemm(1, 0, D, HD, M, 1.f, ebar, D, dE, HD, 0.f, dWe, HD, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWinner != nullptr && layers > 1) {
+        GCGCN_TRY(cuda_ok(cudaMemsetAsync(dWinner, 0, static_cast<size_t>(heads) * layers * slab * gd * sizeof(float), st),
+                          "memset dWinner"));
+        // dWinner[h][l][m*g + k][c] = sum_rows G[row][h*S + m*g + k] * dZ[row][h*S + l*g + c],  m < l
+        // (all heads of one sub-layer in a single batched launch)
+        for (int l = 1; l < layers; ++l)
+            GCGCN_TRY(launch_gemm_batched(1, 0, l * gd, gd, M, 1.f, G, HD, dZ + l * gd, HD, 0.f,
+                                          dWinner + static_cast<size_t>(l) * slab * gd, gd, heads, slab, slab,
+                                          static_cast<long long>(layers) * slab * gd, gws, GEMM_WS_BYTES, st));
+    }
     return GCGCN_OK;
 }
 
@@ -466,46 +550,82 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
     GCGCN_TRY(check_device_ptr(dx, "dx"));
     GCGCN_TRY(check_device_ptr(debar, "debar"));
     GCGCN_TRY(check_device_ptr(dA, "dA"));
+    return stack_bwd_impl(bt, heads, layers, in_dim, slab, flags, ATT_GRAD_DA, x, ebar, A, nullptr, WnX, We, Winner,
+                          Wout, keep, Z, G, F, dy, dx, debar, dA, dWnX, dWe, dWinner, dWout, dbout, ws, ws_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+// ---- a5 + a6 fused: MultiHeadAttention scores inside the MAGGC block kernels --------------------
+int gcgcn_block_supported(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t mha) {
+    if (bt == nullptr || layers < 1 || D % layers != 0) return 0;
+    return block_kernels_usable(bt, heads, layers, D, mha != 0) ? 1 : 0;
+}
+
+int gcgcn_mha_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, const float* x, const float* ebar,
+                        const float* Wq, const float* bq, const float* WnX, const float* We, const float* Winner,
+                        const float* Wout, const float* bout, float* q, float* P, float* Z, float* G, float* F,
+                        float* y, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(heads >= 1 && layers >= 1 && D % layers == 0, "mha_stack_fwd: bad heads/layers");
+    if (!block_kernels_usable(bt, heads, layers, D, true))
+        return fail(GCGCN_ERR_UNSUPPORTED, "mha_stack_fwd: needs documents of <= 64 nodes, 2 or 4 sub-layers and 4 or 8 "
+                    "heads (got max_nodes %d, layers %d, heads %d); use gcgcn_mha_fwd + gcgcn_graphconv_stack_fwd",
+                    bt->max_nodes, layers, heads);
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(ebar, "ebar"));
+    GCGCN_TRY(check_device_ptr(Wq, "Wq"));
+    GCGCN_TRY(check_device_ptr(WnX, "WnX"));
+    GCGCN_TRY(check_device_ptr(We, "We"));
+    GCGCN_TRY(check_device_ptr(Wout, "Wout"));
+    GCGCN_TRY(check_device_ptr(q, "q"));
+    GCGCN_TRY(check_device_ptr(P, "P"));
+    GCGCN_TRY(check_device_ptr(Z, "Z"));
+    GCGCN_TRY(check_device_ptr(G, "G"));
+    GCGCN_TRY(check_device_ptr(F, "F"));
+    GCGCN_TRY(check_device_ptr(y, "y"));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int HD = heads * slab, M = bt->total_nodes, gd = slab / layers;
+    GCGCN_TRY(launch_gemm(0, 1, bt->total_nodes, D, D, 1.f, x, D, Wq, D, 0.f, q, D, bq, ws, ws_bytes, st));
+    return stack_fwd_impl(bt, heads, layers, D, D, BLOCK_FLAGS_ALL, x, ebar, nullptr, q, P, WnX, We, Winner, Wout, bout,
+                          nullptr, Z, G, F, y, ws, ws_bytes, st);
+}
+
+int gcgcn_mha_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, const float* x, const float* ebar,
+                        const float* Wq, const float* WnX, const float* We, const float* Winner, const float* Wout,
+                        const float* q, const float* P, const float* Z, const float* G, const float* F,
+                        const float* dy, float* dx, float* debar, float* dWq, float* dbq, float* dWnX, float* dWe,
+                        float* dWinner, float* dWout, float* dbout, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(heads >= 1 && layers >= 1 && D % layers == 0, "mha_stack_bwd: bad heads/layers");
+    if (!block_kernels_usable(bt, heads, layers, D, true))
+        return fail(GCGCN_ERR_UNSUPPORTED, "mha_stack_bwd: unsupported configuration (see gcgcn_mha_stack_fwd)");
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(x, "node_feat"));
+    GCGCN_TRY(check_device_ptr(q, "q"));
+    GCGCN_TRY(check_device_ptr(P, "P"));
+    GCGCN_TRY(check_device_ptr(Z, "Z"));
+    GCGCN_TRY(check_device_ptr(G, "G"));
+    GCGCN_TRY(check_device_ptr(dy, "dy"));
+    GCGCN_TRY(check_device_ptr(dx, "dx"));
+    GCGCN_TRY(check_device_ptr(debar, "debar"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar(ws, ws_bytes);
-    float* dFbuf = linear ? ar.take<float>(static_cast<size_t>(M) * HD) : nullptr;
-    float* dZ = ar.take<float>(static_cast<size_t>(M) * HD);
-    float* dE = ar.take<float>(static_cast<size_t>(M) * HD);
-    float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
-    if ((linear && dFbuf == nullptr) || dZ == nullptr || dE == nullptr || gws == nullptr)
-        return fail(GCGCN_ERR_WORKSPACE, "stack_bwd: workspace too small");
-    const float* dF = dy;
-    if (linear) {
-        GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, dy, D, Wout, HD, 0.f, dFbuf, HD, nullptr, gws, GEMM_WS_BYTES, st));
-        if (dWout != nullptr)
-            GCGCN_TRY(launch_gemm(1, 0, D, HD, M, 1.f, dy, D, F, HD, 0.f, dWout, HD, nullptr, gws, GEMM_WS_BYTES, st));
-        if (dbout != nullptr) GCGCN_TRY(launch_colsum(dy, M, D, D, dbout, gws, GEMM_WS_BYTES, st));
-        dF = dFbuf;
-    }
-    GCGCN_TRY(launch_stack_bwd(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, dA, st));
-    // dx = [residual: sum_h dF_h] + dZ WnX^T ; debar = dE We^T
-    float beta = 0.f;
-    if (flags & GCGCN_STACK_RESIDUAL) {
-        GCGCN_TRY(launch_head_sum(dF, heads, M, dx, st));
-        beta = 1.f;
-    }
-    GCGCN_TRY(launch_gemm(0, 1, M, in_dim, HD, 1.f, dZ, HD, WnX, HD, beta, dx, in_dim, nullptr, gws, GEMM_WS_BYTES, st));
-    GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, dE, HD, We, HD, 0.f, debar, D, nullptr, gws, GEMM_WS_BYTES, st));
-    if (dWnX != nullptr)
-        GCGCN_TRY(launch_gemm(1, 0, in_dim, HD, M, 1.f, x, in_dim, dZ, HD, 0.f, dWnX, HD, nullptr, gws, GEMM_WS_BYTES, st));
-    if (dWe != nullptr)
-        GCGCN_TRY(launch_gemm(1, 0, D, HD, M, 1.f, ebar, D, dE, HD, 0.f, dWe, HD, nullptr, gws, GEMM_WS_BYTES, st));
-    if (dWinner != nullptr && layers > 1) {
-        GCGCN_TRY(cuda_ok(cudaMemsetAsync(dWinner, 0, static_cast<size_t>(heads) * layers * slab * gd * sizeof(float), st),
-                          "memset dWinner"));
-        // dWinner[h][l][m*g + k][c] = sum_rows G[row][h*S + m*g + k] * dZ[row][h*S + l*g + c],  m < l
-        // (all heads of one sub-layer in a single batched launch)
-        for (int l = 1; l < layers; ++l)
-            GCGCN_TRY(launch_gemm_batched(1, 0, l * gd, gd, M, 1.f, G, HD, dZ + l * gd, HD, 0.f,
-                                          dWinner + static_cast<size_t>(l) * slab * gd, gd, heads, slab, slab,
-                                          static_cast<long long>(layers) * slab * gd, gws, GEMM_WS_BYTES, st));
-    }
+    float* dq = ar.take<float>(static_cast<size_t>(bt->total_nodes) * D);
+    if (dq == nullptr) return fail(GCGCN_ERR_WORKSPACE, "mha_stack_bwd: workspace too small");
+    void* rest = static_cast<char*>(ws) + ar.off;
+    const size_t rest_bytes = ws_bytes - ar.off;
+    GCGCN_TRY(stack_bwd_impl(bt, heads, layers, D, D, BLOCK_FLAGS_ALL, ATT_GRAD_DQ, x, ebar, P, q, WnX, We, Winner, Wout,
+                             nullptr, Z, G, F, dy, dx, debar, dq, dWnX, dWe, dWinner, dWout, dbout, rest, rest_bytes, st));
+    // q = x Wq^T + bq :  dx += dq Wq ; dWq = dq^T x ; dbq = colsum(dq)
+    Arena ar2(rest, rest_bytes);
+    float* gws = ar2.take<float>(GEMM_WS_BYTES / sizeof(float));
+    if (gws == nullptr) return fail(GCGCN_ERR_WORKSPACE, "mha_stack_bwd: workspace too small");
+    GCGCN_TRY(launch_gemm(0, 0, bt->total_nodes, D, D, 1.f, dq, D, Wq, D, 1.f, dx, D, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dWq != nullptr)
+        GCGCN_TRY(launch_gemm(1, 0, D, D, bt->total_nodes, 1.f, dq, D, x, D, 0.f, dWq, D, nullptr, gws, GEMM_WS_BYTES, st));
+    if (dbq != nullptr) GCGCN_TRY(launch_colsum(dq, bt->total_nodes, D, D, dbq, gws, GEMM_WS_BYTES, st));
     return GCGCN_OK;
 }
 
@@ -654,12 +774,24 @@ int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const
         return fail(GCGCN_ERR_WORKSPACE, "caggc_bwd: workspace too small");
     void* rest = static_cast<char*>(ws) + ar.off;
     const size_t rest_bytes = ws_bytes - ar.off;
-    GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, nullptr,
-                                        s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner, dWout, dbout,
-                                        rest, rest_bytes, stream));
-    GCGCN_TRY(gcgcn_gat_bwd(bt, x, e, edge_dtype, u, v, nullptr, 0, nullptr, s.P, dA, debar, dx, de, du, dv, dc,
-                            rest, rest_bytes, stream));
-    return launch_add(dx, dx_stack, static_cast<size_t>(bt->total_nodes) * D, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (block_kernels_usable(bt, 1, layers, D, false)) {
+        // the block kernel finishes the softmax backward in shared memory: dA never exists in HBM
+        float* dS = dA;
+        GCGCN_API_ENTER(stream);
+        GCGCN_TRY(stack_bwd_impl(bt, 1, layers, D, D, BLOCK_FLAGS, ATT_GRAD_DS, x, s.ebar, s.P, nullptr, WnX, We, Winner,
+                                 Wout, nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dS, dWnX, dWe, dWinner, dWout, dbout,
+                                 rest, rest_bytes, st));
+        Arena ar2(rest, rest_bytes);
+        GCGCN_TRY(gat_bwd_from_ds(bt, x, e, edge_dtype, u, v, dS, debar, dx, de, du, dv, dc, ar2, st));
+    } else {
+        GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout,
+                                            nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner, dWout,
+                                            dbout, rest, rest_bytes, stream));
+        GCGCN_TRY(gcgcn_gat_bwd(bt, x, e, edge_dtype, u, v, nullptr, 0, nullptr, s.P, dA, debar, dx, de, du, dv, dc,
+                                rest, rest_bytes, stream));
+    }
+    return launch_add(dx, dx_stack, static_cast<size_t>(bt->total_nodes) * D, st);
 }
 
 int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x, const void* e,
@@ -670,6 +802,9 @@ int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     MagSaved s = carve_mag(saved, bt->total_nodes, bt->total_pairs, heads);
     GCGCN_TRY(gcgcn_edge_mean_fwd(bt, e, edge_dtype, s.ebar, stream));
+    if (block_kernels_usable(bt, heads, layers, D, true))
+        return gcgcn_mha_stack_fwd(bt, heads, layers, x, s.ebar, Wq, bq, WnX, We, Winner, Wout, bout, s.q, s.P, s.Z, s.G,
+                                   s.F, y, ws, ws_bytes, stream);
     GCGCN_TRY(gcgcn_mha_fwd(bt, heads, x, Wq, bq, nullptr, s.q, s.P, s.P, ws, ws_bytes, stream));
     return gcgcn_graphconv_stack_fwd(bt, heads, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, bout,
                                      nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, stream);
@@ -691,6 +826,11 @@ int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
         return fail(GCGCN_ERR_WORKSPACE, "maggc_bwd: workspace too small");
     void* rest = static_cast<char*>(ws) + ar.off;
     const size_t rest_bytes = ws_bytes - ar.off;
+    if (block_kernels_usable(bt, heads, layers, D, true)) {
+        GCGCN_TRY(gcgcn_mha_stack_bwd(bt, heads, layers, x, s.ebar, Wq, WnX, We, Winner, Wout, s.q, s.P, s.Z, s.G, s.F, dy,
+                                      dx, debar, dWq, dbq, dWnX, dWe, dWinner, dWout, dbout, rest, rest_bytes, stream));
+        return gcgcn_edge_mean_bwd(bt, debar, edge_dtype, de, stream);
+    }
     GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, heads, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout,
                                         nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner,
                                         dWout, dbout, rest, rest_bytes, stream));

@@ -234,6 +234,95 @@ class StackFn(Function):
         return (dx, debar, dA, dWnX, dWe, dWinner, dWout, dbout, None, None, None, None, None, None, None)
 
 
+# ------------------------------------------------------------------------------- fused blocks
+def block_supported(batch: RaggedBatch, heads: int, layers: int, mha: bool) -> bool:
+    """True when the (document, head) block kernels cover this batch (gcgcn_block_supported)."""
+    return bool(_lib.load().gcgcn_block_supported(batch.ref, heads, layers, int(mha)))
+
+
+class CaggcFn(Function):
+    """CAGGC block without dropout masks: GATAttention + GraphConvolution on one pass over e
+    (G:330-333) through gcgcn_caggc_fwd / gcgcn_caggc_bwd.  Returns (y, A) -- A is the GAT map."""
+
+    @staticmethod
+    def forward(ctx, x, e, u, v, c, WnX, We, Winner, Wout, bout, batch: RaggedBatch, layers: int):
+        x = _cuda(x, "node_feat")
+        e, dt = _edge(e, "edge_feat")
+        u, v, c = _cuda(u, "u"), _cuda(v, "v"), _cuda(c, "c")
+        WnX, We, Wout, bout = _cuda(WnX, "WnX"), _cuda(We, "We"), _cuda(Wout, "Wout"), _cuda(bout, "bout")
+        Winner = None if Winner is None else _cuda(Winner, "Winner")
+        dev = x.device
+        nb = _lib.load().gcgcn_block_saved_bytes(batch.total_nodes, batch.total_pairs, 1)
+        saved = torch.empty(int(nb), dtype=torch.uint8, device=dev)
+        y = torch.empty(batch.total_nodes, D, device=dev)
+        ws, wsb = _ws_for(batch, 1, dev)
+        _lib.call("gcgcn_caggc_fwd", batch.ref, layers, _p(x), _p(e), dt, _p(u), _p(v), _p(c), _p(WnX), _p(We),
+                  _p(Winner), _p(Wout), _p(bout), _p(y), _p(saved), ws, wsb, _stream(dev))
+        ctx.save_for_backward(x, e, u, v, WnX, We, Winner, Wout, saved)
+        ctx.cfg = (batch, layers, dt)
+        att = saved[: batch.total_pairs * 4].view(torch.float32)      # P is the first slab of the arena
+        ctx.mark_non_differentiable(att)
+        return y, att
+
+    @staticmethod
+    def backward(ctx, dy, _datt):
+        x, e, u, v, WnX, We, Winner, Wout, saved = ctx.saved_tensors
+        batch, layers, dt = ctx.cfg
+        dev = x.device
+        dy = _cuda(dy, "dy")
+        dx, de = torch.empty_like(x), torch.empty_like(e)
+        du, dv, dc = torch.empty(D, device=dev), torch.empty(D, device=dev), torch.empty(1, device=dev)
+        dWnX, dWe, dWout = torch.empty_like(WnX), torch.empty_like(We), torch.empty_like(Wout)
+        dWinner = None if Winner is None else torch.empty_like(Winner)
+        dbout = torch.empty(D, device=dev)
+        ws, wsb = _ws_for(batch, 1, dev)
+        _lib.call("gcgcn_caggc_bwd", batch.ref, layers, _p(x), _p(e), dt, _p(u), _p(v), _p(WnX), _p(We), _p(Winner),
+                  _p(Wout), _p(dy), _p(saved), _p(dx), _p(de), _p(du), _p(dv), _p(dc), _p(dWnX), _p(dWe),
+                  _p(dWinner), _p(dWout), _p(dbout), ws, wsb, _stream(dev))
+        return dx, de, du, dv, dc.reshape(()), dWnX, dWe, dWinner, dWout, dbout, None, None
+
+
+class MhaStackFn(Function):
+    """MultiHeadAttention + MultiGraphConvolution without dropout masks (G:336-337) with the attention
+    softmax, its backward and dq inside the block kernels.  Returns (y, P [H, total_pairs])."""
+
+    @staticmethod
+    def forward(ctx, x, ebar, Wq, bq, WnX, We, Winner, Wout, bout, batch: RaggedBatch, heads: int, layers: int):
+        x, ebar = _cuda(x, "node_feat"), _cuda(ebar, "ebar")
+        Wq, bq = _cuda(Wq, "Wq"), _cuda(bq, "bq")
+        WnX, We, Wout, bout = _cuda(WnX, "WnX"), _cuda(We, "We"), _cuda(Wout, "Wout"), _cuda(bout, "bout")
+        Winner = None if Winner is None else _cuda(Winner, "Winner")
+        dev, M, HD = x.device, batch.total_nodes, heads * D
+        q = torch.empty(M, D, device=dev)
+        P = torch.empty(heads, batch.total_pairs, device=dev)
+        Z, G, F = (torch.empty(M, HD, device=dev) for _ in range(3))
+        y = torch.empty(M, D, device=dev)
+        ws, wsb = _ws_for(batch, heads, dev)
+        _lib.call("gcgcn_mha_stack_fwd", batch.ref, heads, layers, _p(x), _p(ebar), _p(Wq), _p(bq), _p(WnX), _p(We),
+                  _p(Winner), _p(Wout), _p(bout), _p(q), _p(P), _p(Z), _p(G), _p(F), _p(y), ws, wsb, _stream(dev))
+        ctx.save_for_backward(x, ebar, Wq, WnX, We, Winner, Wout, q, P, Z, G, F)
+        ctx.cfg = (batch, heads, layers)
+        ctx.mark_non_differentiable(P)
+        return y, P
+
+    @staticmethod
+    def backward(ctx, dy, _dP):
+        x, ebar, Wq, WnX, We, Winner, Wout, q, P, Z, G, F = ctx.saved_tensors
+        batch, heads, layers = ctx.cfg
+        dev = x.device
+        dy = _cuda(dy, "dy")
+        dx, debar = torch.empty_like(x), torch.empty_like(ebar)
+        dWq, dbq = torch.empty_like(Wq), torch.empty(D, device=dev)
+        dWnX, dWe, dWout = torch.empty_like(WnX), torch.empty_like(We), torch.empty_like(Wout)
+        dWinner = None if Winner is None else torch.empty_like(Winner)
+        dbout = torch.empty(D, device=dev)
+        ws, wsb = _ws_for(batch, heads, dev)
+        _lib.call("gcgcn_mha_stack_bwd", batch.ref, heads, layers, _p(x), _p(ebar), _p(Wq), _p(WnX), _p(We),
+                  _p(Winner), _p(Wout), _p(q), _p(P), _p(Z), _p(G), _p(F), _p(dy), _p(dx), _p(debar), _p(dWq),
+                  _p(dbq), _p(dWnX), _p(dWe), _p(dWinner), _p(dWout), _p(dbout), ws, wsb, _stream(dev))
+        return dx, debar, dWq, dbq, dWnX, dWe, dWinner, dWout, dbout, None, None, None
+
+
 # ------------------------------------------------------------------------------- parameter packing
 _PTR_TABLES: dict = {}
 

@@ -25,7 +25,8 @@ from torch import nn
 
 from . import _lib
 from .batch import PairTables, PoolTable, RaggedBatch, single_doc_batch
-from .functional import EdgeMeanFn, GatFn, MhaFn, PackStackFn, PairGatherFn, PoolFn, StackFn
+from .functional import (CaggcFn, EdgeMeanFn, GatFn, MhaFn, MhaStackFn, PackStackFn, PairGatherFn, PoolFn, StackFn,
+                         block_supported)
 
 HIDDEN = 128
 
@@ -316,6 +317,9 @@ class GraphBlocks(nn.Module, _KeepMixin):
         # overlap: stream the hop-1 edge tensor (mean forward, broadcast-write backward: pure HBM work)
         # on a side stream while the CAGGC block (tensor-core / latency-bound work) runs on the main one
         self.overlap = overlap
+        # fused: route dropout-free passes through the block-level C-ABI entry points (gcgcn_caggc_*,
+        # gcgcn_mha_stack_*) whose kernels keep the attention maps and their gradients on chip
+        self.fused = True
         self._side = {}
         if graph_hop != 2:
             raise _lib.GcgcnError("graph_hop = 2 (config/Config.py:71) is the only supported depth")
@@ -345,15 +349,33 @@ class GraphBlocks(nn.Module, _KeepMixin):
             with torch.cuda.stream(side):
                 ebar1 = EdgeMeanFn.apply(e1, batch)
             ebar1.record_stream(main)
-        a0, ebar0 = self.get_weighted_adj_matrix.forward_batched(x0, e0, batch, mask)   # G:332
-        new = self.graphcnn[0].forward_batched(x0, ebar0, a0.view(1, -1), batch)        # G:333
+        gat, mha = self.get_weighted_adj_matrix, self.get_adj_matrix[0]
+        cag, mag = self.graphcnn
+        # no dropout mask to inject into the kernels: use the block-level entry points
+        plain = not (self._dropping() or gat._dropping() or mha._dropping() or cag._dropping() or mag._dropping())
+        if plain and self.fused and not gat.apply_mask:
+            u, v, c = gat.collapse()
+            wn_x, w_e, winner = _pack_stack(cag.graphconv, 1, cag.layer_num, cag._g)
+            new, a0 = CaggcFn.apply(x0, e0, u, v, c, wn_x, w_e, winner, cag.linear_layer.weight,
+                                    cag.linear_layer.bias, batch, cag.layer_num)                # G:332-333
+        else:
+            a0, ebar0 = gat.forward_batched(x0, e0, batch, mask)                                # G:332
+            new = cag.forward_batched(x0, ebar0, a0.view(1, -1), batch)                         # G:333
         y1 = self._blend(new, x0)
-        a1 = self.get_adj_matrix[0].forward_batched(y1, batch)                          # G:336
+        fuse_mha = plain and self.fused and block_supported(batch, mag.head_num, mag.layer_num, True)
+        a1 = None if fuse_mha else mha.forward_batched(y1, batch)                               # G:336
         if ebar1 is None:
             ebar1 = EdgeMeanFn.apply(e1, batch)
         else:
             torch.cuda.current_stream(e1.device).wait_stream(self._side[e1.device])
-        new = self.graphcnn[1].forward_batched(y1, ebar1, a1, batch)                    # G:337
+        if fuse_mha:
+            wq = torch.cat([l.weight for l in mha.linears_q], 0)
+            bq = torch.cat([l.bias for l in mha.linears_q], 0)
+            wn_x, w_e, winner = _pack_stack(mag.graphconv, mag.head_num, mag.layer_num, mag._g)
+            new, a1 = MhaStackFn.apply(y1, ebar1, wq, bq, wn_x, w_e, winner, mag.linear_layer.weight,
+                                       mag.linear_layer.bias, batch, mag.head_num, mag.layer_num)  # G:336-337
+        else:
+            new = mag.forward_batched(y1, ebar1, a1, batch)                                     # G:337
         y2 = self._blend(new, y1)
         return {"y1": y1, "y2": y2, "a0": a0, "a1": a1, "node_feats": torch.cat([x0, x0, y1], 1)}
 

@@ -167,6 +167,33 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
                               float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
                               void* ws, size_t ws_bytes, void* stream);
 
+/* ---- a5 + a6 fused: MultiHeadAttention inside the MAGGC block kernels (G:133-142 + G:97-120) ----
+ * Inference / no-dropout form of  adj = MultiHeadAttention(x) ; y = MultiGraphConvolution(x, e, adj)
+ * (the reference's call pair at G:336-337) for documents of <= 64 entities, layer_num 2 or 4 and
+ * head_num 4 or 8 -- gcgcn_block_supported(bt, heads, layers, 1) says whether a batch qualifies
+ * (mha = 0 asks the same for a given attention map, i.e. the CAGGC block).  The softmax of
+ * q_h q_h^T / sqrt(d_h) is taken inside the per-(document, head) kernel that consumes it and, in the
+ * backward, the softmax gradient and dq are finished there too: no [H][sum n^2] array is re-read.
+ * q [total_nodes,128] and P [heads][total_pairs] are outputs of fwd (saved for bwd; P is the
+ * attention list the reference would return); Z, G, F, dx, debar and the parameter gradients are as
+ * in gcgcn_graphconv_stack_*.  ebar = gcgcn_edge_mean_fwd(e); the caller sends debar through
+ * gcgcn_edge_mean_bwd.                                                                        */
+int gcgcn_block_supported(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t mha);
+int gcgcn_mha_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers,
+                        const float* x, const float* ebar, const float* Wq, const float* bq,
+                        const float* WnX, const float* We, const float* Winner,
+                        const float* Wout, const float* bout,
+                        float* q, float* P, float* Z, float* G, float* F, float* y,
+                        void* ws, size_t ws_bytes, void* stream);
+int gcgcn_mha_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers,
+                        const float* x, const float* ebar, const float* Wq,
+                        const float* WnX, const float* We, const float* Winner, const float* Wout,
+                        const float* q, const float* P, const float* Z, const float* G,
+                        const float* F, const float* dy,
+                        float* dx, float* debar, float* dWq, float* dbq,
+                        float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* ---- parameter packing for the stack entry points ----------------------------------------
  * The reference keeps one weights_node [128 + l*g, g] and one weights_edge [128, g] per GraphConv
  * (G:24-25, heads*layers of them).  pack gathers them (device arrays of heads*layers device pointers,

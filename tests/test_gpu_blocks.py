@@ -13,10 +13,12 @@ from gcgcn_b200.batch import RaggedBatch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["block-kernels", "per-op"])
 @pytest.mark.parametrize("variant", list(VARIANTS))
-def test_batched_blocks_match_oracle_and_reference_golden(variant):
+def test_batched_blocks_match_oracle_and_reference_golden(variant, fused):
     layers, heads = VARIANTS[variant]
     gb, state = device_blocks(layers, heads)
+    gb.fused = fused      # True: gcgcn_caggc_* / gcgcn_mha_stack_* (attention on chip); False: one entry point per op
     docs = S.make_batch()
     before = _lib.launch_count()
     res = run_blocks(gb, docs)
