@@ -40,64 +40,78 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Row softmax of the MHA scores of one (document, head): one warp per row, scores parked in the row of
-// the shared attention tile they will occupy.  Writes P (global, rows < n), the zero-padded tile and the
-// reciprocal row normalisers 1 / (rowsum + [rowsum == 0])  (G:47-49).
-template <int DH>
-__device__ __forceinline__ void mha_rows(const float* __restrict__ qs, float* __restrict__ As, float* __restrict__ rs,
-                                         float* __restrict__ Pg, int n, int NP, int LDA, float scale) {
-    constexpr int LQ = DH + 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < NP; i += BK_WARPS) {
-        float* row = As + i * LDA;
-        if (i >= n) {
-            for (int j = lane; j < NP; j += WARP) row[j] = 0.f;
-            if (lane == 0) rs[i] = 1.f;
-            continue;
-        }
-        float qi[DH];
-#pragma unroll
-        for (int k = 0; k < DH; ++k) qi[k] = qs[i * LQ + k];
-        float m = -INFINITY;
-        for (int j = lane; j < n; j += WARP) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < DH; ++k) s += qi[k] * qs[j * LQ + k];
-            s *= scale;
-            row[j] = s;
-            m = fmaxf(m, s);
-        }
-        m = warp_max(m);
-        float z = 0.f;
-        for (int j = lane; j < n; j += WARP) {
-            const float ex = expf(row[j] - m);
-            row[j] = ex;
-            z += ex;
-        }
-        z = warp_sum(z);
-        float sum = 0.f;
-        for (int j = lane; j < NP; j += WARP) {
-            float p = 0.f;
-            if (j < n) {
-                p = row[j] / z;
-                Pg[static_cast<size_t>(i) * n + j] = p;
-            }
-            row[j] = p;
-            sum += p;
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) rs[i] = 1.0f / (sum + (sum == 0.f ? 1.f : 0.f));
-    }
+// ---- operand planes and fragment loads -----------------------------------------------------
+// Every MMA operand that several warps read lives in shared memory already split into a TF32-exact "hi"
+// plane and an fp32 "lo = x - hi" plane (the split is paid once per element, not once per fragment use),
+// with rows of stride == 4 (mod 8) words so that ldmatrix -- whose 8x8 b16 tile is an 8x4 tile of 32-bit
+// words, exactly one m16n8k8 TF32 fragment register per lane -- is bank-conflict free.
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const float* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(s_addr(p))
+                 : "memory");
 }
+__device__ __forceinline__ void split_f(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
+}
+__device__ __forceinline__ void split_f4(const float4 v, float4& hi, float4& lo) {
+    split_f(v.x, hi.x, lo.x); split_f(v.y, hi.y, lo.y); split_f(v.z, hi.z, lo.z); split_f(v.w, hi.w, lo.w);
+}
+// c += a b  with  a = ah + al, b = bh + bl  (3xTF32: the lo*lo term is below fp32 resolution)
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                     uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    const uint32_t bh[2] = {bh0, bh1}, bl[2] = {bl0, bl1};
+    mma_tf32(c, al, bh);
+    mma_tf32(c, ah, bl);
+    mma_tf32(c, ah, bh);
+}
+__device__ __forceinline__ void mma3f(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0,
+                                      float b1) {
+    float h0, l0, h1, l1;
+    split_f(b0, h0, l0);
+    split_f(b1, h1, l1);
+    mma3(c, ah, al, __float_as_uint(h0), __float_as_uint(h1), __float_as_uint(l0), __float_as_uint(l1));
+}
+__device__ __forceinline__ float group8_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+__device__ __forceinline__ float group8_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    return v;
+}
+
+// Per-lane geometry shared by both kernels.
+//   ldmatrix A fragment (16 rows x 8 k): lane supplies row a_row, k offset a_col of the tile
+//   ldmatrix B fragment, operand stored [n][k] (hi and lo planes in one x4): row b_row, k offset b_col, plane b_lo
+//   row-wise passes: 8 lanes per attention row (4 rows per warp, 32 per CTA pass), lane l8 takes columns l8 + 8r
+struct LaneGeo {
+    int warp, lane, g, t, a_row, a_col, b_row, b_col, b_lo, l8, rsub;
+    __device__ __forceinline__ LaneGeo() {
+        warp = threadIdx.x >> 5; lane = threadIdx.x & 31;
+        g = lane >> 2; t = lane & 3;
+        a_row = (lane & 7) + ((lane >> 3) & 1) * 8; a_col = (lane >> 4) * 4;
+        b_row = lane & 7; b_col = ((lane >> 3) & 1) * 4; b_lo = lane >> 4;
+        l8 = lane & 7; rsub = warp * 4 + (lane >> 3);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // DH = 0: attention map given in A.  DH > 0: MHA scores from the head slice of q (width DH); P is written.
-template <int GD, int DH>
+// MTC = size class: every document of the launch is padded to NP = 16 MTC rows (compile-time strides, fully
+// unrolled tile loops -- with run-time strides the integer address arithmetic outweighed the MMAs 4:1).
+template <int GD, int DH, int MTC>
 __global__ void __launch_bounds__(BK_THREADS, 3)
 block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
                  const float* __restrict__ A, const float* __restrict__ q, float* __restrict__ P,
                  float* __restrict__ Z, const float* __restrict__ E, const float* __restrict__ Winner,
-                 const float* __restrict__ x, float* __restrict__ G, float* __restrict__ F, int layers, int heads,
+                 const float* __restrict__ x, float* __restrict__ G, float* __restrict__ F, int heads,
                  long long total_pairs, const int* __restrict__ doc_order, int first, float scale) {
     extern __shared__ __align__(16) float smem[];
     const int b = doc_order != nullptr ? doc_order[first + blockIdx.x] : blockIdx.x;
@@ -105,27 +119,36 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
-    constexpr int S = D, LDZ = GD + 8, CG = GD / 4, NGU = GD / 16;
-    const int HD = heads * S, KI = (layers - 1) * GD;
-    const int NP = (n + 15) & ~15, MT = NP / 16;
-    const int LDA = NP + 4, LDG = KI + 4;
+    // NTW column tiles of 8; warp -> (column tile wnt, row-tile group wmg); at most MTW row tiles per warp
+    constexpr int S = D, layers = D / GD, LDZ = GD + 8, CG = GD / 4, NTW = GD / 8, MG = BK_WARPS / NTW;
+    constexpr int MTW = (MTC + MG - 1) / MG, DHH = DH > 0 ? DH : 8;
+    constexpr int NP = 16 * MTC, MT = MTC, NT8 = 2 * MTC, LDA = NP + 4, KI = (layers - 1) * GD, LDG = KI + 4;
+    const int HD = DH > 0 ? (D / DHH) * S : heads * S;
 
-    float* As = smem;                  // [NP][LDA]   attention map, zero padded
-    float* Zs0 = As + NP * LDA;        // [2][NP][LDZ] ring of projection tiles Zx_l (-> Z_l in place)
-    float* Gs = Zs0 + 2 * NP * LDZ;    // [NP][LDG]   g_0 .. g_{L-2}
-    float* rs = Gs + NP * LDG;         // [NP]        reciprocal row normalisers
-    float* qs = Gs;                    // [n][DH+1]   head slice of q, dead before the first g_l is written
+    float* Ahi = smem;                 // [NP][LDA]    attention map, zero padded, hi plane
+    float* Alo = Ahi + NP * LDA;       // [NP][LDA]    lo plane (scratch for the raw scores before the softmax)
+    float* Zs0 = Alo + NP * LDA;       // [2][NP][LDZ] ring of projection tiles Zx_l (-> Z_l in place), fp32
+    float* Ghi = Zs0 + 2 * NP * LDZ;   // [NP][LDG]    g_0 .. g_{L-2}, hi plane
+    float* Glo = Ghi + NP * LDG;       // [NP][LDG]    lo plane
+    float* rs = Glo + NP * LDG;        // [NP]         reciprocal row normalisers
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x;
+    const LaneGeo L;
+    const int wnt = L.warp % NTW, wmg = L.warp / NTW;
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const size_t hbase = static_cast<size_t>(node0) * HD + h * S;       // + i*HD + l*GD + col  (32-bit offsets)
+    const float* zsrc = Z + hbase;
+    const float* Eb = E + hbase;
+    float* Gb = G + hbase;
+    float* Fb = F + hbase;
+    const float* xb = x + static_cast<size_t>(node0) * S;
 
     auto issue_z = [&](int l) {        // rows < n of the x-part projection of sub-layer l -> ring slot l & 1
         float* dst = Zs0 + (l & 1) * NP * LDZ;
-        const float* src = Z + static_cast<size_t>(node0) * HD + static_cast<size_t>(h) * S + l * GD;
+        const float* src = zsrc + l * GD;
         for (int idx = tid; idx < n * CG; idx += BK_THREADS) {
             const int i = idx / CG, c4 = (idx - i * CG) * 4;
-            cp_async16(dst + i * LDZ + c4, src + static_cast<size_t>(i) * HD + c4);
+            cp_async16(dst + i * LDZ + c4, src + i * HD + c4);
         }
     };
     issue_z(0);
@@ -137,102 +160,203 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         Zs0[n * LDZ + idx] = 0.f;
         Zs0[NP * LDZ + n * LDZ + idx] = 0.f;
     }
-    for (int idx = tid; idx < (NP - n) * LDG; idx += BK_THREADS) Gs[n * LDG + idx] = 0.f;
 
     if (DH > 0) {
-        constexpr int LQ = DH + 1, Q4 = (DH > 0 ? DH : 4) / 4;
-        for (int idx = tid; idx < n * Q4; idx += BK_THREADS) {
+        // ---- MHA scores on the tensor cores: S = scale q_h q_h^T (fp32 via 3xTF32) -> Alo ----
+        constexpr int LQ = DHH + 4, Q4 = DHH / 4;
+        float* qh = Ghi;               // [NP][LQ] hi / lo planes of the head slice of q; dead before g_0 exists
+        float* ql = Glo;
+        for (int idx = tid; idx < NP * Q4; idx += BK_THREADS) {
             const int j = idx / Q4, k4 = (idx - j * Q4) * 4;
-            const float4 v = ld4g(q + static_cast<size_t>(node0 + j) * D + h * DH + k4);
-            float* d = qs + j * LQ + k4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+            if (j < n) v = ld4g(q + static_cast<size_t>(node0 + j) * D + h * DHH + k4);
+            split_f4(v, hi, lo);
+            *reinterpret_cast<float4*>(qh + j * LQ + k4) = hi;
+            *reinterpret_cast<float4*>(ql + j * LQ + k4) = lo;
         }
         __syncthreads();
-        mha_rows<(DH > 0 ? DH : 4)>(qs, As, rs, P + abase, n, NP, LDA, scale);
-    } else {
-        const float* Ab = A + abase;
-        for (int i = warp; i < NP; i += BK_WARPS) {
-            float s = 0.f;
-            for (int j = lane; j < NP; j += WARP) {
-                const float v = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
-                As[i * LDA + j] = v;
-                s += v;
+        for (int u = L.warp; u < MT * NT8; u += BK_WARPS) {
+            const int mt = u / NT8, nt = u - mt * NT8;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* pa = qh + (16 * mt + L.a_row) * LQ + L.a_col;
+            const float* pb = (L.b_lo ? ql : qh) + (8 * nt + L.b_row) * LQ + L.b_col;
+#pragma unroll
+            for (int k0 = 0; k0 < DHH; k0 += 8) {
+                uint32_t ah[4], al[4], bb[4];
+                ldsm4(ah, pa + k0);
+                ldsm4(al, pa + NP * LDG + k0);
+                ldsm4(bb, pb + k0);
+                mma3(c, ah, al, bb[0], bb[1], bb[2], bb[3]);
             }
-            s = warp_sum(s);
-            if (lane == 0) rs[i] = 1.0f / (s + (s == 0.f ? 1.f : 0.f));
+            float* srow = Alo + (16 * mt + L.g) * LDA + 8 * nt + 2 * L.t;
+            *reinterpret_cast<float2*>(srow) = make_float2(c[0] * scale, c[1] * scale);
+            *reinterpret_cast<float2*>(srow + 8 * LDA) = make_float2(c[2] * scale, c[3] * scale);
         }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < (NP - n) * LDG; idx += BK_THREADS) {   // padding rows of the g planes (q is dead now)
+        Ghi[n * LDG + idx] = 0.f;
+        Glo[n * LDG + idx] = 0.f;
+    }
+    // ---- attention rows: softmax (MHA) or load (given), hi/lo planes, reciprocal row normalisers (G:47-49) ----
+#pragma unroll
+    for (int r0 = 0; r0 < NP; r0 += 32) {
+        const int i = r0 + L.rsub;
+        if (i >= NP) continue;         // warp-uniform: a warp owns 4 consecutive rows, NP is a multiple of 16
+        const bool rv = i < n;
+        float v[8];
+        float m = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int j = L.l8 + 8 * r;
+            v[r] = -INFINITY;
+            if (r < NT8 && rv && j < n) {
+                v[r] = DH > 0 ? Alo[i * LDA + j] : A[abase + static_cast<long long>(i) * n + j];
+                m = fmaxf(m, v[r]);
+            }
+        }
+        float inv = 1.f;
+        if (DH > 0) {
+            m = group8_max(m);
+            float z = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                v[r] = (v[r] == -INFINITY) ? 0.f : __expf(v[r] - m);
+                z += v[r];
+            }
+            z = group8_sum(z);
+            inv = rv ? 1.0f / z : 0.f;
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int j = L.l8 + 8 * r;
+            if (r < NT8) {
+                float p = 0.f;
+                if (rv && j < n) {
+                    p = v[r] * inv;
+                    if (DH > 0) P[abase + static_cast<long long>(i) * n + j] = p;
+                }
+                float hi, lo;
+                split_f(p, hi, lo);
+                Ahi[i * LDA + j] = hi;
+                Alo[i * LDA + j] = lo;
+                sum += p;
+            }
+        }
+        sum = group8_sum(sum);
+        if (L.l8 == 0) rs[i] = 1.0f / (sum + (sum == 0.f ? 1.f : 0.f));
     }
 
+#pragma unroll
     for (int l = 0; l < layers; ++l) {
         float* Zs = Zs0 + (l & 1) * NP * LDZ;
         const int kin = l * GD;
-        const size_t colbase = static_cast<size_t>(h) * S + l * GD;
         cp_async_wait<1>();            // this thread's copies of tile l have landed ...
-        __syncthreads();               // ... and everyone's; also publishes As/rs (l = 0) and g_{l-1} (l > 0)
+        __syncthreads();               // ... and everyone's; also publishes the attention planes / g_{l-1}
+        float c[MTW][4];
+        float* zc = Zs + L.g * LDZ + 8 * wnt + 2 * L.t;               // this lane's C-fragment corner in the tile
         if (l > 0) {
             // Z_l += g_{<l} Winner_l   (dense connection, row-local in the reference: G:72-73)
-            const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
-            for (int u = warp; u < MT * NGU; u += BK_WARPS) {
-                const int mt = u / NGU, ng = u - mt * NGU;
-                float c[2][4];
-                float* zc = Zs + (16 * mt) * LDZ + 16 * ng;
+            const float* wb = Winner + (static_cast<size_t>(h) * layers + l) * S * GD + L.t * GD + 8 * wnt + L.g;
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const float2 lo = *reinterpret_cast<const float2*>(zc + g * LDZ + 8 * nt + 2 * t);
-                    const float2 hi = *reinterpret_cast<const float2*>(zc + (g + 8) * LDZ + 8 * nt + 2 * t);
-                    c[nt][0] = lo.x; c[nt][1] = lo.y; c[nt][2] = hi.x; c[nt][3] = hi.y;
+            for (int r = 0; r < MTW; ++r) {
+                const int mt = wmg + MG * r;
+                if (mt < MT) {
+                    const float2 lo2 = *reinterpret_cast<const float2*>(zc + 16 * mt * LDZ);
+                    const float2 hi2 = *reinterpret_cast<const float2*>(zc + (16 * mt + 8) * LDZ);
+                    c[r][0] = lo2.x; c[r][1] = lo2.y; c[r][2] = hi2.x; c[r][3] = hi2.y;
                 }
-                warp_gemm<2, false>(c, kin / 8, Gs + (16 * mt) * LDG, LDG, wsrc + 16 * ng, GD);
+            }
+#pragma unroll 4
+            for (int k0 = 0; k0 < kin; k0 += 8) {
+                const float b0 = __ldg(wb + k0 * GD), b1 = __ldg(wb + (k0 + 4) * GD);
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    *reinterpret_cast<float2*>(zc + g * LDZ + 8 * nt + 2 * t) = make_float2(c[nt][0], c[nt][1]);
-                    *reinterpret_cast<float2*>(zc + (g + 8) * LDZ + 8 * nt + 2 * t) = make_float2(c[nt][2], c[nt][3]);
+                for (int r = 0; r < MTW; ++r) {
+                    const int mt = wmg + MG * r;
+                    if (mt < MT) {
+                        uint32_t ah[4], al[4];
+                        const float* pa = Ghi + (16 * mt + L.a_row) * LDG + k0 + L.a_col;
+                        ldsm4(ah, pa);
+                        ldsm4(al, pa + NP * LDG);
+                        mma3f(c[r], ah, al, b0, b1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MTW; ++r) {
+                const int mt = wmg + MG * r;
+                if (mt < MT) {
+                    *reinterpret_cast<float2*>(zc + 16 * mt * LDZ) = make_float2(c[r][0], c[r][1]);
+                    *reinterpret_cast<float2*>(zc + (16 * mt + 8) * LDZ) = make_float2(c[r][2], c[r][3]);
                 }
             }
             __syncthreads();
             for (int idx = tid; idx < n * CG; idx += BK_THREADS) {       // final Z_l, saved for backward
                 const int i = idx / CG, c4 = (idx - i * CG) * 4;
-                *reinterpret_cast<float4*>(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4) =
+                *reinterpret_cast<float4*>(Z + hbase + (i * HD + kin + c4)) =
                     *reinterpret_cast<const float4*>(Zs + i * LDZ + c4);
             }
         }
         // out = (E + P Z_l) / r ; g_l = relu(out) ; F_l = g_l + x_l
-        for (int u = warp; u < MT * NGU; u += BK_WARPS) {
-            const int mt = u / NGU, ng = u - mt * NGU;
-            // epilogue operands first: their latency hides behind the MMA loop
-            float2 e2[2][2], x2[2][2];
+        // epilogue operands first: their latency hides behind the MMA loop
+        float2 e2[MTW][2], x2[MTW][2];
+#pragma unroll
+        for (int r = 0; r < MTW; ++r) {
+            const int mt = wmg + MG * r;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int i = 16 * mt + g + 8 * half;
+                const int i = 16 * mt + L.g + 8 * half;
+                e2[r][half] = make_float2(0.f, 0.f);
+                x2[r][half] = make_float2(0.f, 0.f);
+                if (mt < MT && i < n) {
+                    const int col = 8 * wnt + 2 * L.t;
+                    e2[r][half] = ld2g(Eb + (i * HD + kin + col));
+                    x2[r][half] = ld2g(xb + (i * S + kin + col));
+                }
+            }
+        }
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const int col = 16 * ng + 8 * nt + 2 * t;
-                    e2[half][nt] = make_float2(0.f, 0.f);
-                    x2[half][nt] = make_float2(0.f, 0.f);
-                    if (i < n) {
-                        e2[half][nt] = ld2g(E + static_cast<size_t>(node0 + i) * HD + colbase + col);
-                        x2[half][nt] = ld2g(x + static_cast<size_t>(node0 + i) * S + l * GD + col);
+        for (int r = 0; r < MTW; ++r) { c[r][0] = 0.f; c[r][1] = 0.f; c[r][2] = 0.f; c[r][3] = 0.f; }
+        {
+            const float* zb = Zs + L.t * LDZ + 8 * wnt + L.g;
+#pragma unroll
+            for (int k0 = 0; k0 < NP; k0 += 8) {
+                const float b0 = zb[k0 * LDZ], b1 = zb[(k0 + 4) * LDZ];
+#pragma unroll
+                for (int r = 0; r < MTW; ++r) {
+                    const int mt = wmg + MG * r;
+                    if (mt < MT) {
+                        uint32_t ah[4], al[4];
+                        const float* pa = Ahi + (16 * mt + L.a_row) * LDA + k0 + L.a_col;
+                        ldsm4(ah, pa);
+                        ldsm4(al, pa + NP * LDA);
+                        mma3f(c[r], ah, al, b0, b1);
                     }
                 }
             }
-            float c[2][4];
-            zero_frag<2>(c);
-            warp_gemm<2, false>(c, NP / 8, As + (16 * mt) * LDA, LDA, Zs + 16 * ng, LDZ);
+        }
+#pragma unroll
+        for (int r = 0; r < MTW; ++r) {
+            const int mt = wmg + MG * r;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int i = 16 * mt + g + 8 * half;
-                if (i >= n) continue;
+                const int i = 16 * mt + L.g + 8 * half;
+                if (mt >= MT || i >= n) continue;
                 const float rinv = rs[i];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const int col = 16 * ng + 8 * nt + 2 * t;
-                    const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + col;
-                    float2 o;
-                    o.x = fmaxf((e2[half][nt].x + c[nt][2 * half]) * rinv, 0.f);
-                    o.y = fmaxf((e2[half][nt].y + c[nt][2 * half + 1]) * rinv, 0.f);
-                    *reinterpret_cast<float2*>(G + off) = o;
-                    if (l < layers - 1) *reinterpret_cast<float2*>(Gs + i * LDG + kin + col) = o;
-                    *reinterpret_cast<float2*>(F + off) = make_float2(o.x + x2[half][nt].x, o.y + x2[half][nt].y);
+                const int col = 8 * wnt + 2 * L.t;
+                const int off = i * HD + kin + col;
+                float2 o;
+                o.x = fmaxf((e2[r][half].x + c[r][2 * half]) * rinv, 0.f);
+                o.y = fmaxf((e2[r][half].y + c[r][2 * half + 1]) * rinv, 0.f);
+                *reinterpret_cast<float2*>(Gb + off) = o;
+                *reinterpret_cast<float2*>(Fb + off) = make_float2(o.x + x2[r][half].x, o.y + x2[r][half].y);
+                if (l < layers - 1) {
+                    float2 hi, lo;
+                    split_f(o.x, hi.x, lo.x);
+                    split_f(o.y, hi.y, lo.y);
+                    *reinterpret_cast<float2*>(Ghi + i * LDG + kin + col) = hi;
+                    *reinterpret_cast<float2*>(Glo + i * LDG + kin + col) = lo;
                 }
             }
         }
@@ -247,12 +371,12 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 // OUT = BK_OUT_DA: dA (head-major, like A) is written and the softmax backward is left to the caller.
 // OUT = BK_OUT_DS: A is a softmax output; dS = A (dA - rowsum(dA A)) is written instead (GAT, one head).
 // OUT = BK_OUT_DQ: as DS, then dq_h = scale (dS + dS^T) q_h is written to the head slice of dq [rows][128].
-template <int GD, int DH, int OUT>
+template <int GD, int DH, int OUT, int MTC>
 __global__ void __launch_bounds__(BK_THREADS, 3)
 block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
                  const float* __restrict__ A, const float* __restrict__ q, const float* __restrict__ Z,
                  const float* __restrict__ G, const float* __restrict__ Winner, const float* __restrict__ dF,
-                 float* __restrict__ dZ, float* __restrict__ dE, float* __restrict__ dOut, int layers, int heads,
+                 float* __restrict__ dZ, float* __restrict__ dE, float* __restrict__ dOut, int heads,
                  long long total_pairs, const int* __restrict__ doc_order, int first, float scale) {
     extern __shared__ __align__(16) float smem[];
     const int b = doc_order != nullptr ? doc_order[first + blockIdx.x] : blockIdx.x;
@@ -260,49 +384,65 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
-    constexpr int S = D, LDN = GD + 12, CG = GD / 4, RPP = BK_THREADS / CG, NGU = GD / 16;
-    const int HD = heads * S, KI = (layers - 1) * GD;
-    const int NP = (n + 15) & ~15, MT = NP / 16, NT8 = NP / 8;
-    const int LDA = NP + 4, LDG = KI + 4;
+    constexpr int S = D, layers = D / GD, LDN = GD + 12, CG = GD / 4, RPP = BK_THREADS / CG;
+    constexpr int NTW = GD / 8, MG = BK_WARPS / NTW, MTW = (MTC + MG - 1) / MG, DHH = DH > 0 ? DH : 8;
+    constexpr int NP = 16 * MTC, MT = MTC, NT8 = 2 * MTC, LDA = NP + 4, KI = (layers - 1) * GD, LDG = KI + 4;
+    const int HD = DH > 0 ? (D / DHH) * S : heads * S;
 
-    float* Ats = smem;                 // [NP][LDA]  A transposed: Ats[j][i] = A[i][j]
-    float* dAs = Ats + NP * LDA;       // [NP][LDA]  dA accumulated over the sub-layers
-    float* dNs = dAs + NP * LDA;       // [NP][LDN]  dN_l = relu'(g_l) dG_l / r
-    float* Ts = dNs + NP * LDN;        // [NP][LDN]  Z_l, then dZ_l
-    float* dGs = Ts + NP * LDN;        // [NP][LDG]  dense-connect gradient parked for sub-layers < l
+    float* AtH = smem;                 // [NP][LDA]  A transposed (AtH[j][i] + AtL[j][i] = A[i][j]), hi plane
+    float* AtL = AtH + NP * LDA;       //            lo plane
+    float* dAs = AtL + NP * LDA;       // [NP][LDA]  dA accumulated over the sub-layers (fp32)
+    float* dNh = dAs + NP * LDA;       // [NP][LDN]  dN_l = relu'(g_l) dG_l / r, hi / lo planes
+    float* dNl = dNh + NP * LDN;
+    float* Th = dNl + NP * LDN;        // [NP][LDN]  Z_l, then dZ_l, hi / lo planes
+    float* Tl = Th + NP * LDN;
+    float* dGs = Tl + NP * LDN;        // [NP][LDG]  dense-connect gradient parked for sub-layers < l (fp32)
     float* rs = dGs + NP * LDG;        // [NP]
     float* drs = rs + NP;              // [NP]
-    float* qs = dNs;                   // [n][DH+1]  (final phase only)
-    float* rowbuf = Ts;                // [BK_WARPS][NP]  (final phase only)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x;
+    const LaneGeo L;
+    const int wnt = L.warp % NTW, wmg = L.warp / NTW;
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
     const float* Ab = A + abase;
+    const size_t hbase = static_cast<size_t>(node0) * HD + h * S;       // + i*HD + l*GD + col  (32-bit offsets)
 
-    for (int i = warp; i < NP; i += BK_WARPS) {
-        float s = 0.f;
-        for (int j = lane; j < NP; j += WARP) {
-            const float v = (i < n && j < n) ? Ab[static_cast<size_t>(i) * n + j] : 0.f;
-            Ats[j * LDA + i] = v;
-            s += v;
+#pragma unroll
+    for (int r0 = 0; r0 < NP; r0 += 32) {
+        const int i = r0 + L.rsub;
+        if (i >= NP) continue;
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int j = L.l8 + 8 * r;
+            if (r < NT8) {
+                const float v = (i < n && j < n) ? Ab[i * n + j] : 0.f;
+                float hi, lo;
+                split_f(v, hi, lo);
+                AtH[j * LDA + i] = hi;
+                AtL[j * LDA + i] = lo;
+                sum += v;
+            }
         }
-        s = warp_sum(s);
-        if (lane == 0) { rs[i] = 1.0f / (s + (s == 0.f ? 1.f : 0.f)); drs[i] = 0.f; }
+        sum = group8_sum(sum);
+        if (L.l8 == 0) { rs[i] = 1.0f / (sum + (sum == 0.f ? 1.f : 0.f)); drs[i] = 0.f; }
     }
     __syncthreads();
 
     const int cg = tid % CG, rg = tid / CG, c0 = cg * 4;
+#pragma unroll
     for (int l = layers - 1; l >= 0; --l) {
-        const size_t colbase = static_cast<size_t>(h) * S + l * GD;
         const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
         const bool first_layer = (l == layers - 1);
         // (a) row-local: dG_l -> dN_l (shared), dE_l (global), dr (shared); Z_l -> shared
-        for (int i = rg; i < NP; i += RPP) {
+#pragma unroll
+        for (int i0 = 0; i0 < NP; i0 += RPP) {
+            const int i = i0 + rg;
+            if (NP % RPP != 0 && i >= NP) continue;        // warp-uniform (RPP rows = 2 or 4 per warp)
             float4 dn = make_float4(0.f, 0.f, 0.f, 0.f), zl = dn;
             float drp = 0.f;
             if (i < n) {
-                const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + c0;
+                const size_t off = hbase + (i * HD + l * GD + c0);
                 float4 dg = ld4g(dF + off);
                 const float4 g4 = ld4g(G + off);
                 zl = ld4g(Z + off);
@@ -317,62 +457,112 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 *reinterpret_cast<float4*>(dE + off) = dn;
                 drp = -(dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
             }
-            *reinterpret_cast<float4*>(dNs + i * LDN + c0) = dn;
-            *reinterpret_cast<float4*>(Ts + i * LDN + c0) = zl;
+            float4 hi, lo;
+            split_f4(dn, hi, lo);
+            *reinterpret_cast<float4*>(dNh + i * LDN + c0) = hi;
+            *reinterpret_cast<float4*>(dNl + i * LDN + c0) = lo;
+            split_f4(zl, hi, lo);
+            *reinterpret_cast<float4*>(Th + i * LDN + c0) = hi;
+            *reinterpret_cast<float4*>(Tl + i * LDN + c0) = lo;
 #pragma unroll
             for (int o = CG / 2; o > 0; o >>= 1) drp += __shfl_xor_sync(0xffffffffu, drp, o);
             if (cg == 0 && i < n) drs[i] += drp;
         }
         __syncthreads();
-        // (c) dA += dN_l Z_l^T
-        for (int u = warp; u < MT * NT8; u += BK_WARPS) {
+        // (c) dA += dN_l Z_l^T      (both operands K-contiguous: ldmatrix on either side)
+        for (int u = L.warp; u < MT * NT8; u += BK_WARPS) {
             const int mt = u / NT8, jt = u - mt * NT8;
-            float c[1][4];
-            zero_frag<1>(c);
-            warp_gemm<1, true>(c, GD / 8, dNs + (16 * mt) * LDN, LDN, Ts + (8 * jt) * LDN, LDN);
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* pa = dNh + (16 * mt + L.a_row) * LDN + L.a_col;
+            const float* pb = (L.b_lo ? Tl : Th) + (8 * jt + L.b_row) * LDN + L.b_col;
+#pragma unroll
+            for (int k0 = 0; k0 < GD; k0 += 8) {
+                uint32_t ah[4], al[4], bb[4];
+                ldsm4(ah, pa + k0);
+                ldsm4(al, pa + NP * LDN + k0);
+                ldsm4(bb, pb + k0);
+                mma3(c, ah, al, bb[0], bb[1], bb[2], bb[3]);
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                float2* p = reinterpret_cast<float2*>(dAs + (16 * mt + g + 8 * half) * LDA + 8 * jt + 2 * t);
-                float2 v = make_float2(c[0][2 * half], c[0][2 * half + 1]);
+                float2* p = reinterpret_cast<float2*>(dAs + (16 * mt + L.g + 8 * half) * LDA + 8 * jt + 2 * L.t);
+                float2 v = make_float2(c[2 * half], c[2 * half + 1]);
                 if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
                 *p = v;
             }
         }
-        __syncthreads();
-        // (b) dZ_l = A^T dN_l  -> Ts (for the dense-connect push-down) and global
-        for (int u = warp; u < MT * NGU; u += BK_WARPS) {
-            const int jt = u / NGU, ng = u - jt * NGU;
-            float c[2][4];
-            zero_frag<2>(c);
-            warp_gemm<2, false>(c, NP / 8, Ats + (16 * jt) * LDA, LDA, dNs + 16 * ng, LDN);
+        // (b) dZ_l = A^T dN_l  -> T planes (for the dense-connect push-down) and global
+        {
+            float c[MTW][4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int j = 16 * jt + g + 8 * half;
+            for (int r = 0; r < MTW; ++r) { c[r][0] = 0.f; c[r][1] = 0.f; c[r][2] = 0.f; c[r][3] = 0.f; }
+            const float* nb = dNh + L.t * LDN + 8 * wnt + L.g;
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const int col = 16 * ng + 8 * nt + 2 * t;
-                    const float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
-                    *reinterpret_cast<float2*>(Ts + j * LDN + col) = v;
+            for (int k0 = 0; k0 < NP; k0 += 8) {
+                const uint32_t bh0 = __float_as_uint(nb[k0 * LDN]), bh1 = __float_as_uint(nb[(k0 + 4) * LDN]);
+                const uint32_t bl0 = __float_as_uint(nb[NP * LDN + k0 * LDN]);
+                const uint32_t bl1 = __float_as_uint(nb[NP * LDN + (k0 + 4) * LDN]);
+#pragma unroll
+                for (int r = 0; r < MTW; ++r) {
+                    const int jt = wmg + MG * r;
+                    if (jt < MT) {
+                        uint32_t ah[4], al[4];
+                        const float* pa = AtH + (16 * jt + L.a_row) * LDA + k0 + L.a_col;
+                        ldsm4(ah, pa);
+                        ldsm4(al, pa + NP * LDA);
+                        mma3(c[r], ah, al, bh0, bh1, bl0, bl1);
+                    }
+                }
+            }
+            __syncthreads();           // every warp is done reading Z_l (phase c): the T planes may be overwritten
+#pragma unroll
+            for (int r = 0; r < MTW; ++r) {
+                const int jt = wmg + MG * r;
+                if (jt >= MT) continue;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int j = 16 * jt + L.g + 8 * half, col = 8 * wnt + 2 * L.t;
+                    const float2 v = make_float2(c[r][2 * half], c[r][2 * half + 1]);
+                    float2 hi, lo;
+                    split_f(v.x, hi.x, lo.x);
+                    split_f(v.y, hi.y, lo.y);
+                    *reinterpret_cast<float2*>(Th + j * LDN + col) = hi;
+                    *reinterpret_cast<float2*>(Tl + j * LDN + col) = lo;
                     if (j < n)
-                        *reinterpret_cast<float2*>(dZ + static_cast<size_t>(node0 + j) * HD + colbase + col) = v;
+                        *reinterpret_cast<float2*>(dZ + hbase + (j * HD + l * GD + col)) = v;
                 }
             }
         }
         __syncthreads();
         // push dZ_l through the dense connection: dG_m[j][c'] += sum_c dZ_l[j][c] * Wn_l[128 + m*GD + c'][c]
-        for (int u = warp; u < l * MT * NGU; u += BK_WARPS) {
-            const int m = u / (MT * NGU), rem = u - m * (MT * NGU);
-            const int jt = rem / NGU, ng = rem - jt * NGU;
-            float c[2][4];
-            zero_frag<2>(c);
-            warp_gemm<2, true>(c, GD / 8, Ts + (16 * jt) * LDN, LDN, wsrc + static_cast<size_t>(m * GD + 16 * ng) * GD, GD);
+        for (int m = 0; m < l; ++m) {
+            float c[MTW][4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int j = 16 * jt + g + 8 * half;
+            for (int r = 0; r < MTW; ++r) { c[r][0] = 0.f; c[r][1] = 0.f; c[r][2] = 0.f; c[r][3] = 0.f; }
+            const float* wb = wsrc + static_cast<size_t>(m * GD + 8 * wnt + L.g) * GD + L.t;
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    float2* p = reinterpret_cast<float2*>(dGs + j * LDG + m * GD + 16 * ng + 8 * nt + 2 * t);
-                    float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+            for (int k0 = 0; k0 < GD; k0 += 8) {
+                const float b0 = __ldg(wb + k0), b1 = __ldg(wb + k0 + 4);
+#pragma unroll
+                for (int r = 0; r < MTW; ++r) {
+                    const int jt = wmg + MG * r;
+                    if (jt < MT) {
+                        uint32_t ah[4], al[4];
+                        const float* pa = Th + (16 * jt + L.a_row) * LDN + k0 + L.a_col;
+                        ldsm4(ah, pa);
+                        ldsm4(al, pa + NP * LDN);
+                        mma3f(c[r], ah, al, b0, b1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MTW; ++r) {
+                const int jt = wmg + MG * r;
+                if (jt >= MT) continue;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float2* p = reinterpret_cast<float2*>(dGs + (16 * jt + L.g + 8 * half) * LDG + m * GD + 8 * wnt + 2 * L.t);
+                    float2 v = make_float2(c[r][2 * half], c[r][2 * half + 1]);
                     if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
                     *p = v;
                 }
@@ -381,51 +571,84 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         __syncthreads();
     }
 
-    // ---- attention gradient leaves the CTA -------------------------------------------------
-    if (OUT == BK_OUT_DA) {
-        float* dAb = dOut + abase;
-        for (int i = warp; i < n; i += BK_WARPS) {
-            const float dr = drs[i];
-            for (int j = lane; j < n; j += WARP) dAb[static_cast<size_t>(i) * n + j] = dAs[i * LDA + j] + dr;
-        }
-        return;
-    }
-    if (OUT == BK_OUT_DQ) {
-        constexpr int LQ = DH + 1, Q4 = (DH > 0 ? DH : 4) / 4;
-        for (int idx = tid; idx < n * Q4; idx += BK_THREADS) {
-            const int j = idx / Q4, k4 = (idx - j * Q4) * 4;
-            const float4 v = ld4g(q + static_cast<size_t>(node0 + j) * D + h * DH + k4);
-            float* d = qs + j * LQ + k4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-    }
-    // softmax backward, one warp per row: dS_ij = P_ij (dA_ij - sum_j dA_ij P_ij)
-    for (int i = warp; i < n; i += BK_WARPS) {
-        const float dr = drs[i];
+    // ---- attention gradient leaves the CTA: rows in groups of 8 lanes ---------------------------
+#pragma unroll
+    for (int r0 = 0; r0 < NP; r0 += 32) {
+        const int i = r0 + L.rsub;
+        if (i >= NP) continue;
+        const bool rv = i < n;
+        const float dr = rv ? drs[i] : 0.f;
+        float p[8], dp[8];
         float dot = 0.f;
-        for (int j = lane; j < n; j += WARP) dot += (dAs[i * LDA + j] + dr) * Ats[j * LDA + i];
-        dot = warp_sum(dot);
-        for (int j = lane; j < n; j += WARP) {
-            const float ds = Ats[j * LDA + i] * (dAs[i * LDA + j] + dr - dot);
-            if (OUT == BK_OUT_DS) dOut[abase + static_cast<size_t>(i) * n + j] = ds;
-            else dAs[i * LDA + j] = ds;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int j = L.l8 + 8 * r;
+            p[r] = 0.f; dp[r] = 0.f;
+            if (r < NT8 && rv && j < n) {
+                dp[r] = dAs[i * LDA + j] + dr;
+                if (OUT != BK_OUT_DA) { p[r] = AtH[j * LDA + i] + AtL[j * LDA + i]; dot += dp[r] * p[r]; }
+            }
+        }
+        if (OUT != BK_OUT_DA) dot = group8_sum(dot);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int j = L.l8 + 8 * r;
+            if (r < NT8) {
+                const float ds = (OUT == BK_OUT_DA) ? dp[r] : p[r] * (dp[r] - dot);
+                if (OUT == BK_OUT_DQ) dAs[i * LDA + j] = ds;           // zeros in the padding
+                else if (rv && j < n) dOut[abase + static_cast<long long>(i) * n + j] = ds;
+            }
         }
     }
     if (OUT == BK_OUT_DQ) {
+        // dq_h = scale (dS + dS^T) q_h   (S = scale q q^T is symmetric in q) -- one more small MMA
+        constexpr int LQ = DHH + 8, Q4 = DHH / 4;
+        float* Wh = dNh;               // [NP][LDA] hi / lo planes of dS + dS^T (the dN / T planes are dead)
+        float* Wl = Wh + NP * LDA;
+        float* qs = Wl + NP * LDA;     // [NP][LQ]  head slice of q, fp32
+        for (int idx = tid; idx < NP * Q4; idx += BK_THREADS) {
+            const int j = idx / Q4, k4 = (idx - j * Q4) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n) v = ld4g(q + static_cast<size_t>(node0 + j) * D + h * DHH + k4);
+            *reinterpret_cast<float4*>(qs + j * LQ + k4) = v;
+        }
         __syncthreads();
-        // dq_h[i,:] = scale * sum_j (dS_ij + dS_ji) q_h[j,:]      (S = scale q q^T is symmetric in q)
-        constexpr int DHH = DH > 0 ? DH : 4, LQ = DHH + 1, GROUPS = WARP / DHH;
-        const int k = lane % DHH, grp = lane / DHH;
-        float* buf = rowbuf + warp * NP;
-        for (int i = warp; i < n; i += BK_WARPS) {
-            for (int j = lane; j < n; j += WARP) buf[j] = dAs[i * LDA + j] + dAs[j * LDA + i];
-            __syncwarp();
-            float acc = 0.f;
-            for (int j = grp; j < n; j += GROUPS) acc += buf[j] * qs[j * LQ + k];
-            if (GROUPS >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (GROUPS >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-            if (grp == 0) dOut[static_cast<size_t>(node0 + i) * D + h * DHH + k] = acc * scale;
-            __syncwarp();
+#pragma unroll
+        for (int r0 = 0; r0 < NP; r0 += 32) {
+            const int i = r0 + L.rsub;
+            if (i >= NP) continue;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int j = L.l8 + 8 * r;
+                if (r < NT8) {
+                    float hi, lo;
+                    split_f(dAs[i * LDA + j] + dAs[j * LDA + i], hi, lo);
+                    Wh[i * LDA + j] = hi;
+                    Wl[i * LDA + j] = lo;
+                }
+            }
+        }
+        __syncthreads();
+        constexpr int QT = DHH / 8;
+        for (int u = L.warp; u < MT * QT; u += BK_WARPS) {
+            const int mt = u / QT, nt = u - mt * QT;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* pa = Wh + (16 * mt + L.a_row) * LDA + L.a_col;
+            const float* qb = qs + L.t * LQ + 8 * nt + L.g;
+#pragma unroll
+            for (int k0 = 0; k0 < NP; k0 += 8) {
+                uint32_t ah[4], al[4];
+                ldsm4(ah, pa + k0);
+                ldsm4(al, pa + NP * LDA + k0);
+                mma3f(c, ah, al, qb[k0 * LQ], qb[(k0 + 4) * LQ]);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = 16 * mt + L.g + 8 * half;
+                if (i < n)
+                    *reinterpret_cast<float2*>(dOut + static_cast<size_t>(node0 + i) * D + h * DHH + 8 * nt + 2 * L.t) =
+                        make_float2(c[2 * half] * scale, c[2 * half + 1] * scale);
+            }
         }
     }
 }
@@ -433,12 +656,12 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 // ---------------------------------------------------------------------------------------------
 static size_t block_fwd_smem(int np, int layers, int gd) {
     const int ki = (layers - 1) * gd;
-    return (static_cast<size_t>(np) * (np + 4) + 2 * static_cast<size_t>(np) * (gd + 8) +
-            static_cast<size_t>(np) * (ki + 4) + np) * sizeof(float);
+    return (2 * static_cast<size_t>(np) * (np + 4) + 2 * static_cast<size_t>(np) * (gd + 8) +
+            2 * static_cast<size_t>(np) * (ki + 4) + np) * sizeof(float);
 }
 static size_t block_bwd_smem(int np, int layers, int gd) {
     const int ki = (layers - 1) * gd;
-    return (2 * static_cast<size_t>(np) * (np + 4) + 2 * static_cast<size_t>(np) * (gd + 12) +
+    return (3 * static_cast<size_t>(np) * (np + 4) + 4 * static_cast<size_t>(np) * (gd + 12) +
             static_cast<size_t>(np) * (ki + 4) + 2 * np) * sizeof(float);
 }
 
@@ -480,6 +703,36 @@ static int prepare_kernel(K kernel, size_t max_bytes, const char* name) {
                                         static_cast<int>(max_bytes)), name);
 }
 
+template <int GD, int DH, int MTC>
+static int launch_fwd_class(const gcgcn_batch* bt, int heads, int count, int first, const int* order, const float* A,
+                            const float* q, float* P, float* Z, const float* E, const float* Winner, const float* x,
+                            float* G, float* F, float scale, cudaStream_t st) {
+    constexpr int layers = D / GD;
+    const size_t smem = block_fwd_smem(16 * MTC, layers, GD);
+    static bool ready = false;
+    if (!ready) { GCGCN_TRY(prepare_kernel(block_fwd_kernel<GD, DH, MTC>, smem, "block_fwd")); ready = true; }
+    block_fwd_kernel<GD, DH, MTC><<<dim3(count, heads), BK_THREADS, smem, st>>>(
+        bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), A, q, P, Z, E, Winner, x, G, F, heads,
+        bt->total_pairs, order, first, scale);
+    GCGCN_CHECK_LAUNCH(DH > 0 ? "block_fwd<mha>" : "block_fwd<given>");
+    return GCGCN_OK;
+}
+
+template <int GD, int DH>
+static int launch_fwd_all(const gcgcn_batch* bt, int heads, const float* A, const float* q, float* P, float* Z,
+                          const float* E, const float* Winner, const float* x, float* G, float* F, float scale,
+                          cudaStream_t st) {
+    return for_each_size_class(bt, [&](int count, int first, int nmax, const int* order) -> int {
+        switch ((nmax + 15) / 16) {
+            case 1: return launch_fwd_class<GD, DH, 1>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
+            case 2: return launch_fwd_class<GD, DH, 2>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
+            case 3: return launch_fwd_class<GD, DH, 3>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
+            case 4: return launch_fwd_class<GD, DH, 4>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
+            default: return fail(GCGCN_ERR_UNSUPPORTED, "block_fwd: %d nodes > 64", nmax);
+        }
+    });
+}
+
 // A != nullptr: attention given (q, P unused).  A == nullptr: MHA from q, P written.
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
@@ -488,21 +741,8 @@ int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* 
     const int gd = D / layers;
     const int dh = A != nullptr ? 0 : D / heads;
     const float scale = dh > 0 ? 1.0f / sqrtf(static_cast<float>(dh)) : 1.f;
-    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
-    const size_t max_smem = block_fwd_smem(64, layers, gd);
-#define GCGCN_BK_FWD(GD_, DH_)                                                                                       \
-    if (gd == GD_ && dh == DH_) {                                                                                    \
-        static bool ready = false;                                                                                   \
-        if (!ready) { GCGCN_TRY(prepare_kernel(block_fwd_kernel<GD_, DH_>, max_smem, "block_fwd")); ready = true; }  \
-        return for_each_size_class(bt, [&](int count, int first, int nmax, const int* order) -> int {                \
-            const size_t smem = block_fwd_smem((nmax + 15) & ~15, layers, gd);                                       \
-            block_fwd_kernel<GD_, DH_><<<dim3(count, heads), BK_THREADS, smem, st>>>(                                \
-                bt->node_ptr, pp, A, q, P, Z, E, Winner, x, G, F, layers, heads, bt->total_pairs, order, first,     \
-                scale);                                                                                              \
-            GCGCN_CHECK_LAUNCH(DH_ > 0 ? "block_fwd<mha>" : "block_fwd<given>");                                     \
-            return GCGCN_OK;                                                                                         \
-        });                                                                                                          \
-    }
+#define GCGCN_BK_FWD(GD_, DH_) \
+    if (gd == GD_ && dh == DH_) return launch_fwd_all<GD_, DH_>(bt, heads, A, q, P, Z, E, Winner, x, G, F, scale, st);
     GCGCN_BK_FWD(64, 0)
     GCGCN_BK_FWD(64, 16)
     GCGCN_BK_FWD(64, 32)
@@ -511,6 +751,36 @@ int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* 
     GCGCN_BK_FWD(32, 32)
 #undef GCGCN_BK_FWD
     return fail(GCGCN_ERR_UNSUPPORTED, "block_fwd: sub-layer width %d / head width %d not supported", gd, dh);
+}
+
+template <int GD, int DH, int OUT, int MTC>
+static int launch_bwd_class(const gcgcn_batch* bt, int heads, int count, int first, const int* order, const float* A,
+                            const float* q, const float* Z, const float* G, const float* Winner, const float* dF,
+                            float* dZ, float* dE, float* dOut, float scale, cudaStream_t st) {
+    constexpr int layers = D / GD;
+    const size_t smem = block_bwd_smem(16 * MTC, layers, GD);
+    static bool ready = false;
+    if (!ready) { GCGCN_TRY(prepare_kernel(block_bwd_kernel<GD, DH, OUT, MTC>, smem, "block_bwd")); ready = true; }
+    block_bwd_kernel<GD, DH, OUT, MTC><<<dim3(count, heads), BK_THREADS, smem, st>>>(
+        bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), A, q, Z, G, Winner, dF, dZ, dE, dOut, heads,
+        bt->total_pairs, order, first, scale);
+    GCGCN_CHECK_LAUNCH(OUT == BK_OUT_DQ ? "block_bwd<dq>" : (OUT == BK_OUT_DS ? "block_bwd<dS>" : "block_bwd<dA>"));
+    return GCGCN_OK;
+}
+
+template <int GD, int DH, int OUT>
+static int launch_bwd_all(const gcgcn_batch* bt, int heads, const float* A, const float* q, const float* Z,
+                          const float* G, const float* Winner, const float* dF, float* dZ, float* dE, float* dOut,
+                          float scale, cudaStream_t st) {
+    return for_each_size_class(bt, [&](int count, int first, int nmax, const int* order) -> int {
+        switch ((nmax + 15) / 16) {
+            case 1: return launch_bwd_class<GD, DH, OUT, 1>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+            case 2: return launch_bwd_class<GD, DH, OUT, 2>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+            case 3: return launch_bwd_class<GD, DH, OUT, 3>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+            case 4: return launch_bwd_class<GD, DH, OUT, 4>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+            default: return fail(GCGCN_ERR_UNSUPPORTED, "block_bwd: %d nodes > 64", nmax);
+        }
+    });
 }
 
 // out_mode: BK_OUT_DA -> dOut = dA [heads][total_pairs]; BK_OUT_DS -> dOut = dS (same shape; A must be a softmax
@@ -522,32 +792,17 @@ int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode,
     const int gd = D / layers;
     const int dh = out_mode == BK_OUT_DQ ? D / heads : 0;
     const float scale = dh > 0 ? 1.0f / sqrtf(static_cast<float>(dh)) : 1.f;
-    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
-    const size_t max_smem = block_bwd_smem(64, layers, gd);
-#define GCGCN_BK_BWD(GD_, DH_, OUT_, NAME_)                                                                          \
-    if (gd == GD_ && dh == DH_ && out_mode == OUT_) {                                                                \
-        static bool ready = false;                                                                                   \
-        if (!ready) {                                                                                                \
-            GCGCN_TRY(prepare_kernel(block_bwd_kernel<GD_, DH_, OUT_>, max_smem, "block_bwd"));                      \
-            ready = true;                                                                                            \
-        }                                                                                                            \
-        return for_each_size_class(bt, [&](int count, int first, int nmax, const int* order) -> int {                \
-            const size_t smem = block_bwd_smem((nmax + 15) & ~15, layers, gd);                                       \
-            block_bwd_kernel<GD_, DH_, OUT_><<<dim3(count, heads), BK_THREADS, smem, st>>>(                          \
-                bt->node_ptr, pp, A, q, Z, G, Winner, dF, dZ, dE, dOut, layers, heads, bt->total_pairs, order,      \
-                first, scale);                                                                                       \
-            GCGCN_CHECK_LAUNCH(NAME_);                                                                               \
-            return GCGCN_OK;                                                                                         \
-        });                                                                                                          \
-    }
-    GCGCN_BK_BWD(64, 0, BK_OUT_DA, "block_bwd<dA>")
-    GCGCN_BK_BWD(32, 0, BK_OUT_DA, "block_bwd<dA>")
-    GCGCN_BK_BWD(64, 0, BK_OUT_DS, "block_bwd<dS>")
-    GCGCN_BK_BWD(32, 0, BK_OUT_DS, "block_bwd<dS>")
-    GCGCN_BK_BWD(64, 16, BK_OUT_DQ, "block_bwd<dq>")
-    GCGCN_BK_BWD(64, 32, BK_OUT_DQ, "block_bwd<dq>")
-    GCGCN_BK_BWD(32, 16, BK_OUT_DQ, "block_bwd<dq>")
-    GCGCN_BK_BWD(32, 32, BK_OUT_DQ, "block_bwd<dq>")
+#define GCGCN_BK_BWD(GD_, DH_, OUT_)                      \
+    if (gd == GD_ && dh == DH_ && out_mode == OUT_)       \
+        return launch_bwd_all<GD_, DH_, OUT_>(bt, heads, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+    GCGCN_BK_BWD(64, 0, BK_OUT_DA)
+    GCGCN_BK_BWD(32, 0, BK_OUT_DA)
+    GCGCN_BK_BWD(64, 0, BK_OUT_DS)
+    GCGCN_BK_BWD(32, 0, BK_OUT_DS)
+    GCGCN_BK_BWD(64, 16, BK_OUT_DQ)
+    GCGCN_BK_BWD(64, 32, BK_OUT_DQ)
+    GCGCN_BK_BWD(32, 16, BK_OUT_DQ)
+    GCGCN_BK_BWD(32, 32, BK_OUT_DQ)
 #undef GCGCN_BK_BWD
     return fail(GCGCN_ERR_UNSUPPORTED, "block_bwd: sub-layer width %d / head width %d / mode %d not supported", gd, dh,
                 out_mode);
