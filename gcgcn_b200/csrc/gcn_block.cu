@@ -87,6 +87,14 @@ __device__ __forceinline__ float group8_max(float v) {
     return v;
 }
 
+// Warp tiling of a [16 MT] x [8 NT] product: each warp takes one row tile and NTW column tiles, NTW the smallest
+// power of two that fits all MT * NT / NTW units into the 8 warps.
+__host__ __device__ constexpr int col_tiles_per_warp(int mt, int nt) {
+    int w = 1;
+    while (mt * (nt / w) > BK_WARPS && w < nt) w *= 2;
+    return w;
+}
+
 // Per-lane geometry shared by both kernels.
 //   ldmatrix A fragment (16 rows x 8 k): lane supplies row a_row, k offset a_col of the tile
 //   ldmatrix B fragment, operand stored [n][k] (hi and lo planes in one x4): row b_row, k offset b_col, plane b_lo
@@ -119,9 +127,8 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
-    // NTW column tiles of 8; warp -> (column tile wnt, row-tile group wmg); at most MTW row tiles per warp
-    constexpr int S = D, layers = D / GD, LDZ = GD + 8, CG = GD / 4, NTW = GD / 8, MG = BK_WARPS / NTW;
-    constexpr int MTW = (MTC + MG - 1) / MG, DHH = DH > 0 ? DH : 8;
+    constexpr int S = D, layers = D / GD, LDZ = GD + 8, CG = GD / 4, DHH = DH > 0 ? DH : 8;
+    constexpr int NTW = col_tiles_per_warp(MTC, GD / 8), NG = (GD / 8) / NTW, UNITS = MTC * NG;
     constexpr int NP = 16 * MTC, MT = MTC, NT8 = 2 * MTC, LDA = NP + 4, KI = (layers - 1) * GD, LDG = KI + 4;
     const int HD = DH > 0 ? (D / DHH) * S : heads * S;
 
@@ -134,7 +141,6 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 
     const int tid = threadIdx.x;
     const LaneGeo L;
-    const int wnt = L.warp % NTW, wmg = L.warp / NTW;
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
     const size_t hbase = static_cast<size_t>(node0) * HD + h * S;       // + i*HD + l*GD + col  (32-bit offsets)
     const float* zsrc = Z + hbase;
@@ -254,41 +260,37 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         const int kin = l * GD;
         cp_async_wait<1>();            // this thread's copies of tile l have landed ...
         __syncthreads();               // ... and everyone's; also publishes the attention planes / g_{l-1}
-        float c[MTW][4];
-        float* zc = Zs + L.g * LDZ + 8 * wnt + 2 * L.t;               // this lane's C-fragment corner in the tile
+        // warp -> unit (row tile mt, group ng of NTW column tiles): the expensive fragment (16 x 8 hi+lo of the
+        // row operand, 8 shared-memory wavefronts) is loaded once per NTW cheap column fragments
+        const int mt = L.warp / NG, ng = L.warp - mt * NG;
+        const bool busy = L.warp < UNITS;
+        const int col0 = 8 * NTW * ng;                                 // first column of this warp's tile
+        float c[NTW][4];
+        float* zc = Zs + (16 * mt + L.g) * LDZ + col0 + 2 * L.t;      // this lane's C-fragment corner in the tile
         if (l > 0) {
             // Z_l += g_{<l} Winner_l   (dense connection, row-local in the reference: G:72-73)
-            const float* wb = Winner + (static_cast<size_t>(h) * layers + l) * S * GD + L.t * GD + 8 * wnt + L.g;
+            if (busy) {
+                const float* wb = Winner + (static_cast<size_t>(h) * layers + l) * S * GD + L.t * GD + col0 + L.g;
 #pragma unroll
-            for (int r = 0; r < MTW; ++r) {
-                const int mt = wmg + MG * r;
-                if (mt < MT) {
-                    const float2 lo2 = *reinterpret_cast<const float2*>(zc + 16 * mt * LDZ);
-                    const float2 hi2 = *reinterpret_cast<const float2*>(zc + (16 * mt + 8) * LDZ);
-                    c[r][0] = lo2.x; c[r][1] = lo2.y; c[r][2] = hi2.x; c[r][3] = hi2.y;
+                for (int nt = 0; nt < NTW; ++nt) {
+                    const float2 lo2 = *reinterpret_cast<const float2*>(zc + 8 * nt);
+                    const float2 hi2 = *reinterpret_cast<const float2*>(zc + 8 * LDZ + 8 * nt);
+                    c[nt][0] = lo2.x; c[nt][1] = lo2.y; c[nt][2] = hi2.x; c[nt][3] = hi2.y;
                 }
-            }
-#pragma unroll 4
-            for (int k0 = 0; k0 < kin; k0 += 8) {
-                const float b0 = __ldg(wb + k0 * GD), b1 = __ldg(wb + (k0 + 4) * GD);
+                const float* pa = Ghi + (16 * mt + L.a_row) * LDG + L.a_col;
+#pragma unroll 2
+                for (int k0 = 0; k0 < kin; k0 += 8) {
+                    uint32_t ah[4], al[4];
+                    ldsm4(ah, pa + k0);
+                    ldsm4(al, pa + NP * LDG + k0);
 #pragma unroll
-                for (int r = 0; r < MTW; ++r) {
-                    const int mt = wmg + MG * r;
-                    if (mt < MT) {
-                        uint32_t ah[4], al[4];
-                        const float* pa = Ghi + (16 * mt + L.a_row) * LDG + k0 + L.a_col;
-                        ldsm4(ah, pa);
-                        ldsm4(al, pa + NP * LDG);
-                        mma3f(c[r], ah, al, b0, b1);
-                    }
+                    for (int nt = 0; nt < NTW; ++nt)
+                        mma3f(c[nt], ah, al, __ldg(wb + k0 * GD + 8 * nt), __ldg(wb + (k0 + 4) * GD + 8 * nt));
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < MTW; ++r) {
-                const int mt = wmg + MG * r;
-                if (mt < MT) {
-                    *reinterpret_cast<float2*>(zc + 16 * mt * LDZ) = make_float2(c[r][0], c[r][1]);
-                    *reinterpret_cast<float2*>(zc + (16 * mt + 8) * LDZ) = make_float2(c[r][2], c[r][3]);
+                for (int nt = 0; nt < NTW; ++nt) {
+                    *reinterpret_cast<float2*>(zc + 8 * nt) = make_float2(c[nt][0], c[nt][1]);
+                    *reinterpret_cast<float2*>(zc + 8 * LDZ + 8 * nt) = make_float2(c[nt][2], c[nt][3]);
                 }
             }
             __syncthreads();
@@ -299,64 +301,56 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
             }
         }
         // out = (E + P Z_l) / r ; g_l = relu(out) ; F_l = g_l + x_l
-        // epilogue operands first: their latency hides behind the MMA loop
-        float2 e2[MTW][2], x2[MTW][2];
-#pragma unroll
-        for (int r = 0; r < MTW; ++r) {
-            const int mt = wmg + MG * r;
+        if (busy) {
+            // epilogue operands first: their latency hides behind the MMA loop
+            float2 e2[2][NTW], x2[2][NTW];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int i = 16 * mt + L.g + 8 * half;
-                e2[r][half] = make_float2(0.f, 0.f);
-                x2[r][half] = make_float2(0.f, 0.f);
-                if (mt < MT && i < n) {
-                    const int col = 8 * wnt + 2 * L.t;
-                    e2[r][half] = ld2g(Eb + (i * HD + kin + col));
-                    x2[r][half] = ld2g(xb + (i * S + kin + col));
-                }
-            }
-        }
 #pragma unroll
-        for (int r = 0; r < MTW; ++r) { c[r][0] = 0.f; c[r][1] = 0.f; c[r][2] = 0.f; c[r][3] = 0.f; }
-        {
-            const float* zb = Zs + L.t * LDZ + 8 * wnt + L.g;
-#pragma unroll
-            for (int k0 = 0; k0 < NP; k0 += 8) {
-                const float b0 = zb[k0 * LDZ], b1 = zb[(k0 + 4) * LDZ];
-#pragma unroll
-                for (int r = 0; r < MTW; ++r) {
-                    const int mt = wmg + MG * r;
-                    if (mt < MT) {
-                        uint32_t ah[4], al[4];
-                        const float* pa = Ahi + (16 * mt + L.a_row) * LDA + k0 + L.a_col;
-                        ldsm4(ah, pa);
-                        ldsm4(al, pa + NP * LDA);
-                        mma3f(c[r], ah, al, b0, b1);
+                for (int nt = 0; nt < NTW; ++nt) {
+                    e2[half][nt] = make_float2(0.f, 0.f);
+                    x2[half][nt] = make_float2(0.f, 0.f);
+                    if (i < n) {
+                        const int col = col0 + 8 * nt + 2 * L.t;
+                        e2[half][nt] = ld2g(Eb + (i * HD + kin + col));
+                        x2[half][nt] = ld2g(xb + (i * S + kin + col));
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int r = 0; r < MTW; ++r) {
-            const int mt = wmg + MG * r;
+            for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+            const float* pa = Ahi + (16 * mt + L.a_row) * LDA + L.a_col;
+            const float* zb = Zs + L.t * LDZ + col0 + L.g;
+#pragma unroll
+            for (int k0 = 0; k0 < NP; k0 += 8) {
+                uint32_t ah[4], al[4];
+                ldsm4(ah, pa + k0);
+                ldsm4(al, pa + NP * LDA + k0);
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) mma3f(c[nt], ah, al, zb[k0 * LDZ + 8 * nt], zb[(k0 + 4) * LDZ + 8 * nt]);
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int i = 16 * mt + L.g + 8 * half;
-                if (mt >= MT || i >= n) continue;
+                if (i >= n) continue;
                 const float rinv = rs[i];
-                const int col = 8 * wnt + 2 * L.t;
-                const int off = i * HD + kin + col;
-                float2 o;
-                o.x = fmaxf((e2[r][half].x + c[r][2 * half]) * rinv, 0.f);
-                o.y = fmaxf((e2[r][half].y + c[r][2 * half + 1]) * rinv, 0.f);
-                *reinterpret_cast<float2*>(Gb + off) = o;
-                *reinterpret_cast<float2*>(Fb + off) = make_float2(o.x + x2[r][half].x, o.y + x2[r][half].y);
-                if (l < layers - 1) {
-                    float2 hi, lo;
-                    split_f(o.x, hi.x, lo.x);
-                    split_f(o.y, hi.y, lo.y);
-                    *reinterpret_cast<float2*>(Ghi + i * LDG + kin + col) = hi;
-                    *reinterpret_cast<float2*>(Glo + i * LDG + kin + col) = lo;
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) {
+                    const int col = col0 + 8 * nt + 2 * L.t;
+                    const int off = i * HD + kin + col;
+                    float2 o;
+                    o.x = fmaxf((e2[half][nt].x + c[nt][2 * half]) * rinv, 0.f);
+                    o.y = fmaxf((e2[half][nt].y + c[nt][2 * half + 1]) * rinv, 0.f);
+                    *reinterpret_cast<float2*>(Gb + off) = o;
+                    *reinterpret_cast<float2*>(Fb + off) = make_float2(o.x + x2[half][nt].x, o.y + x2[half][nt].y);
+                    if (l < layers - 1) {
+                        float2 hi, lo;
+                        split_f(o.x, hi.x, lo.x);
+                        split_f(o.y, hi.y, lo.y);
+                        *reinterpret_cast<float2*>(Ghi + i * LDG + kin + col) = hi;
+                        *reinterpret_cast<float2*>(Glo + i * LDG + kin + col) = lo;
+                    }
                 }
             }
         }
@@ -385,7 +379,9 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
     constexpr int S = D, layers = D / GD, LDN = GD + 12, CG = GD / 4, RPP = BK_THREADS / CG;
-    constexpr int NTW = GD / 8, MG = BK_WARPS / NTW, MTW = (MTC + MG - 1) / MG, DHH = DH > 0 ? DH : 8;
+    constexpr int DHH = DH > 0 ? DH : 8;
+    constexpr int NTW = col_tiles_per_warp(MTC, GD / 8), NG = (GD / 8) / NTW, UNITS = MTC * NG;           // [NP] x [GD] products
+    constexpr int NTW_C = MTC == 3 ? 3 : col_tiles_per_warp(MTC, 2 * MTC), NG_C = (2 * MTC) / NTW_C, UNITS_C = MTC * NG_C;  // [NP] x [NP]
     constexpr int NP = 16 * MTC, MT = MTC, NT8 = 2 * MTC, LDA = NP + 4, KI = (layers - 1) * GD, LDG = KI + 4;
     const int HD = DH > 0 ? (D / DHH) * S : heads * S;
 
@@ -402,7 +398,6 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 
     const int tid = threadIdx.x;
     const LaneGeo L;
-    const int wnt = L.warp % NTW, wmg = L.warp / NTW;
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
     const float* Ab = A + abase;
     const size_t hbase = static_cast<size_t>(node0) * HD + h * S;       // + i*HD + l*GD + col  (32-bit offsets)
@@ -470,102 +465,103 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         }
         __syncthreads();
         // (c) dA += dN_l Z_l^T      (both operands K-contiguous: ldmatrix on either side)
-        for (int u = L.warp; u < MT * NT8; u += BK_WARPS) {
-            const int mt = u / NT8, jt = u - mt * NT8;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
+        if (L.warp < UNITS_C) {
+            const int mt = L.warp / NG_C, jg = L.warp - mt * NG_C;
+            float c[NTW_C][4];
+#pragma unroll
+            for (int nt = 0; nt < NTW_C; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
             const float* pa = dNh + (16 * mt + L.a_row) * LDN + L.a_col;
-            const float* pb = (L.b_lo ? Tl : Th) + (8 * jt + L.b_row) * LDN + L.b_col;
+            const float* pb = (L.b_lo ? Tl : Th) + (8 * NTW_C * jg + L.b_row) * LDN + L.b_col;
 #pragma unroll
             for (int k0 = 0; k0 < GD; k0 += 8) {
-                uint32_t ah[4], al[4], bb[4];
+                uint32_t ah[4], al[4];
                 ldsm4(ah, pa + k0);
                 ldsm4(al, pa + NP * LDN + k0);
-                ldsm4(bb, pb + k0);
-                mma3(c, ah, al, bb[0], bb[1], bb[2], bb[3]);
+#pragma unroll
+                for (int nt = 0; nt < NTW_C; ++nt) {
+                    uint32_t bb[4];
+                    ldsm4(bb, pb + 8 * nt * LDN + k0);
+                    mma3(c[nt], ah, al, bb[0], bb[1], bb[2], bb[3]);
+                }
             }
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float2* p = reinterpret_cast<float2*>(dAs + (16 * mt + L.g + 8 * half) * LDA + 8 * jt + 2 * L.t);
-                float2 v = make_float2(c[2 * half], c[2 * half + 1]);
-                if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
-                *p = v;
-            }
+            for (int nt = 0; nt < NTW_C; ++nt)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float2* p = reinterpret_cast<float2*>(dAs + (16 * mt + L.g + 8 * half) * LDA + 8 * (NTW_C * jg + nt) + 2 * L.t);
+                    float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+                    if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
+                    *p = v;
+                }
         }
         // (b) dZ_l = A^T dN_l  -> T planes (for the dense-connect push-down) and global
+        const int jt = L.warp / NG, ng = L.warp - jt * NG;
+        const bool busy = L.warp < UNITS;
+        const int col0 = 8 * NTW * ng;
         {
-            float c[MTW][4];
+            float c[NTW][4];
 #pragma unroll
-            for (int r = 0; r < MTW; ++r) { c[r][0] = 0.f; c[r][1] = 0.f; c[r][2] = 0.f; c[r][3] = 0.f; }
-            const float* nb = dNh + L.t * LDN + 8 * wnt + L.g;
+            for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+            if (busy) {
+                const float* pa = AtH + (16 * jt + L.a_row) * LDA + L.a_col;
+                const float* nb = dNh + L.t * LDN + col0 + L.g;
 #pragma unroll
-            for (int k0 = 0; k0 < NP; k0 += 8) {
-                const uint32_t bh0 = __float_as_uint(nb[k0 * LDN]), bh1 = __float_as_uint(nb[(k0 + 4) * LDN]);
-                const uint32_t bl0 = __float_as_uint(nb[NP * LDN + k0 * LDN]);
-                const uint32_t bl1 = __float_as_uint(nb[NP * LDN + (k0 + 4) * LDN]);
+                for (int k0 = 0; k0 < NP; k0 += 8) {
+                    uint32_t ah[4], al[4];
+                    ldsm4(ah, pa + k0);
+                    ldsm4(al, pa + NP * LDA + k0);
 #pragma unroll
-                for (int r = 0; r < MTW; ++r) {
-                    const int jt = wmg + MG * r;
-                    if (jt < MT) {
-                        uint32_t ah[4], al[4];
-                        const float* pa = AtH + (16 * jt + L.a_row) * LDA + k0 + L.a_col;
-                        ldsm4(ah, pa);
-                        ldsm4(al, pa + NP * LDA);
-                        mma3(c[r], ah, al, bh0, bh1, bl0, bl1);
-                    }
+                    for (int nt = 0; nt < NTW; ++nt)
+                        mma3(c[nt], ah, al, __float_as_uint(nb[k0 * LDN + 8 * nt]), __float_as_uint(nb[(k0 + 4) * LDN + 8 * nt]),
+                             __float_as_uint(nb[NP * LDN + k0 * LDN + 8 * nt]),
+                             __float_as_uint(nb[NP * LDN + (k0 + 4) * LDN + 8 * nt]));
                 }
             }
             __syncthreads();           // every warp is done reading Z_l (phase c): the T planes may be overwritten
+            if (busy) {
 #pragma unroll
-            for (int r = 0; r < MTW; ++r) {
-                const int jt = wmg + MG * r;
-                if (jt >= MT) continue;
+                for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int j = 16 * jt + L.g + 8 * half, col = 8 * wnt + 2 * L.t;
-                    const float2 v = make_float2(c[r][2 * half], c[r][2 * half + 1]);
-                    float2 hi, lo;
-                    split_f(v.x, hi.x, lo.x);
-                    split_f(v.y, hi.y, lo.y);
-                    *reinterpret_cast<float2*>(Th + j * LDN + col) = hi;
-                    *reinterpret_cast<float2*>(Tl + j * LDN + col) = lo;
-                    if (j < n)
-                        *reinterpret_cast<float2*>(dZ + hbase + (j * HD + l * GD + col)) = v;
-                }
+                    for (int half = 0; half < 2; ++half) {
+                        const int j = 16 * jt + L.g + 8 * half, col = col0 + 8 * nt + 2 * L.t;
+                        const float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+                        float2 hi, lo;
+                        split_f(v.x, hi.x, lo.x);
+                        split_f(v.y, hi.y, lo.y);
+                        *reinterpret_cast<float2*>(Th + j * LDN + col) = hi;
+                        *reinterpret_cast<float2*>(Tl + j * LDN + col) = lo;
+                        if (j < n) *reinterpret_cast<float2*>(dZ + hbase + (j * HD + l * GD + col)) = v;
+                    }
             }
         }
         __syncthreads();
         // push dZ_l through the dense connection: dG_m[j][c'] += sum_c dZ_l[j][c] * Wn_l[128 + m*GD + c'][c]
-        for (int m = 0; m < l; ++m) {
-            float c[MTW][4];
+        if (busy) {
 #pragma unroll
-            for (int r = 0; r < MTW; ++r) { c[r][0] = 0.f; c[r][1] = 0.f; c[r][2] = 0.f; c[r][3] = 0.f; }
-            const float* wb = wsrc + static_cast<size_t>(m * GD + 8 * wnt + L.g) * GD + L.t;
+            for (int m = 0; m < l; ++m) {
+                float c[NTW][4];
 #pragma unroll
-            for (int k0 = 0; k0 < GD; k0 += 8) {
-                const float b0 = __ldg(wb + k0), b1 = __ldg(wb + k0 + 4);
+                for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+                const float* wb = wsrc + (m * GD + col0 + L.g) * GD + L.t;
+                const float* pa = Th + (16 * jt + L.a_row) * LDN + L.a_col;
+#pragma unroll 2
+                for (int k0 = 0; k0 < GD; k0 += 8) {
+                    uint32_t ah[4], al[4];
+                    ldsm4(ah, pa + k0);
+                    ldsm4(al, pa + NP * LDN + k0);
 #pragma unroll
-                for (int r = 0; r < MTW; ++r) {
-                    const int jt = wmg + MG * r;
-                    if (jt < MT) {
-                        uint32_t ah[4], al[4];
-                        const float* pa = Th + (16 * jt + L.a_row) * LDN + k0 + L.a_col;
-                        ldsm4(ah, pa);
-                        ldsm4(al, pa + NP * LDN);
-                        mma3f(c[r], ah, al, b0, b1);
+                    for (int nt = 0; nt < NTW; ++nt)
+                        mma3f(c[nt], ah, al, __ldg(wb + 8 * nt * GD + k0), __ldg(wb + 8 * nt * GD + k0 + 4));
+                }
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float2* p = reinterpret_cast<float2*>(dGs + (16 * jt + L.g + 8 * half) * LDG + m * GD + col0 + 8 * nt + 2 * L.t);
+                        float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+                        if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
+                        *p = v;
                     }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < MTW; ++r) {
-                const int jt = wmg + MG * r;
-                if (jt >= MT) continue;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float2* p = reinterpret_cast<float2*>(dGs + (16 * jt + L.g + 8 * half) * LDG + m * GD + 8 * wnt + 2 * L.t);
-                    float2 v = make_float2(c[r][2 * half], c[r][2 * half + 1]);
-                    if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
-                    *p = v;
-                }
             }
         }
         __syncthreads();
