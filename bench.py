@@ -51,19 +51,11 @@ def parse():
     ap.add_argument("--variant", default="glove", choices=list(VARIANTS))
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="edge-tensor storage")
     ap.add_argument("--tile", type=int, default=512, help="12-document batches per GPU per step")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of the captured pass instead of eager launches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
-
-
-def read_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
 # ------------------------------------------------------------------------------- CPU oracle arm
@@ -147,9 +139,16 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                 "-lms", "25"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def count(self) -> int:
+        try:
+            with open(self.tmp.name) as f:
+                return sum(1 for _ in f)
+        except OSError:
+            return 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -184,17 +183,56 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- roofline helpers
-def kernel_bytes(name: str, bt, H: int, esz: int) -> float:
-    """Minimum HBM bytes one launch of a kernel must move (its operands once), for the batch."""
+def read_peaks():
+    """(HBM GB/s, TF32 tensor TFLOP/s, provenance).  MEASURED_PEAKS.json holds a copy bandwidth and a cuBLAS
+    bf16 GEMM rate; the projection GEMMs run kind::tf32, whose dense rate is half the bf16 one, so the
+    tensor denominator is bf16_tflops_sustained / 2 (the kernels are timed inside a long step)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return (float(pk["hbm_gbs"]), float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])) / 2.0,
+                "measured (MEASURED_PEAKS.json: hbm_gbs; bf16_tflops_sustained / 2 for kind::tf32)")
+    return 6650.0, 1400.0 / 2.0, "fallback (B200_PROFILING.md: 6.65 TB/s; 1.4 PFLOP/s sustained bf16 / 2 for tf32)"
+
+
+def kernel_bytes(name: str, bt, H: int, L: int, esz: int) -> float:
+    """Algorithmic HBM bytes of all launches of one kernel name in one step: every operand once
+    (SURVEY 8d for the edge streams; the [rows, H*128] intermediates of the block kernels likewise)."""
     n1, n2, d = bt.total_nodes, bt.total_pairs, 128
-    hd = H * d
+    node, slab = n1 * d * 4, n1 * H * d * 4           # one [rows,128] / [rows,H*128] fp32 array
     table = {
-        "edge_row_fwd<score+mean>": n2 * d * esz + n2 * 4 + n1 * d * 4,           # read e0; write A, ebar
-        "edge_row_fwd<mean>": n2 * d * esz + n1 * d * 4,                           # read e1; write ebar
-        "edge_row_bwd<score+mean>": 2 * n2 * d * esz + n2 * 4 + n1 * d * 4,        # read e0, dS, debar; write de0
-        "edge_row_bwd<mean>": n2 * d * esz + n1 * d * 4,                           # write de1
+        "edge_row_fwd<score+mean>": n2 * d * esz + n2 * 4 + node,             # read e0; write A, ebar
+        "edge_row_fwd<mean>": n2 * d * esz + node,                             # read e1; write ebar
+        "edge_row_bwd<score+mean>": 2 * n2 * d * esz + n2 * 4 + node,          # read e0, dS, debar; write de0
+        "edge_row_bwd<mean>": n2 * d * esz + node,                             # write de1
+        # MAGGC block kernels (H heads): read Zx, E, x, q; write Z_(l>0), G, F, P
+        "block_fwd<mha>": 2 * slab + 2 * node + slab * (L - 1) / L + 2 * slab + H * n2 * 4,
+        # read P, Z, G, dF, q; write dZ, dE, dq
+        "block_bwd<dq>": H * n2 * 4 + 3 * slab + node + 2 * slab + node,
+        # CAGGC block kernels (one head): read A, Zx, E, x; write Z_(l>0), G, F  /  read A, Z, G, dF; write dZ, dE, dS
+        "block_fwd<given>": n2 * 4 + 3 * node + node * (L - 1) / L + 2 * node,
+        "block_bwd<dS>": n2 * 4 + 3 * node + 2 * node + n2 * 4,
     }
     return float(table.get(name, 0.0))
+
+
+def kernel_roofline(name, launches, ms, flop, bt, H, L, esz, steps, hbm_peak, tensor_peak):
+    """{bound, achieved, peak, unit, frac} of one kernel name over the timed region (or None)."""
+    secs = ms * 1e-3
+    if secs <= 0:
+        return None
+    if flop > 0:          # dense projections: 3 TF32 MMA passes per fp32-accurate product
+        ach = 3.0 * flop / secs / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+                "fp32_equivalent_tflops": flop / secs / 1e12,
+                "note": "executed TF32 flops = 3 x 2MNK (hi*hi + hi*lo + lo*hi split for fp32 parity)"}
+    kb = kernel_bytes(name, bt, H, L, esz) * steps
+    if kb > 0:
+        ach = kb / secs / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "bytes_per_launch": kb / max(launches, 1)}
+    return None
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -276,12 +314,14 @@ def run_gpu_arm(args):
             ms = float(t.item())
         return ms, _lib.launch_count() - launches0, kern
 
+    # nvidia-smi needs ~1 s to start: the sampler runs from the warm-up steps to the end of the timed region
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     # per-kernel breakdown: an eager pass with the library's per-launch events (not the headline)
     ms_eager, launches, kern = timed(step, args.steps, with_kernel_events=True)
     graphed = None
-    if not args.no_graph:
+    if args.graph:
         from gcgcn_b200.graphs import GraphedPass
         x0.grad = e0.grad = e1.grad = None
         for p in params:
@@ -304,9 +344,15 @@ def run_gpu_arm(args):
 
         for _ in range(max(args.warmup, 3)):
             step()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:          # keep the GPU under the same load until a few samples exist
+        t_wait = time.perf_counter() + 3.0
+        while sampler.count() < 3 and time.perf_counter() < t_wait:
+            step()
+        torch.cuda.synchronize()
     ms, _, _ = timed(step, args.steps)
     clocks = sampler.stop() if sampler else {}
+    if clocks:
+        clocks["window"] = "warm-up steps + timed region (same kernels, back to back)"
     value = world * ndocs * args.steps / (ms * 1e-3)
 
     # ---- end to end from pinned host buffers (same step; H2D of inputs and D2H of results inside)
@@ -345,34 +391,46 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    peak, peak_src = read_peaks()
+    hbm_peak, tensor_peak, peak_src = read_peaks()
     step_s = ms * 1e-3 / args.steps
     alg = bt.algorithmic_bytes(esz, backward=True)
     path_gbs = alg / step_s / 1e9
-    top = None
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_tab = json.load(f)
     total_k = sum(v[1] for v in kern.values()) or 1.0
     ranked = sorted(((k, v) for k, v in kern.items() if not k.startswith("(")), key=lambda kv: -kv[1][1])
-    breakdown = [{"kernel": k, "launches": v[0], "ms_per_step": v[1] / args.steps, "share": v[1] / total_k}
-                 for k, v in ranked[:30]]
-    gaps = kern.get("(between calls)", (0, 0.0))
+    breakdown = []
+    for k, v in ranked[:30]:
+        row = {"kernel": k, "launches": v[0], "ms_per_step": v[1] / args.steps, "share": v[1] / total_k}
+        rl = kernel_roofline(k, v[0], v[1], v[2], bt, heads, layers, esz, args.steps, hbm_peak, tensor_peak)
+        if rl:
+            row.update(bound=rl["bound"], achieved=rl["achieved"], unit=rl["unit"], frac=rl["frac"])
+        breakdown.append(row)
+    gaps = kern.get("(between calls)", (0, 0.0, 0.0))
     breakdown.append({"kernel": "(time between C-ABI calls: torch packing/autograd glue)", "launches": gaps[0],
                       "ms_per_step": gaps[1] / args.steps, "share": gaps[1] / total_k})
+    top = None
     if ranked:
-        name, (cnt, tot_ms) = ranked[0]
-        per_launch_s = tot_ms * 1e-3 / cnt
-        kb = kernel_bytes(name, bt, heads, esz)
+        name, (cnt, tot_ms, flop) = ranked[0]
+        rl = kernel_roofline(name, cnt, tot_ms, flop, bt, heads, layers, esz, args.steps, hbm_peak, tensor_peak) or \
+            {"bound": "hbm", "achieved": 0.0, "peak": hbm_peak, "unit": "GB/s", "frac": 0.0}
+        tr = traffic_tab.get(name)
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(name)
-        top = {"bound": "hbm", "kernel": name, "achieved": kb / per_launch_s / 1e9 if kb else 0.0, "peak": peak,
-               "unit": "GB/s", "frac": (kb / per_launch_s / 1e9 / peak) if kb else 0.0, "traffic": traffic,
-               "bytes_per_launch": kb, "us_per_launch": per_launch_s * 1e6, "share_of_step": tot_ms / total_k,
-               "peak_source": peak_src,
-               "path_bytes_per_step": alg, "path_achieved": path_gbs, "path_frac": path_gbs / peak,
-               "path_note": "whole step: SURVEY 8d algorithmic bytes s*d*(5n^2+8n) per document / step time",
-               "kernels": breakdown}
+        if tr and "dram_bytes_per_step" in tr:      # ncu dram__bytes_read+write of this kernel, same workload
+            traffic = tr["dram_bytes_per_step"] * args.steps / max(cnt, 1)
+        top = dict(rl)
+        top.update({"kernel": name, "traffic": traffic, "traffic_source": tr.get("source") if tr else None,
+                    "launches_per_step": cnt / args.steps, "us_per_launch": tot_ms * 1e3 / cnt,
+                    "share_of_step": tot_ms / total_k, "peak_source": peak_src,
+                    "timing": "per-launch CUDA events recorded by the library on the launching stream during "
+                              "an eager pass of the same K steps",
+                    "path_bytes_per_step": alg, "path_achieved": path_gbs, "path_frac": path_gbs / hbm_peak,
+                    "path_note": "whole step: SURVEY 8d algorithmic bytes s*d*(5n^2+8n) per document / step time "
+                                 "vs the measured HBM peak",
+                    "kernels": breakdown})
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -152,13 +152,13 @@ def timing_begin(stream: int) -> None:
 
 
 def timing_end(stream: int) -> dict:
-    """{kernel name: (launches, total_ms)} since timing_begin."""
+    """{kernel name: (launches, total_ms, total_flop)} since timing_begin."""
     buf = ctypes.create_string_buffer(1 << 16)
     call("gcgcn_timing_end", stream, buf, len(buf))
     out = {}
     for line in buf.value.decode().splitlines():
-        name, cnt, ms = line.split("\t")
-        out[name] = (int(cnt), float(ms))
+        name, cnt, ms, work = line.split("\t")
+        out[name] = (int(cnt), float(ms), float(work))
     return out
 
 

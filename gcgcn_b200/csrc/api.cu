@@ -67,7 +67,8 @@ std::atomic<uint64_t> g_launches{0};
 std::atomic<bool> g_timing{false};
 
 namespace {
-struct Mark { const char* name; cudaEvent_t ev; cudaStream_t st; };
+struct Mark { const char* name; cudaEvent_t ev; cudaStream_t st; double work; };
+thread_local double g_pending_work = 0.0;
 std::mutex g_tmutex;
 std::vector<Mark> g_marks;
 std::vector<cudaEvent_t> g_event_pool;
@@ -84,7 +85,12 @@ void timing_mark(const char* name, cudaStream_t st) {
     cudaEvent_t e = take_event();
     if (e == nullptr) return;
     cudaEventRecord(e, st);
-    g_marks.push_back({name, e, st});
+    g_marks.push_back({name, e, st, g_pending_work});
+    g_pending_work = 0.0;
+}
+
+void timing_set_work(double work) {
+    if (g_timing.load(std::memory_order_relaxed)) g_pending_work = work;
 }
 
 char* error_buffer() {
@@ -225,12 +231,12 @@ int gcgcn_timing_begin(void* stream) {
     cudaEvent_t e = take_event();
     if (e == nullptr) return fail(GCGCN_ERR_CUDA, "timing_begin: cannot create an event");
     GCGCN_TRY(cuda_ok(cudaEventRecord(e, static_cast<cudaStream_t>(stream)), "timing_begin"));
-    g_marks.push_back({"(begin)", e, static_cast<cudaStream_t>(stream)});
+    g_marks.push_back({"(begin)", e, static_cast<cudaStream_t>(stream), 0.0});
     g_timing.store(true);
     return GCGCN_OK;
 }
 
-// writes one line per kernel name: "<name>\t<launches>\t<total milliseconds>\n"
+// writes one line per kernel name: "<name>\t<launches>\t<total milliseconds>\t<total work (flop)>\n"
 int gcgcn_timing_end(void* stream, char* buf, size_t cap) {
     g_timing.store(false);
     std::lock_guard<std::mutex> lk(g_tmutex);
@@ -240,7 +246,8 @@ int gcgcn_timing_end(void* stream, char* buf, size_t cap) {
     if (g_marks.empty()) return GCGCN_OK;
     GCGCN_TRY(cuda_ok(cudaEventSynchronize(g_marks.back().ev), "timing_end"));
     GCGCN_TRY(cuda_ok(cudaDeviceSynchronize(), "timing_end"));
-    std::map<std::string, std::pair<long, double>> acc;
+    struct Acc { long count = 0; double ms = 0.0, work = 0.0; };
+    std::map<std::string, Acc> acc;
     std::map<cudaStream_t, cudaEvent_t> last;          // a kernel's time = gap to the previous mark on ITS stream
     for (size_t i = 0; i < g_marks.size(); ++i) {
         auto it = last.find(g_marks[i].st);
@@ -252,8 +259,9 @@ int gcgcn_timing_end(void* stream, char* buf, size_t cap) {
                 // chain reset only
             } else if (cudaEventElapsedTime(&ms, it->second, g_marks[i].ev) == cudaSuccess) {
                 auto& slot = acc[g_marks[i].name];
-                slot.first += 1;
-                slot.second += ms;
+                slot.count += 1;
+                slot.ms += ms;
+                slot.work += g_marks[i].work;
             } else {
                 cudaGetLastError();
             }
@@ -262,7 +270,8 @@ int gcgcn_timing_end(void* stream, char* buf, size_t cap) {
     }
     size_t off = 0;
     for (auto& kv : acc) {
-        int w = snprintf(buf + off, cap - off, "%s\t%ld\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        int w = snprintf(buf + off, cap - off, "%s\t%ld\t%.6f\t%.6e\n", kv.first.c_str(), kv.second.count, kv.second.ms,
+                         kv.second.work);
         if (w < 0 || static_cast<size_t>(w) >= cap - off) break;
         off += static_cast<size_t>(w);
     }

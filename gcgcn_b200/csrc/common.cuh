@@ -25,6 +25,8 @@ extern std::atomic<uint64_t> g_launches;
 // every API entry; a kernel's time is the gap to the previous event on the same stream.
 extern std::atomic<bool> g_timing;
 void timing_mark(const char* name, cudaStream_t st);
+// floating-point operations (or bytes) the NEXT marked launch performs; summed per kernel name by timing_end
+void timing_set_work(double work);
 
 inline int cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return GCGCN_OK;

@@ -287,23 +287,30 @@ gat_node_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restric
 }
 
 // out[c] = sum_p partial[p][c]  (deterministic second stage of every cross-CTA reduction)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, int parts, int width,
                        float* __restrict__ out0, int width0, float* __restrict__ out1) {
-    // block = 32 columns x 8 row lanes; lane r adds parts r, r+8, ... in order, then the 8 lane sums are
-    // added in a fixed order, so the result does not depend on scheduling
-    __shared__ float red[8][33];
+    // block = 32 columns x 32 row lanes; lane r adds parts r, r+32, ... in order (two interleaved chains, so
+    // two loads are in flight), then the 32 lane sums are added in a fixed order: the result does not depend on
+    // scheduling
+    __shared__ float red[32][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
-    float s = 0.f;
-    if (c < width)
-        for (int p = rl; p < parts; p += 8) s += partial[static_cast<size_t>(p) * width + c];
-    red[rl][cl] = s;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < width) {
+        int p = rl;
+        for (; p + 32 < parts; p += 64) {
+            s0 += partial[static_cast<size_t>(p) * width + c];
+            s1 += partial[static_cast<size_t>(p + 32) * width + c];
+        }
+        if (p < parts) s0 += partial[static_cast<size_t>(p) * width + c];
+    }
+    red[rl][cl] = s0 + s1;
     __syncthreads();
     if (rl == 0 && c < width) {
         float t = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += red[r][cl];
+        for (int r = 0; r < 32; ++r) t += red[r][cl];
         if (c < width0) out0[c] = t;
         else if (out1 != nullptr) out1[c - width0] = t;
     }
@@ -419,7 +426,7 @@ int launch_gat_node_bwd(const gcgcn_batch* bt, const float* dS, const float* x, 
 
 int launch_reduce_partials(const float* partial, int parts, int width, float* out0, int width0,
                            float* out1, cudaStream_t st) {
-    reduce_partials_kernel<<<ceil_div(width, 32), 256, 0, st>>>(partial, parts, width, out0, width0,
+    reduce_partials_kernel<<<ceil_div(width, 32), 1024, 0, st>>>(partial, parts, width, out0, width0,
                                                                 out1);
     GCGCN_CHECK_LAUNCH("reduce_partials");
     return GCGCN_OK;

@@ -146,13 +146,56 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
     if (idx >= total) return;
     partial += static_cast<size_t>(blockIdx.y) * splits * total;      // batched: one product per blockIdx.y
     C += static_cast<size_t>(blockIdx.y) * batch_stride_c;
-    float s = 0.f;
-    for (int p = 0; p < splits; ++p) s += partial[p * total + idx];
+    // four interleaved partial sums in a fixed order (deterministic, 4 loads in flight)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 4 <= splits; p += 4) {
+        s0 += partial[(p + 0) * total + idx];
+        s1 += partial[(p + 1) * total + idx];
+        s2 += partial[(p + 2) * total + idx];
+        s3 += partial[(p + 3) * total + idx];
+    }
+    for (; p < splits; ++p) s0 += partial[p * total + idx];
+    const float s = (s0 + s1) + (s2 + s3);
     const int m = static_cast<int>(idx / N), n = static_cast<int>(idx - static_cast<size_t>(m) * N);
     float v = alpha * s;
     if (bias != nullptr) v += bias[n];
     float* c = C + static_cast<size_t>(m) * ldc + n;
     if (beta != 0.f) v += beta * (*c);
+    *c = v;
+}
+
+// same, four consecutive columns per thread (N, ldc multiples of 4)
+__global__ void __launch_bounds__(256)
+splitk_reduce4_kernel(const float* __restrict__ partial, int splits, int M, int N, float alpha, float beta,
+                      float* __restrict__ C, int ldc, const float* __restrict__ bias, long long batch_stride_c) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;    // float4 index
+    const size_t total4 = static_cast<size_t>(M) * N / 4;
+    if (idx >= total4) return;
+    const float4* part = reinterpret_cast<const float4*>(partial) + static_cast<size_t>(blockIdx.y) * splits * total4;
+    C += static_cast<size_t>(blockIdx.y) * batch_stride_c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    int p = 0;
+    for (; p + 2 <= splits; p += 2) {
+        const float4 u = part[(p + 0) * total4 + idx], w = part[(p + 1) * total4 + idx];
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+    }
+    if (p < splits) {
+        const float4 u = part[p * total4 + idx];
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+    }
+    const int m = static_cast<int>(idx / (N / 4)), n = static_cast<int>(idx - static_cast<size_t>(m) * (N / 4)) * 4;
+    float4 v = make_float4(alpha * (a.x + b.x), alpha * (a.y + b.y), alpha * (a.z + b.z), alpha * (a.w + b.w));
+    if (bias != nullptr) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias + n);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    }
+    float4* c = reinterpret_cast<float4*>(C + static_cast<size_t>(m) * ldc + n);
+    if (beta != 0.f) {
+        const float4 cur = *c;
+        v.x += beta * cur.x; v.y += beta * cur.y; v.z += beta * cur.z; v.w += beta * cur.w;
+    }
     *c = v;
 }
 
@@ -169,14 +212,44 @@ colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ldx, int ro
     partial[static_cast<size_t>(blockIdx.y) * N + c] = s;
 }
 
+// N == 128 fast path: block = 32 float4 column lanes x 8 row lanes, fixed-order combine
+__global__ void __launch_bounds__(256)
+colsum128_partial_kernel(const float* __restrict__ X, int M, int ldx, int rows_per_block, float* __restrict__ partial) {
+    __shared__ float4 red[8][32];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0 + rl; r < r1; r += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(X + static_cast<size_t>(r) * ldx + 4 * cl);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    red[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0) {
+        float4 t = red[0][cl];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) { const float4 v = red[r][cl]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        *reinterpret_cast<float4*>(partial + static_cast<size_t>(blockIdx.x) * 128 + 4 * cl) = t;
+    }
+}
+
 int launch_reduce_partials(const float* partial, int parts, int width, float* out0, int width0,
                            float* out1, cudaStream_t st);
 
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, float alpha, float beta, float* C,
                          int ldc, const float* bias, cudaStream_t st, int batch = 1, long long sC = 0) {
     const size_t total = static_cast<size_t>(M) * N;
-    dim3 grid(ceil_div(total, 256), batch);
-    splitk_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias, sC);
+    const bool vec = N % 4 == 0 && ldc % 4 == 0 && sC % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(partial) & 15) == 0 &&
+                     (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    if (vec) {
+        dim3 grid(ceil_div(total / 4, 256), batch);
+        splitk_reduce4_kernel<<<grid, 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias, sC);
+    } else {
+        dim3 grid(ceil_div(total, 256), batch);
+        splitk_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias, sC);
+    }
     GCGCN_CHECK_LAUNCH("splitk_reduce");
     return GCGCN_OK;
 }
@@ -221,6 +294,7 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
     else if (ta && !tb) GCGCN_GEMM(true, false);
     else GCGCN_GEMM(true, true);
 #undef GCGCN_GEMM
+    timing_set_work(2.0 * M * N * K);
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tt" : "gemm_tn") : (tb ? "gemm_nt" : "gemm_nn"));
     if (splits > 1) GCGCN_TRY(launch_splitk_reduce(partial, splits, M, N, alpha, beta, C, ldc, bias, st));
     return GCGCN_OK;
@@ -246,6 +320,15 @@ int launch_gemm_batched(int ta, int tb, int M, int N, int K, float alpha, const 
 int launch_colsum(const float* X, int M, int N, int ldx, float* out, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
     if (N <= 0) return GCGCN_OK;
+    if (N == D && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && M > 0) {
+        const int rows_per_block = max(64, ceil_div(M, sm_count() * 4));
+        const int parts = ceil_div(M, rows_per_block);
+        if (ws == nullptr || ws_bytes < static_cast<size_t>(parts) * N * sizeof(float))
+            return fail(GCGCN_ERR_WORKSPACE, "colsum: workspace too small");
+        colsum128_partial_kernel<<<parts, 256, 0, st>>>(X, M, ldx, rows_per_block, static_cast<float*>(ws));
+        GCGCN_CHECK_LAUNCH("colsum_partial");
+        return launch_reduce_partials(static_cast<const float*>(ws), parts, N, out, N, nullptr, st);
+    }
     int parts = max(1, min(ceil_div(M, 64), sm_count() * 16));
     const size_t need = static_cast<size_t>(parts) * N * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return fail(GCGCN_ERR_WORKSPACE, "colsum: workspace too small");

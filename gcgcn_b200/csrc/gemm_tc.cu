@@ -440,7 +440,8 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     const int sms = sm_count();
     int splits = 1;
     if (tiles < sms && K >= 4096) {
-        splits = std::min(ceil_div(2 * sms, tiles), ceil_div(K, 512));
+        // one wave: as many K slices as fit the SMs without a second, partially filled wave
+        splits = std::min(std::max(sms / tiles, 1), ceil_div(K, 512));
         const size_t per = static_cast<size_t>(M) * N * sizeof(float) * batch;
         if (ws == nullptr) splits = 1;
         else splits = static_cast<int>(std::min<size_t>(splits, ws_bytes / per));
@@ -474,6 +475,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3);
     else GCGCN_TC_LAUNCH(false, false, 2);
 #undef GCGCN_TC_LAUNCH
+    timing_set_work(2.0 * M * N * K * batch);
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));

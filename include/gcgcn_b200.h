@@ -75,7 +75,8 @@ uint64_t gcgcn_launch_count(void);
 /* fills SM count and compute capability of the current device */
 int gcgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* per-kernel timing for bench.py: begin() starts recording one CUDA event after every launch on
- * `stream`; end() synchronises and writes "<kernel>\t<launches>\t<total ms>\n" lines into buf. */
+ * `stream`; end() synchronises and writes "<kernel>\t<launches>\t<total ms>\t<total flop>\n" lines
+ * into buf (flop: 2MNK summed over the launches of the dense-projection kernels, 0 for the others). */
 int gcgcn_timing_begin(void* stream);
 int gcgcn_timing_end(void* stream, char* buf, size_t cap);
 /* upper bound, in bytes, of the workspace any entry point below needs for this batch shape */
