@@ -29,17 +29,18 @@ int launch_mha_fwd(const gcgcn_batch* bt, int heads, const float* q, const float
 int launch_mha_bwd(const gcgcn_batch* bt, int heads, const float* q, const float* dS, float* dq, cudaStream_t st);
 int launch_stack_fwd(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A, float* Z,
                      const float* E, const float* Winner, const float* keep, const float* x, float* G, float* F,
-                     cudaStream_t st);
+                     float* frag_ws, cudaStream_t st);
 int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A, const float* Z,
                      const float* G, const float* Winner, const float* keep, const float* dF, float* dZ,
-                     float* dE, float* dA, cudaStream_t st);
+                     float* dE, float* dA, float* frag_ws, cudaStream_t st);
 bool block_kernels_usable(const gcgcn_batch* bt, int heads, int layers, int slab, bool mha);
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
-                     cudaStream_t st);
+                     float* frag_ws, cudaStream_t st);
 int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode, const float* A, const float* q,
                      const float* Z, const float* G, const float* Winner, const float* dF, float* dZ, float* dE,
-                     float* dOut, cudaStream_t st);
+                     float* dOut, float* frag_ws, cudaStream_t st);
+size_t block_frag_floats(int heads, int layers);
 enum { ATT_GRAD_DA = 0, ATT_GRAD_DS = 1, ATT_GRAD_DQ = 2 };   // == BK_OUT_* of gcn_block.cu
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                 int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
@@ -220,6 +221,7 @@ size_t gcgcn_workspace_bytes(int32_t total_nodes, int64_t total_pairs, int32_t h
     b += align256(pairs * (heads < 1 ? 1 : heads) * sizeof(float));    // dS
     b += 2 * align256(nodes * D * sizeof(float));                      // dq / ux / misc
     b += GEMM_WS_BYTES + (size_t(8) << 20);                            // split-K and reduction partials
+    b += size_t(4) << 20;                                              // fragment-ordered dense-connect weights
     return b;
 }
 
@@ -441,14 +443,15 @@ static int stack_fwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
     Arena ar(ws, ws_bytes);
     float* E = ar.take<float>(static_cast<size_t>(M) * HD);
     float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
+    float* frag = (slab == D && layers > 1 && D % layers == 0) ? ar.take<float>(block_frag_floats(heads, layers)) : nullptr;
     if (E == nullptr || gws == nullptr) return fail(GCGCN_ERR_WORKSPACE, "stack_fwd: workspace too small");
     GCGCN_TRY(launch_gemm(0, 0, M, HD, in_dim, 1.f, x, in_dim, WnX, HD, 0.f, Z, HD, nullptr, gws, GEMM_WS_BYTES, st));
     GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, ebar, D, We, HD, 0.f, E, HD, nullptr, gws, GEMM_WS_BYTES, st));
     float* Fout = linear ? F : y;
     if (q != nullptr)
-        GCGCN_TRY(launch_block_fwd(bt, heads, layers, nullptr, q, P, Z, E, Winner, x, G, Fout, st));
+        GCGCN_TRY(launch_block_fwd(bt, heads, layers, nullptr, q, P, Z, E, Winner, x, G, Fout, frag, st));
     else
-        GCGCN_TRY(launch_stack_fwd(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, Fout, st));
+        GCGCN_TRY(launch_stack_fwd(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, Fout, frag, st));
     if (linear)
         GCGCN_TRY(launch_gemm(0, 1, M, D, HD, 1.f, F, HD, Wout, HD, 0.f, y, D, bout, gws, GEMM_WS_BYTES, st));
     return GCGCN_OK;
@@ -496,6 +499,7 @@ static int stack_bwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
     float* dZ = ar.take<float>(static_cast<size_t>(M) * HD);
     float* dE = ar.take<float>(static_cast<size_t>(M) * HD);
     float* gws = ar.take<float>(GEMM_WS_BYTES / sizeof(float));
+    float* frag = (slab == D && layers > 1 && D % layers == 0) ? ar.take<float>(block_frag_floats(heads, layers)) : nullptr;
     if ((linear && dFbuf == nullptr) || dZ == nullptr || dE == nullptr || gws == nullptr)
         return fail(GCGCN_ERR_WORKSPACE, "stack_bwd: workspace too small");
     const float* dF = dy;
@@ -507,9 +511,9 @@ static int stack_bwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
         dF = dFbuf;
     }
     if (att_grad == ATT_GRAD_DA)
-        GCGCN_TRY(launch_stack_bwd(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, att_out, st));
+        GCGCN_TRY(launch_stack_bwd(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, att_out, frag, st));
     else
-        GCGCN_TRY(launch_block_bwd(bt, heads, layers, att_grad, A, q, Z, G, Winner, dF, dZ, dE, att_out, st));
+        GCGCN_TRY(launch_block_bwd(bt, heads, layers, att_grad, A, q, Z, G, Winner, dF, dZ, dE, att_out, frag, st));
     // dx = [residual: sum_h dF_h] + dZ WnX^T ; debar = dE We^T
     float beta = 0.f;
     if (flags & GCGCN_STACK_RESIDUAL) {

@@ -95,6 +95,46 @@ __host__ __device__ constexpr int col_tiles_per_warp(int mt, int nt) {
     return w;
 }
 
+// ---- dense-connect weights in MMA-fragment order ----------------------------------------------------
+// The B fragments of the dense-connect products come straight from global memory (16-24 KB per head, L1/L2
+// resident).  Read from the row-major Winner block, one fragment load touches 4-8 different 32-byte sectors;
+// re-ordered once per call so that the 32 lanes of a fragment register are contiguous -- and already split
+// into hi/lo -- it is one 128-byte line per register.
+//   forward  (B(k, n) = W_l[k][n]):            Wf[h][l][ks][nt][q][lane],      k = 8 ks + t + 4 (q & 1), n = 8 nt + g
+//   backward (B(k, n) = W_l[m gd + n][k]):     Wb[h][l][m][ks][nt][q][lane],   k = 8 ks + t + 4 (q & 1), n = 8 nt + g
+// q = {hi b0, hi b1, lo b0, lo b1}, lane = 4 g + t.  Both arrays hold heads * layers * KI * gd * 2 floats.
+size_t block_frag_floats(int heads, int layers) {
+    const int gd = D / layers, ki = (layers - 1) * gd;
+    return 2 * static_cast<size_t>(heads) * layers * ki * gd * 2;      // Wf then Wb
+}
+
+__global__ void __launch_bounds__(256)
+winner_frag_kernel(const float* __restrict__ Winner, int layers, int gd, float* __restrict__ Wf, float* __restrict__ Wb) {
+    const int hl = blockIdx.x, l = hl % layers;
+    const int ki = (layers - 1) * gd, nt_n = gd / 8;
+    const size_t per = static_cast<size_t>(ki) * gd * 2;
+    const float* W = Winner + static_cast<size_t>(hl) * D * gd;           // [128][gd] block of GraphConv (h, l)
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < static_cast<int>(per); idx += gridDim.y * blockDim.x) {
+        const int lane = idx & 31, q = (idx >> 5) & 3, g = lane >> 2, t = lane & 3;
+        const int rest = idx >> 7;                                        // (ks, nt) forward; (m, ks, nt) backward
+        const int nt = rest % nt_n;
+        {   // forward order
+            const int ks = rest / nt_n;
+            const int k = 8 * ks + t + 4 * (q & 1), n = 8 * nt + g;
+            const float v = k < l * gd ? W[static_cast<size_t>(k) * gd + n] : 0.f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            Wf[hl * per + idx] = (q & 2) ? v - hi : hi;
+        }
+        {   // backward order
+            const int ks = (rest / nt_n) % nt_n, m = rest / (nt_n * nt_n);
+            const int k = 8 * ks + t + 4 * (q & 1), row = m * gd + 8 * nt + g;
+            const float v = m < l ? W[static_cast<size_t>(row) * gd + k] : 0.f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            Wb[hl * per + idx] = (q & 2) ? v - hi : hi;
+        }
+    }
+}
+
 // Per-lane geometry shared by both kernels.
 //   ldmatrix A fragment (16 rows x 8 k): lane supplies row a_row, k offset a_col of the tile
 //   ldmatrix B fragment, operand stored [n][k] (hi and lo planes in one x4): row b_row, k offset b_col, plane b_lo
@@ -118,7 +158,7 @@ template <int GD, int DH, int MTC>
 __global__ void __launch_bounds__(BK_THREADS, 3)
 block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
                  const float* __restrict__ A, const float* __restrict__ q, float* __restrict__ P,
-                 float* __restrict__ Z, const float* __restrict__ E, const float* __restrict__ Winner,
+                 float* __restrict__ Z, const float* __restrict__ E, const float* __restrict__ Wf,
                  const float* __restrict__ x, float* __restrict__ G, float* __restrict__ F, int heads,
                  long long total_pairs, const int* __restrict__ doc_order, int first, float scale) {
     extern __shared__ __align__(16) float smem[];
@@ -270,7 +310,8 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         if (l > 0) {
             // Z_l += g_{<l} Winner_l   (dense connection, row-local in the reference: G:72-73)
             if (busy) {
-                const float* wb = Winner + (static_cast<size_t>(h) * layers + l) * S * GD + L.t * GD + col0 + L.g;
+                // fragment-ordered hi/lo weights: [ks][nt][4][32] floats per (head, sub-layer)
+                const float* wb = Wf + (static_cast<size_t>(h) * layers + l) * (KI * GD * 2) + (col0 / 8) * 128 + L.lane;
 #pragma unroll
                 for (int nt = 0; nt < NTW; ++nt) {
                     const float2 lo2 = *reinterpret_cast<const float2*>(zc + 8 * nt);
@@ -284,8 +325,11 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                     ldsm4(ah, pa + k0);
                     ldsm4(al, pa + NP * LDG + k0);
 #pragma unroll
-                    for (int nt = 0; nt < NTW; ++nt)
-                        mma3f(c[nt], ah, al, __ldg(wb + k0 * GD + 8 * nt), __ldg(wb + (k0 + 4) * GD + 8 * nt));
+                    for (int nt = 0; nt < NTW; ++nt) {
+                        const float* f = wb + (k0 / 8) * (GD / 8) * 128 + nt * 128;
+                        mma3(c[nt], ah, al, __float_as_uint(__ldg(f)), __float_as_uint(__ldg(f + 32)),
+                             __float_as_uint(__ldg(f + 64)), __float_as_uint(__ldg(f + 96)));
+                    }
                 }
 #pragma unroll
                 for (int nt = 0; nt < NTW; ++nt) {
@@ -369,7 +413,7 @@ template <int GD, int DH, int OUT, int MTC>
 __global__ void __launch_bounds__(BK_THREADS, 3)
 block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
                  const float* __restrict__ A, const float* __restrict__ q, const float* __restrict__ Z,
-                 const float* __restrict__ G, const float* __restrict__ Winner, const float* __restrict__ dF,
+                 const float* __restrict__ G, const float* __restrict__ Wb, const float* __restrict__ dF,
                  float* __restrict__ dZ, float* __restrict__ dE, float* __restrict__ dOut, int heads,
                  long long total_pairs, const int* __restrict__ doc_order, int first, float scale) {
     extern __shared__ __align__(16) float smem[];
@@ -427,7 +471,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     const int cg = tid % CG, rg = tid / CG, c0 = cg * 4;
 #pragma unroll
     for (int l = layers - 1; l >= 0; --l) {
-        const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
+        const float* wsrc = Wb + (static_cast<size_t>(h) * layers + l) * (KI * GD * 2);   // [m][ks][nt][4][32]
         const bool first_layer = (l == layers - 1);
         // (a) row-local: dG_l -> dN_l (shared), dE_l (global), dr (shared); Z_l -> shared
 #pragma unroll
@@ -542,7 +586,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 float c[NTW][4];
 #pragma unroll
                 for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
-                const float* wb = wsrc + (m * GD + col0 + L.g) * GD + L.t;
+                const float* wb = wsrc + m * (GD * GD * 2) + (col0 / 8) * 128 + L.lane;
                 const float* pa = Th + (16 * jt + L.a_row) * LDN + L.a_col;
 #pragma unroll 2
                 for (int k0 = 0; k0 < GD; k0 += 8) {
@@ -550,8 +594,11 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                     ldsm4(ah, pa + k0);
                     ldsm4(al, pa + NP * LDN + k0);
 #pragma unroll
-                    for (int nt = 0; nt < NTW; ++nt)
-                        mma3f(c[nt], ah, al, __ldg(wb + 8 * nt * GD + k0), __ldg(wb + 8 * nt * GD + k0 + 4));
+                    for (int nt = 0; nt < NTW; ++nt) {
+                        const float* f = wb + (k0 / 8) * (GD / 8) * 128 + nt * 128;
+                        mma3(c[nt], ah, al, __float_as_uint(__ldg(f)), __float_as_uint(__ldg(f + 32)),
+                             __float_as_uint(__ldg(f + 64)), __float_as_uint(__ldg(f + 96)));
+                    }
                 }
 #pragma unroll
                 for (int nt = 0; nt < NTW; ++nt)
@@ -730,10 +777,21 @@ static int launch_fwd_all(const gcgcn_batch* bt, int heads, const float* A, cons
 }
 
 // A != nullptr: attention given (q, P unused).  A == nullptr: MHA from q, P written.
+static int launch_winner_frag(const float* Winner, int heads, int layers, float* frag_ws, cudaStream_t st) {
+    if (layers < 2) return GCGCN_OK;
+    if (frag_ws == nullptr) return fail(GCGCN_ERR_WORKSPACE, "block kernels: no workspace for the fragment-ordered weights");
+    const size_t half = block_frag_floats(heads, layers) / 2;
+    winner_frag_kernel<<<dim3(heads * layers, 8), 256, 0, st>>>(Winner, layers, D / layers, frag_ws, frag_ws + half);
+    GCGCN_CHECK_LAUNCH("winner_frag");
+    return GCGCN_OK;
+}
+
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
-                     float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
-                     cudaStream_t st) {
+                     float* Z, const float* E, const float* Winner_rowmajor, const float* x, float* G, float* F,
+                     float* frag_ws, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
+    GCGCN_TRY(launch_winner_frag(Winner_rowmajor, heads, layers, frag_ws, st));
+    const float* Winner = frag_ws;                      // forward-ordered half
     const int gd = D / layers;
     const int dh = A != nullptr ? 0 : D / heads;
     const float scale = dh > 0 ? 1.0f / sqrtf(static_cast<float>(dh)) : 1.f;
@@ -782,9 +840,11 @@ static int launch_bwd_all(const gcgcn_batch* bt, int heads, const float* A, cons
 // out_mode: BK_OUT_DA -> dOut = dA [heads][total_pairs]; BK_OUT_DS -> dOut = dS (same shape; A must be a softmax
 // output); BK_OUT_DQ -> dOut = dq [total_nodes][128] (A = the MHA probabilities, q their query projection).
 int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode, const float* A, const float* q,
-                     const float* Z, const float* G, const float* Winner, const float* dF, float* dZ, float* dE,
-                     float* dOut, cudaStream_t st) {
+                     const float* Z, const float* G, const float* Winner_rowmajor, const float* dF, float* dZ, float* dE,
+                     float* dOut, float* frag_ws, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
+    GCGCN_TRY(launch_winner_frag(Winner_rowmajor, heads, layers, frag_ws, st));
+    const float* Winner = frag_ws == nullptr ? nullptr : frag_ws + block_frag_floats(heads, layers) / 2;   // backward-ordered half
     const int gd = D / layers;
     const int dh = out_mode == BK_OUT_DQ ? D / heads : 0;
     const float scale = dh > 0 ? 1.0f / sqrtf(static_cast<float>(dh)) : 1.f;
