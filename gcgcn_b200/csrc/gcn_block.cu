@@ -9,13 +9,19 @@
 //             then, without leaving the CTA, the softmax backward dS = P (dA - rowsum(dA P)) and either
 //             dq_h = scale (dS + dS^T) q_h  (MHA)  or dS itself (GAT; the edge pass consumes it).
 //
-// Why a second generation of the stack kernel (gcn_stack_mma.cu): ncu showed the first one latency bound
-// (long-scoreboard stalls on five dependent global round trips per CTA, 30-45 % of the SM's warps
-// resident).  Here every global read a CTA needs is issued up front -- the per-sub-layer projection tiles
-// with cp.async into a two-deep shared-memory ring, the epilogue operands into registers ahead of the
-// MMA loop that precedes their use -- the attention map / its gradient never leave shared memory between
-// sub-layers, and the softmax, its backward and the dq reduction ride along instead of being three more
-// passes over [H][sum n^2] arrays in HBM.
+// Why a second generation of the stack kernel (gcn_stack_mma.cu), and what ncu said at each step:
+//   1. the first kernel was latency bound (long-scoreboard stalls on five dependent global round trips per
+//      CTA): here the per-sub-layer projection tiles arrive by cp.async into a two-deep ring and the epilogue
+//      operands are loaded ahead of the MMA loop that precedes their use; the attention map and its gradient
+//      never leave shared memory between sub-layers; the softmax, its backward and the dq reduction ride
+//      along instead of being three more passes over [H][sum n^2] arrays in HBM;
+//   2. then it was instruction bound with HMMA at 13 % of the issued instructions (fragment loads as scalar LDS,
+//      the hi/lo split redone per fragment use, run-time strides): operands are split once into hi/lo planes,
+//      fragments come from ldmatrix, and every size class (16/32/48/64 rows) is its own instantiation so that
+//      strides are immediates and the tile loops unroll;
+//   3. then the L1/shared pipe was the limiter (80-90 %): one row tile x several column tiles per warp (the
+//      1 KB row fragment is read once per 2-4 cheap column fragments) and the dense-connect weights are read in
+//      MMA-fragment order (one 128-byte line per fragment register instead of 4-8 sectors).
 //
 // All small matrix products run on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, see
 // mma_tf32.cuh).  Block configuration only: slab = in_dim = 128, ReLU + residual, no dropout masks
