@@ -50,6 +50,8 @@ struct TcArgs {
     float* partial;     // != nullptr -> split-K partial output [k_splits][M][N]
     float alpha, beta;
     int tiles_m, tiles_n, k_splits, k_per_split;
+    const uint8_t* Bpre;            // != nullptr -> B operand pre-split into ready-to-copy stage blobs [tiles_n][kblocks]
+    int kblocks;                    // ceil(K / TC_BK), blob index stride of Bpre
     int batch;                      // independent products per launch (same shapes, strided operands)
     long long sA, sB, sC;           // element strides between consecutive products
 };
@@ -75,6 +77,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(bar), "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one bulk copy global -> shared; completion is signalled to the mbarrier as `bytes` of its transaction count
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -208,7 +219,12 @@ __device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, con
     }
 }
 
-template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS>
+// BPRE: the B operand is a weight matrix that tc_presplit_b_kernel has already split and laid out as one
+// ready-to-copy blob per (column tile, K block): a single bulk copy per stage replaces the B half of the
+// producers' work, and the registers it frees double-buffer the A loads (two K blocks in flight per group).
+constexpr uint32_t TC_B_BLOB_BYTES = 2 * TC_PART_BYTES;     // B_hi part, B_lo part
+
+template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS, bool BPRE>
 __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const TcArgs args) {
     constexpr int TC_PRODUCER_WARPS = 4 * GROUPS, TC_MMA_WARP = 4 * GROUPS, TC_GROUPS = GROUPS;
     // (no integer round trip on this pointer: the compiler must keep seeing shared memory, or every
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(full_bar(s), 4);    // one arrive per producer warp
+            mbar_init(full_bar(s), BPRE ? 5 : 4);   // one arrive per producer warp (+ the expect_tx arrive of the B blob)
             mbar_init(empty_bar(s), 1);   // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -252,8 +268,48 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
         const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0) && (args.sA % 4 == 0);
         const bool b_vec = (args.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.B) & 15) == 0) && (args.sB % 4 == 0);
         const int group = warp >> 2, tid = threadIdx.x & 127;
+        if (BPRE) {
+            // (batch == 1, k_splits == 1)  flat sequence q of this CTA's K blocks; this group takes q = group (mod GROUPS)
+            const int kblocks = args.kblocks;
+            const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - 1 - blockIdx.x) / static_cast<int>(gridDim.x) + 1 : 0;
+            const int total_q = my_tiles * kblocks;
+            auto fetch = [&](int q, float4 (&v)[8]) {
+                const int tile = blockIdx.x + (q / kblocks) * gridDim.x, kb = q % kblocks;
+                fetch_operand<A_KCONTIG>(args.A, args.lda, (tile / args.tiles_n) * TC_BM, args.M, kb * TC_BK, args.K, a_vec,
+                                         tid, v);
+            };
+            auto commit = [&](int q, const float4 (&v)[8]) {
+                const int stage = q % TC_STAGES;
+                const uint32_t phase = (q / TC_STAGES) & 1;
+                mbar_wait(empty_bar(stage), phase ^ 1);      // the MMAs that read this stage have retired
+                uint8_t* stb = smem + size_t(stage) * TC_STAGE_BYTES;
+                if (tid == 0) {
+                    const int tile = blockIdx.x + (q / kblocks) * gridDim.x, kb = q % kblocks;
+                    const uint8_t* blob = args.Bpre + (static_cast<size_t>(tile % args.tiles_n) * kblocks + kb) * TC_B_BLOB_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), TC_B_BLOB_BYTES);
+                    bulk_copy_g2s(smem_u32(stb + 2 * TC_PART_BYTES), blob, TC_B_BLOB_BYTES, full_bar(stage));
+                }
+                float* st = reinterpret_cast<float*>(stb);
+                store_operand<A_KCONTIG>(st, st + TC_PART_BYTES / 4, tid, v);
+                fence_proxy_async();          // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(stage));
+            };
+            float4 va0[8], va1[8];
+            int q = group;
+            if (q < total_q) fetch(q, va0);
+            while (q < total_q) {
+                if (q + GROUPS < total_q) fetch(q + GROUPS, va1);
+                commit(q, va0);
+                q += GROUPS;
+                if (q >= total_q) break;
+                if (q + GROUPS < total_q) fetch(q + GROUPS, va0);
+                commit(q, va1);
+                q += GROUPS;
+            }
+        }
         int j = 0;                                   // running K-block index of this CTA
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; !BPRE && t < total_tiles; t += gridDim.x) {
             const int bi = t / (tiles_mn * args.k_splits), tb = t - bi * (tiles_mn * args.k_splits);
             const int ks = tb / tiles_mn, rem = tb - ks * tiles_mn;
             const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
@@ -411,6 +467,39 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+// One blob per (128-column tile nt, 32-wide K block kb) of the N x K operand op(B)^T: exactly the B_hi / B_lo half of
+// a shared-memory stage (8 chunk planes of [128 rows][16 B] + pad each), so the GEMM moves it with one bulk copy.
+__global__ void __launch_bounds__(256)
+tc_presplit_b_kernel(const float* __restrict__ B, int ldb, int b_kcontig, int N, int K, int kblocks,
+                     uint8_t* __restrict__ blobs) {
+    const int blob = blockIdx.x, nt = blob / kblocks, kb = blob - nt * kblocks;
+    const int n0 = nt * TC_BN, k0 = kb * TC_BK;
+    float* hi = reinterpret_cast<float*>(blobs + static_cast<size_t>(blob) * TC_B_BLOB_BYTES);
+    float* lo = hi + TC_PART_BYTES / 4;
+    for (int idx = threadIdx.x; idx < TC_BN * (TC_BK / 4); idx += 256) {
+        int r, c;
+        if (b_kcontig) { c = idx & 7; r = idx >> 3; } else { r = idx & (TC_BN - 1); c = idx >> 7; }
+        const int n = n0 + r, k = k0 + 4 * c;
+        float t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            t[q] = 0.f;
+            if (n < N && k + q < K)
+                t[q] = b_kcontig ? B[static_cast<size_t>(n) * ldb + k + q] : B[static_cast<size_t>(k + q) * ldb + n];
+        }
+        split_store(hi, lo, c, r, make_float4(t[0], t[1], t[2], t[3]));
+    }
+}
+
+bool gemm_tc_bpre_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GCGCN_GEMM_BPRE");
+        cached = (e != nullptr && e[0] == '0') ? 0 : 1;   // GCGCN_GEMM_BPRE=0 disables
+    }
+    return cached == 1;
+}
+
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, float alpha, float beta, float* C,
                          int ldc, const float* bias, cudaStream_t st, int batch, long long sC);
 
@@ -456,27 +545,41 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     }
     a.k_splits = splits;
     const int grid = std::min(sms, tiles * splits);
+    a.Bpre = nullptr;
+    a.kblocks = ceil_div(K, TC_BK);
+    // weight-like B operand (small, reused by every 128-row tile of a tall A): pre-split it once per call
+    const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
+    const bool bpre = gemm_tc_bpre_enabled() && batch == 1 && splits == 1 && !ta && M >= 4096 &&
+                      static_cast<size_t>(N) * K * sizeof(float) <= (size_t(2) << 20) && ws != nullptr &&
+                      blob_total <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
+    if (bpre) {
+        tc_presplit_b_kernel<<<a.tiles_n * a.kblocks, 256, 0, st>>>(B, ldb, tb != 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
+        GCGCN_CHECK_LAUNCH("gemm_presplit_b");
+        a.Bpre = static_cast<const uint8_t*>(ws);
+    }
     // op(A)[m,k]: stored [M][K] (K contiguous) when !ta, [K][M] when ta.
     // op(B)[k,n] as the N x K operand: stored [N][K] (K contiguous) when tb, [K][N] when !tb.
     const bool a_kc = !ta, b_kc = (tb != 0);
-#define GCGCN_TC_LAUNCH(AK, BK, G)                                                                       \
+#define GCGCN_TC_LAUNCH(AK, BK, G, PRE)                                                                  \
     do {                                                                                                 \
         static bool attr_done = false;                                                                   \
         if (!attr_done) {                                                                                \
-            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, G>,                            \
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, G, PRE>,                       \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                                    static_cast<int>(TC_SMEM_BYTES)), "gemm_tc smem"));   \
             attr_done = true;                                                                            \
         }                                                                                                \
-        gemm_tc_kernel<AK, BK, G><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);                        \
+        gemm_tc_kernel<AK, BK, G, PRE><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);                   \
     } while (0)
-    if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3);
-    else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3);
-    else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3);
-    else GCGCN_TC_LAUNCH(false, false, 2);
+    if (bpre) GCGCN_TC_LAUNCH(true, true, 3, true);
+    else if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3, false);
+    else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3, false);
+    else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3, false);
+    else GCGCN_TC_LAUNCH(false, false, 2, false);
 #undef GCGCN_TC_LAUNCH
     timing_set_work(2.0 * M * N * K * batch);
-    GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
+    GCGCN_CHECK_LAUNCH(bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
+                            : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));
     *taken = 1;
