@@ -431,7 +431,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     constexpr int S = D, layers = D / GD, LDN = GD + 12, CG = GD / 4, RPP = BK_THREADS / CG;
     constexpr int DHH = DH > 0 ? DH : 8;
     constexpr int NTW = col_tiles_per_warp(MTC, GD / 8), NG = (GD / 8) / NTW, UNITS = MTC * NG;           // [NP] x [GD] products
-    constexpr int NTW_C = MTC == 3 ? 3 : col_tiles_per_warp(MTC, 2 * MTC), NG_C = (2 * MTC) / NTW_C, UNITS_C = MTC * NG_C;  // [NP] x [NP]
+    constexpr int NTW_C = MTC, NG_C = 2, UNITS_C = 2 * MTC;          // [NP] x [NP]: a row tile x half the columns per warp
     constexpr int NP = 16 * MTC, MT = MTC, NT8 = 2 * MTC, LDA = NP + 4, KI = (layers - 1) * GD, LDG = KI + 4;
     const int HD = DH > 0 ? (D / DHH) * S : heads * S;
 
