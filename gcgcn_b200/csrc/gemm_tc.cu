@@ -423,6 +423,20 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
                     const int c4 = (lane & 7) * 4, col = n0 + chunk * 32 + c4;
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (final_out && args.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(args.bias + col);
+                    // beta != 0: fetch the 8 old values first -- interleaved with the stores the compiler must keep
+                    // each load behind the previous store (possible aliasing) and the epilogue becomes a chain of
+                    // eight global round trips per 32-column chunk
+                    float4 cold[8];
+                    const bool rmw = final_out && args.beta != 0.f;
+                    if (rmw) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = 4 * it + (lane >> 3);
+                            cold[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rr < rows_valid)
+                                cold[it] = *reinterpret_cast<const float4*>(out_base + static_cast<size_t>(row_base + rr) * ldo + col);
+                        }
+                    }
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = 4 * it + (lane >> 3);
@@ -432,10 +446,9 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
                             if (final_out) {
                                 val.x = val.x * args.alpha + bias4.x; val.y = val.y * args.alpha + bias4.y;
                                 val.z = val.z * args.alpha + bias4.z; val.w = val.w * args.alpha + bias4.w;
-                                if (args.beta != 0.f) {
-                                    const float4 c = *p;
-                                    val.x += args.beta * c.x; val.y += args.beta * c.y;
-                                    val.z += args.beta * c.z; val.w += args.beta * c.w;
+                                if (rmw) {
+                                    val.x += args.beta * cold[it].x; val.y += args.beta * cold[it].y;
+                                    val.z += args.beta * cold[it].z; val.w += args.beta * cold[it].w;
                                 }
                             }
                             *p = val;
