@@ -38,11 +38,18 @@ class GradBucket:
         return self.flat.numel() * 4
 
     def pack(self):
+        """p.grad -> bucket: one multi-tensor copy for all parameters that have a gradient."""
+        vs = [v for v, p in zip(self.views, self.params) if p.grad is not None]
+        gs = [p.grad for p in self.params if p.grad is not None]
         for v, p in zip(self.views, self.params):
             if p.grad is None:
                 v.zero_()
+        if vs:
+            if hasattr(torch, "_foreach_copy_"):
+                torch._foreach_copy_(vs, gs)
             else:
-                v.copy_(p.grad)
+                for v, g in zip(vs, gs):
+                    v.copy_(g)
 
     def all_reduce(self, group=None, average: bool = False, async_op: bool = False):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -53,13 +60,21 @@ class GradBucket:
         return work
 
     def unpack(self, skip_none: bool = True):
+        """bucket -> p.grad (one multi-tensor copy)."""
+        vs, gs = [], []
         for v, p in zip(self.views, self.params):
             if p.grad is None:
-                if skip_none:
-                    continue
-                p.grad = v.clone()
+                if not skip_none:
+                    p.grad = v.clone()
+                continue
+            vs.append(v)
+            gs.append(p.grad)
+        if gs:
+            if hasattr(torch, "_foreach_copy_"):
+                torch._foreach_copy_(gs, vs)
             else:
-                p.grad.copy_(v)
+                for g, v in zip(gs, vs):
+                    g.copy_(v)
 
 
 def all_reduce_gradients(params: Iterable[torch.nn.Parameter], group=None, average: bool = False,
