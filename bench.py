@@ -51,7 +51,13 @@ def parse():
     ap.add_argument("--variant", default="glove", choices=list(VARIANTS))
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="edge-tensor storage")
     ap.add_argument("--tile", type=int, default=512, help="12-document batches per GPU per step")
+    ap.add_argument("--nodes", type=int, default=0, help="configs[3] entity-count sweep: every document has this many "
+                                                         "entities (128 / 256 in the sweep); 0 = the DocRED-shaped batch")
+    ap.add_argument("--docs", type=int, default=0, help="documents per GPU per step with --nodes (default: ~3 GB of edges)")
+    ap.add_argument("--heads", type=int, default=0, help="override head_num (4 / 8 in the sweep)")
     ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of the captured pass instead of eager launches")
+    ap.add_argument("--train", action="store_true", help="module.train(): dropout keep-masks drawn by torch every step "
+                                                         "(the headline is the dropout-free pass, SURVEY 8d)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -123,6 +129,9 @@ def run_reference_arm(args):
 
 
 def workload_name(args):
+    if getattr(args, "nodes", 0):
+        return (f"configs[3]: entity-count sweep, fully connected graphs of {args.nodes} entities, "
+                f"head_num {args.heads or VARIANTS[args.variant][1]}, graph blocks fwd+bwd")
     return (f"configs[1]: GCGCN_{args.variant} graph blocks fwd+bwd, 12-document DocRED-shaped batch "
             f"(n=42..5, SURVEY 8d) x {args.tile} = {12 * args.tile} documents per GPU per step")
 
@@ -259,11 +268,20 @@ def run_gpu_arm(args):
     _lib.load()
 
     layers, heads = VARIANTS[args.variant]
+    if args.heads:
+        heads = args.heads
     edt = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     esz = 4 if args.dtype == "fp32" else 2
     torch.manual_seed(0)
     gb = GraphBlocks(layers, heads).to(dev).eval()
-    sizes = synthetic.shard_doc_sizes(12 * args.tile)
+    if args.train:
+        gb.train()
+    if args.nodes:
+        import numpy as np
+        ndoc = args.docs or max(1, int(1.5e9 // (args.nodes * args.nodes * 128 * (4 if args.dtype == "fp32" else 2))))
+        sizes = np.full(ndoc, args.nodes, dtype=np.int64)
+    else:
+        sizes = synthetic.shard_doc_sizes(12 * args.tile)
     bt = RaggedBatch(sizes, dev)
     ndocs = bt.num_docs
 
@@ -476,7 +494,8 @@ def run_gpu_arm(args):
                    "collective": "none" if world == 1 else f"one NCCL all-reduce of {bucket.nbytes} B per step",
                    "launch": "eager (one C-ABI call per op)" if graphed is None else
                              "CUDA-graph replay of the captured forward+backward pass (same kernels as eager)",
-                   "eager_ms_per_step": ms_eager / args.steps},
+                   "eager_ms_per_step": ms_eager / args.steps,
+                   "dropout": "train mode: keep-masks from torch.rand every step" if args.train else "none (eval)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": top, "cpu_baseline": cpu,
     }
     sys.stdout.flush()

@@ -31,6 +31,11 @@ class GcgcnError(RuntimeError):
     pass
 
 
+class Dropout(ctypes.Structure):
+    """struct gcgcn_dropout"""
+    _fields_ = [("seed", c_uint64), ("p_att", c_float), ("p_gcn", c_float)]
+
+
 class Batch(ctypes.Structure):
     """struct gcgcn_batch"""
     _fields_ = [
@@ -66,6 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 _P = c_void_p
 _BT = POINTER(Batch)
+_DP = POINTER(Dropout)
 
 # name -> (restype, argtypes); mirrors include/gcgcn_b200.h one to one
 SIGNATURES = {
@@ -91,21 +97,22 @@ SIGNATURES = {
     "gcgcn_graphconv_stack_bwd": (c_int32, [_BT, c_int32, c_int32, c_int32, c_int32, c_int32]
                                   + [_P] * 20 + [_P, c_size_t, _P]),
     "gcgcn_block_supported": (c_int32, [_BT, c_int32, c_int32, c_int32]),
-    "gcgcn_mha_stack_fwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 15 + [_P, c_size_t, _P]),
-    "gcgcn_mha_stack_bwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 22 + [_P, c_size_t, _P]),
+    "gcgcn_dropout_mask": (c_int32, [c_uint64, c_int32, c_float, c_int64, _P, _P]),
+    "gcgcn_mha_stack_fwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 15 + [_DP, _P, c_size_t, _P]),
+    "gcgcn_mha_stack_bwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 22 + [_DP, _P, c_size_t, _P]),
     "gcgcn_pack_stack_weights": (c_int32, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "gcgcn_unpack_stack_grads": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "gcgcn_pair_gather_fwd": (c_int32, [_BT, _P, c_int32, _P, c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "gcgcn_pair_gather_bwd": (c_int32, [_BT, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P,
                                         _P, c_size_t, _P]),
     "gcgcn_block_saved_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
-    "gcgcn_caggc_fwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 8 + [_P, _P, _P, c_size_t, _P]),
+    "gcgcn_caggc_fwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 8 + [_P, _P, _DP, _P, c_size_t, _P]),
     "gcgcn_caggc_bwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 6 + [_P, _P]
-                        + [_P] * 10 + [_P, c_size_t, _P]),
+                        + [_P] * 10 + [_DP, _P, c_size_t, _P]),
     "gcgcn_maggc_fwd": (c_int32, [_BT, c_int32, c_int32, _P, _P, c_int32] + [_P] * 7
-                        + [_P, _P, _P, c_size_t, _P]),
+                        + [_P, _P, _DP, _P, c_size_t, _P]),
     "gcgcn_maggc_bwd": (c_int32, [_BT, c_int32, c_int32, _P, c_int32] + [_P] * 5 + [_P, _P]
-                        + [_P] * 9 + [_P, c_size_t, _P]),
+                        + [_P] * 9 + [_DP, _P, c_size_t, _P]),
     "gcgcn_gemm": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, c_int32, _P,
                              c_int32, c_float, _P, c_int32, _P, _P, c_size_t, _P]),
 }

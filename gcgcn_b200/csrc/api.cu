@@ -36,10 +36,12 @@ int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
 bool block_kernels_usable(const gcgcn_batch* bt, int heads, int layers, int slab, bool mha);
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
-                     float* frag_ws, cudaStream_t st);
+                     float* frag_ws, const BlockDrop& drop, cudaStream_t st);
 int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode, const float* A, const float* q,
                      const float* Z, const float* G, const float* Winner, const float* dF, float* dZ, float* dE,
-                     float* dOut, float* frag_ws, cudaStream_t st);
+                     float* dOut, float* frag_ws, const BlockDrop& drop, cudaStream_t st);
+int launch_dropout_mask(unsigned long long seed, uint32_t stream, uint32_t thr, float inv, long long count, float* out,
+                        cudaStream_t st);
 size_t block_frag_floats(int heads, int layers);
 enum { ATT_GRAD_DA = 0, ATT_GRAD_DS = 1, ATT_GRAD_DQ = 2 };   // == BK_OUT_* of gcn_block.cu
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
@@ -149,6 +151,30 @@ constexpr size_t GEMM_WS_BYTES = size_t(24) << 20;
 constexpr int BLOCK_FLAGS_ALL = GCGCN_STACK_RELU | GCGCN_STACK_RESIDUAL | GCGCN_STACK_LINEAR;
 
 static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// dropout streams of the two blocks (distinct masks for distinct tensors under one seed)
+enum { DROP_STREAM_GAT = 1, DROP_STREAM_CAGGC = 2, DROP_STREAM_MHA = 3, DROP_STREAM_MAGGC = 4 };
+
+static uint32_t drop_threshold(float p) {
+    if (!(p > 0.f)) return 0u;
+    const double t = static_cast<double>(p) * 4294967296.0;
+    return t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+}
+static int make_block_drop(const gcgcn_dropout* d, uint32_t s_att, uint32_t s_gcn, BlockDrop* out) {
+    *out = BlockDrop{};
+    if (d == nullptr) return GCGCN_OK;
+    if (!(d->p_att >= 0.f && d->p_att < 1.f && d->p_gcn >= 0.f && d->p_gcn < 1.f))
+        return fail(GCGCN_ERR_INVALID_ARG, "dropout probabilities must be in [0, 1): p_att %g, p_gcn %g", d->p_att, d->p_gcn);
+    out->seed = d->seed;
+    out->thr_att = drop_threshold(d->p_att);
+    out->thr_gcn = drop_threshold(d->p_gcn);
+    out->inv_att = 1.0f / (1.0f - d->p_att);
+    out->inv_gcn = 1.0f / (1.0f - d->p_gcn);
+    out->s_att = s_att;
+    out->s_gcn = s_gcn;
+    return GCGCN_OK;
+}
+static bool drop_active(const BlockDrop& d) { return d.thr_att != 0u || d.thr_gcn != 0u; }
 
 __global__ void __launch_bounds__(256)
 head_sum_kernel(const float* __restrict__ dF, int heads, int rows, float* __restrict__ dx) {
@@ -437,7 +463,7 @@ static int stack_fwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
                           int32_t flags, const float* x, const float* ebar, const float* A, const float* q, float* P,
                           const float* WnX, const float* We, const float* Winner, const float* Wout,
                           const float* bout, const float* keep, float* Z, float* G, float* F, float* y, void* ws,
-                          size_t ws_bytes, cudaStream_t st) {
+                          size_t ws_bytes, cudaStream_t st, const BlockDrop& drop = BlockDrop{}) {
     const bool linear = flags & GCGCN_STACK_LINEAR;
     const int HD = heads * slab, M = bt->total_nodes;
     Arena ar(ws, ws_bytes);
@@ -449,7 +475,9 @@ static int stack_fwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
     GCGCN_TRY(launch_gemm(0, 0, M, HD, D, 1.f, ebar, D, We, HD, 0.f, E, HD, nullptr, gws, GEMM_WS_BYTES, st));
     float* Fout = linear ? F : y;
     if (q != nullptr)
-        GCGCN_TRY(launch_block_fwd(bt, heads, layers, nullptr, q, P, Z, E, Winner, x, G, Fout, frag, st));
+        GCGCN_TRY(launch_block_fwd(bt, heads, layers, nullptr, q, P, Z, E, Winner, x, G, Fout, frag, drop, st));
+    else if (drop_active(drop))       // in-kernel dropout exists only in the block kernels (given attention map)
+        GCGCN_TRY(launch_block_fwd(bt, heads, layers, A, nullptr, nullptr, Z, E, Winner, x, G, Fout, frag, drop, st));
     else
         GCGCN_TRY(launch_stack_fwd(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, Fout, frag, st));
     if (linear)
@@ -491,7 +519,8 @@ static int stack_bwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
                           const float* q, const float* WnX, const float* We, const float* Winner, const float* Wout,
                           const float* keep, const float* Z, const float* G, const float* F, const float* dy,
                           float* dx, float* debar, float* att_out, float* dWnX, float* dWe, float* dWinner,
-                          float* dWout, float* dbout, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          float* dWout, float* dbout, void* ws, size_t ws_bytes, cudaStream_t st,
+                          const BlockDrop& drop = BlockDrop{}) {
     const bool linear = flags & GCGCN_STACK_LINEAR;
     const int HD = heads * slab, M = bt->total_nodes, gd = slab / layers;
     Arena ar(ws, ws_bytes);
@@ -513,7 +542,7 @@ static int stack_bwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
     if (att_grad == ATT_GRAD_DA)
         GCGCN_TRY(launch_stack_bwd(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, att_out, frag, st));
     else
-        GCGCN_TRY(launch_block_bwd(bt, heads, layers, att_grad, A, q, Z, G, Winner, dF, dZ, dE, att_out, frag, st));
+        GCGCN_TRY(launch_block_bwd(bt, heads, layers, att_grad, A, q, Z, G, Winner, dF, dZ, dE, att_out, frag, drop, st));
     // dx = [residual: sum_h dF_h] + dZ WnX^T ; debar = dE We^T
     float beta = 0.f;
     if (flags & GCGCN_STACK_RESIDUAL) {
@@ -568,6 +597,16 @@ int gcgcn_graphconv_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t laye
                           static_cast<cudaStream_t>(stream));
 }
 
+// ---- dropout stream export (tests) ------------------------------------------------------------
+int gcgcn_dropout_mask(uint64_t seed, int32_t stream_id, float p, int64_t count, float* out, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(p >= 0.f && p < 1.f && count >= 0 && stream_id >= 0, "dropout_mask: bad arguments");
+    if (count == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(out, "out"));
+    return launch_dropout_mask(seed, static_cast<uint32_t>(stream_id), drop_threshold(p), 1.0f / (1.0f - p), count, out,
+                               static_cast<cudaStream_t>(stream));
+}
+
 // ---- a5 + a6 fused: MultiHeadAttention scores inside the MAGGC block kernels --------------------
 int gcgcn_block_supported(const gcgcn_batch* bt, int32_t heads, int32_t layers, int32_t mha) {
     if (bt == nullptr || layers < 1 || D % layers != 0) return 0;
@@ -577,9 +616,11 @@ int gcgcn_block_supported(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
 int gcgcn_mha_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, const float* x, const float* ebar,
                         const float* Wq, const float* bq, const float* WnX, const float* We, const float* Winner,
                         const float* Wout, const float* bout, float* q, float* P, float* Z, float* G, float* F,
-                        float* y, void* ws, size_t ws_bytes, void* stream) {
+                        float* y, const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
     GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
+    BlockDrop drop;
+    GCGCN_TRY(make_block_drop(dropout, DROP_STREAM_MHA, DROP_STREAM_MAGGC, &drop));
     GCGCN_REQUIRE(heads >= 1 && layers >= 1 && D % layers == 0, "mha_stack_fwd: bad heads/layers");
     if (!block_kernels_usable(bt, heads, layers, D, true))
         return fail(GCGCN_ERR_UNSUPPORTED, "mha_stack_fwd: needs documents of <= 64 nodes, 2 or 4 sub-layers and 4 or 8 "
@@ -601,16 +642,19 @@ int gcgcn_mha_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GCGCN_TRY(launch_gemm(0, 1, bt->total_nodes, D, D, 1.f, x, D, Wq, D, 0.f, q, D, bq, ws, ws_bytes, st));
     return stack_fwd_impl(bt, heads, layers, D, D, BLOCK_FLAGS_ALL, x, ebar, nullptr, q, P, WnX, We, Winner, Wout, bout,
-                          nullptr, Z, G, F, y, ws, ws_bytes, st);
+                          nullptr, Z, G, F, y, ws, ws_bytes, st, drop);
 }
 
 int gcgcn_mha_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, const float* x, const float* ebar,
                         const float* Wq, const float* WnX, const float* We, const float* Winner, const float* Wout,
                         const float* q, const float* P, const float* Z, const float* G, const float* F,
                         const float* dy, float* dx, float* debar, float* dWq, float* dbq, float* dWnX, float* dWe,
-                        float* dWinner, float* dWout, float* dbout, void* ws, size_t ws_bytes, void* stream) {
+                        float* dWinner, float* dWout, float* dbout, const gcgcn_dropout* dropout, void* ws,
+                        size_t ws_bytes, void* stream) {
     GCGCN_API_ENTER(stream);
     GCGCN_TRY(check_batch(bt));
+    BlockDrop drop;
+    GCGCN_TRY(make_block_drop(dropout, DROP_STREAM_MHA, DROP_STREAM_MAGGC, &drop));
     GCGCN_REQUIRE(heads >= 1 && layers >= 1 && D % layers == 0, "mha_stack_bwd: bad heads/layers");
     if (!block_kernels_usable(bt, heads, layers, D, true))
         return fail(GCGCN_ERR_UNSUPPORTED, "mha_stack_bwd: unsupported configuration (see gcgcn_mha_stack_fwd)");
@@ -630,7 +674,8 @@ int gcgcn_mha_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers, co
     void* rest = static_cast<char*>(ws) + ar.off;
     const size_t rest_bytes = ws_bytes - ar.off;
     GCGCN_TRY(stack_bwd_impl(bt, heads, layers, D, D, BLOCK_FLAGS_ALL, ATT_GRAD_DQ, x, ebar, P, q, WnX, We, Winner, Wout,
-                             nullptr, Z, G, F, dy, dx, debar, dq, dWnX, dWe, dWinner, dWout, dbout, rest, rest_bytes, st));
+                             nullptr, Z, G, F, dy, dx, debar, dq, dWnX, dWe, dWinner, dWout, dbout, rest, rest_bytes, st,
+                             drop));
     // q = x Wq^T + bq :  dx += dq Wq ; dWq = dq^T x ; dbq = colsum(dq)
     Arena ar2(rest, rest_bytes);
     float* gws = ar2.take<float>(GEMM_WS_BYTES / sizeof(float));
@@ -760,23 +805,35 @@ size_t gcgcn_block_saved_bytes(int32_t total_nodes, int64_t total_pairs, int32_t
 
 int gcgcn_caggc_fwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e, int32_t edge_dtype,
                     const float* u, const float* v, const float* c, const float* WnX, const float* We,
-                    const float* Winner, const float* Wout, const float* bout, float* y, void* saved, void* ws,
-                    size_t ws_bytes, void* stream) {
+                    const float* Winner, const float* Wout, const float* bout, float* y, void* saved,
+                    const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
+    BlockDrop drop;
+    GCGCN_TRY(make_block_drop(dropout, DROP_STREAM_GAT, DROP_STREAM_CAGGC, &drop));
     CagSaved s = carve_cag(saved, bt->total_nodes, bt->total_pairs);
+    // s.P = the GAT softmax output; with dropout the block kernel applies the (regenerated) keep mask to it
     GCGCN_TRY(gcgcn_gat_fwd(bt, x, e, edge_dtype, u, v, c, nullptr, 0, nullptr, s.P, s.P, s.ebar, ws, ws_bytes, stream));
-    return gcgcn_graphconv_stack_fwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, bout,
-                                     nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, stream);
+    if (!drop_active(drop))
+        return gcgcn_graphconv_stack_fwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, bout,
+                                         nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, stream);
+    if (!block_kernels_usable(bt, 1, layers, D, false))
+        return fail(GCGCN_ERR_UNSUPPORTED, "caggc_fwd: in-kernel dropout needs documents of <= 64 nodes and 2 or 4 "
+                    "sub-layers; pass keep masks through gcgcn_gat_fwd / gcgcn_graphconv_stack_fwd instead");
+    GCGCN_API_ENTER(stream);
+    return stack_fwd_impl(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, nullptr, nullptr, WnX, We, Winner, Wout, bout,
+                          nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, static_cast<cudaStream_t>(stream), drop);
 }
 
 int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e, int32_t edge_dtype,
                     const float* u, const float* v, const float* WnX, const float* We, const float* Winner,
                     const float* Wout, const float* dy, const void* saved, float* dx, void* de, float* du,
                     float* dv, float* dc, float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
-                    void* ws, size_t ws_bytes, void* stream) {
+                    const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
+    BlockDrop drop;
+    GCGCN_TRY(make_block_drop(dropout, DROP_STREAM_GAT, DROP_STREAM_CAGGC, &drop));
     CagSaved s = carve_cag(const_cast<void*>(saved), bt->total_nodes, bt->total_pairs);
     // tail of the workspace holds the gradients that flow between the two halves of the block
     Arena ar(ws, ws_bytes);
@@ -794,10 +851,11 @@ int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const
         GCGCN_API_ENTER(stream);
         GCGCN_TRY(stack_bwd_impl(bt, 1, layers, D, D, BLOCK_FLAGS, ATT_GRAD_DS, x, s.ebar, s.P, nullptr, WnX, We, Winner,
                                  Wout, nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dS, dWnX, dWe, dWinner, dWout, dbout,
-                                 rest, rest_bytes, st));
+                                 rest, rest_bytes, st, drop));
         Arena ar2(rest, rest_bytes);
         GCGCN_TRY(gat_bwd_from_ds(bt, x, e, edge_dtype, u, v, dS, debar, dx, de, du, dv, dc, ar2, st));
     } else {
+        if (drop_active(drop)) return fail(GCGCN_ERR_UNSUPPORTED, "caggc_bwd: in-kernel dropout needs the block kernels");
         GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, 1, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout,
                                             nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner, dWout,
                                             dbout, rest, rest_bytes, stream));
@@ -809,15 +867,17 @@ int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const
 
 int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x, const void* e,
                     int32_t edge_dtype, const float* Wq, const float* bq, const float* WnX, const float* We,
-                    const float* Winner, const float* Wout, const float* bout, float* y, void* saved, void* ws,
-                    size_t ws_bytes, void* stream) {
+                    const float* Winner, const float* Wout, const float* bout, float* y, void* saved,
+                    const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     MagSaved s = carve_mag(saved, bt->total_nodes, bt->total_pairs, heads);
     GCGCN_TRY(gcgcn_edge_mean_fwd(bt, e, edge_dtype, s.ebar, stream));
     if (block_kernels_usable(bt, heads, layers, D, true))
         return gcgcn_mha_stack_fwd(bt, heads, layers, x, s.ebar, Wq, bq, WnX, We, Winner, Wout, bout, s.q, s.P, s.Z, s.G,
-                                   s.F, y, ws, ws_bytes, stream);
+                                   s.F, y, dropout, ws, ws_bytes, stream);
+    GCGCN_REQUIRE(dropout == nullptr || (dropout->p_att <= 0.f && dropout->p_gcn <= 0.f),
+                  "maggc_fwd: in-kernel dropout needs the block kernels (n <= 64, 4 or 8 heads)");
     GCGCN_TRY(gcgcn_mha_fwd(bt, heads, x, Wq, bq, nullptr, s.q, s.P, s.P, ws, ws_bytes, stream));
     return gcgcn_graphconv_stack_fwd(bt, heads, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout, bout,
                                      nullptr, s.Z, s.G, s.F, y, ws, ws_bytes, stream);
@@ -826,8 +886,8 @@ int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
 int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x, int32_t edge_dtype,
                     const float* Wq, const float* WnX, const float* We, const float* Winner, const float* Wout,
                     const float* dy, const void* saved, float* dx, void* de, float* dWq, float* dbq, float* dWnX,
-                    float* dWe, float* dWinner, float* dWout, float* dbout, void* ws, size_t ws_bytes,
-                    void* stream) {
+                    float* dWe, float* dWinner, float* dWout, float* dbout, const gcgcn_dropout* dropout, void* ws,
+                    size_t ws_bytes, void* stream) {
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     MagSaved s = carve_mag(const_cast<void*>(saved), bt->total_nodes, bt->total_pairs, heads);
@@ -841,9 +901,12 @@ int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
     const size_t rest_bytes = ws_bytes - ar.off;
     if (block_kernels_usable(bt, heads, layers, D, true)) {
         GCGCN_TRY(gcgcn_mha_stack_bwd(bt, heads, layers, x, s.ebar, Wq, WnX, We, Winner, Wout, s.q, s.P, s.Z, s.G, s.F, dy,
-                                      dx, debar, dWq, dbq, dWnX, dWe, dWinner, dWout, dbout, rest, rest_bytes, stream));
+                                      dx, debar, dWq, dbq, dWnX, dWe, dWinner, dWout, dbout, dropout, rest, rest_bytes,
+                                      stream));
         return gcgcn_edge_mean_bwd(bt, debar, edge_dtype, de, stream);
     }
+    GCGCN_REQUIRE(dropout == nullptr || (dropout->p_att <= 0.f && dropout->p_gcn <= 0.f),
+                  "maggc_bwd: in-kernel dropout needs the block kernels (n <= 64, 4 or 8 heads)");
     GCGCN_TRY(gcgcn_graphconv_stack_bwd(bt, heads, layers, D, D, BLOCK_FLAGS, x, s.ebar, s.P, WnX, We, Winner, Wout,
                                         nullptr, s.Z, s.G, s.F, dy, dx_stack, debar, dA, dWnX, dWe, dWinner,
                                         dWout, dbout, rest, rest_bytes, stream));

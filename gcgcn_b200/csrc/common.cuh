@@ -92,6 +92,36 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- counter-based dropout (train mode of the block kernels) -------------------------------------
+// keep-scale factor of element `idx` of dropout stream `stream` under `seed`: 0 with probability p, else 1/(1-p).
+// One SplitMix64 hash serves the two elements of an even/odd index pair; forward and backward (and
+// gcgcn_dropout_mask, which materialises a stream for the tests) regenerate the same values, so no mask is stored.
+struct BlockDrop {
+    unsigned long long seed;
+    uint32_t thr_att, thr_gcn;      // p * 2^32 of the attention / GraphConv-output dropout (0 = off)
+    float inv_att, inv_gcn;         // 1 / (1 - p)
+    uint32_t s_att, s_gcn;          // stream ids
+};
+__host__ __device__ __forceinline__ unsigned long long drop_hash(unsigned long long seed, uint32_t stream,
+                                                                  unsigned long long pair_idx) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (pair_idx + (static_cast<unsigned long long>(stream) << 56) + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ float drop_keep(unsigned long long seed, uint32_t stream, unsigned long long idx,
+                                                    uint32_t thr, float inv) {
+    const unsigned long long h = drop_hash(seed, stream, idx >> 1);
+    const uint32_t r = (idx & 1ULL) ? static_cast<uint32_t>(h >> 32) : static_cast<uint32_t>(h);
+    return r >= thr ? inv : 0.f;
+}
+// idx even: the factors of idx and idx + 1 from one hash
+__host__ __device__ __forceinline__ float2 drop_keep2(unsigned long long seed, uint32_t stream, unsigned long long idx,
+                                                      uint32_t thr, float inv) {
+    const unsigned long long h = drop_hash(seed, stream, idx >> 1);
+    return make_float2(static_cast<uint32_t>(h) >= thr ? inv : 0.f, static_cast<uint32_t>(h >> 32) >= thr ? inv : 0.f);
+}
+
 // Streaming 4-element loads/stores of an edge vector slice, fp32 or bf16 storage, fp32 math.
 // The n^2 x 128 tensors are read/written exactly once per pass: bypass L1 allocation.
 template <typename T>

@@ -141,6 +141,20 @@ winner_frag_kernel(const float* __restrict__ Winner, int layers, int gd, float* 
     }
 }
 
+// Materialises one dropout stream (tests compare the in-kernel dropout with the keep-mask-in route).
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(unsigned long long seed, uint32_t stream, uint32_t thr, float inv, long long count, float* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx < count) out[idx] = thr != 0u ? drop_keep(seed, stream, idx, thr, inv) : 1.f;
+}
+int launch_dropout_mask(unsigned long long seed, uint32_t stream, uint32_t thr, float inv, long long count, float* out,
+                        cudaStream_t st) {
+    if (count <= 0) return GCGCN_OK;
+    dropout_mask_kernel<<<ceil_div(count, 256), 256, 0, st>>>(seed, stream, thr, inv, count, out);
+    GCGCN_CHECK_LAUNCH("dropout_mask");
+    return GCGCN_OK;
+}
+
 // Per-lane geometry shared by both kernels.
 //   ldmatrix A fragment (16 rows x 8 k): lane supplies row a_row, k offset a_col of the tile
 //   ldmatrix B fragment, operand stored [n][k] (hi and lo planes in one x4): row b_row, k offset b_col, plane b_lo
@@ -166,7 +180,7 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                  const float* __restrict__ A, const float* __restrict__ q, float* __restrict__ P,
                  float* __restrict__ Z, const float* __restrict__ E, const float* __restrict__ Wf,
                  const float* __restrict__ x, float* __restrict__ G, float* __restrict__ F, int heads,
-                 long long total_pairs, const int* __restrict__ doc_order, int first, float scale) {
+                 long long total_pairs, const int* __restrict__ doc_order, int first, float scale, const BlockDrop drop) {
     extern __shared__ __align__(16) float smem[];
     const int b = doc_order != nullptr ? doc_order[first + blockIdx.x] : blockIdx.x;
     const int h = blockIdx.y;
@@ -287,7 +301,9 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 float p = 0.f;
                 if (rv && j < n) {
                     p = v[r] * inv;
-                    if (DH > 0) P[abase + static_cast<long long>(i) * n + j] = p;
+                    const long long pidx = abase + static_cast<long long>(i) * n + j;
+                    if (DH > 0) P[pidx] = p;                   // softmax output, saved for backward (pre-dropout)
+                    if (drop.thr_att != 0u) p *= drop_keep(drop.seed, drop.s_att, pidx, drop.thr_att, drop.inv_att);   // G:141, G:166
                 }
                 float hi, lo;
                 split_f(p, hi, lo);
@@ -393,7 +409,12 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                     o.x = fmaxf((e2[half][nt].x + c[nt][2 * half]) * rinv, 0.f);
                     o.y = fmaxf((e2[half][nt].y + c[nt][2 * half + 1]) * rinv, 0.f);
                     *reinterpret_cast<float2*>(Gb + off) = o;
-                    *reinterpret_cast<float2*>(Fb + off) = make_float2(o.x + x2[half][nt].x, o.y + x2[half][nt].y);
+                    float2 f = o;                                // dropout hits only the output copy (G:72-74)
+                    if (drop.thr_gcn != 0u) {
+                        const float2 k2 = drop_keep2(drop.seed, drop.s_gcn, hbase + off, drop.thr_gcn, drop.inv_gcn);
+                        f.x *= k2.x; f.y *= k2.y;
+                    }
+                    *reinterpret_cast<float2*>(Fb + off) = make_float2(f.x + x2[half][nt].x, f.y + x2[half][nt].y);
                     if (l < layers - 1) {
                         float2 hi, lo;
                         split_f(o.x, hi.x, lo.x);
@@ -421,7 +442,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                  const float* __restrict__ A, const float* __restrict__ q, const float* __restrict__ Z,
                  const float* __restrict__ G, const float* __restrict__ Wb, const float* __restrict__ dF,
                  float* __restrict__ dZ, float* __restrict__ dE, float* __restrict__ dOut, int heads,
-                 long long total_pairs, const int* __restrict__ doc_order, int first, float scale) {
+                 long long total_pairs, const int* __restrict__ doc_order, int first, float scale, const BlockDrop drop) {
     extern __shared__ __align__(16) float smem[];
     const int b = doc_order != nullptr ? doc_order[first + blockIdx.x] : blockIdx.x;
     const int h = blockIdx.y;
@@ -461,7 +482,9 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         for (int r = 0; r < 8; ++r) {
             const int j = L.l8 + 8 * r;
             if (r < NT8) {
-                const float v = (i < n && j < n) ? Ab[i * n + j] : 0.f;
+                float v = (i < n && j < n) ? Ab[i * n + j] : 0.f;
+                if (drop.thr_att != 0u && i < n && j < n)       // A = P * keep, regenerated (Ab then holds the softmax output P)
+                    v *= drop_keep(drop.seed, drop.s_att, abase + i * n + j, drop.thr_att, drop.inv_att);
                 float hi, lo;
                 split_f(v, hi, lo);
                 AtH[j * LDA + i] = hi;
@@ -491,6 +514,11 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 float4 dg = ld4g(dF + off);
                 const float4 g4 = ld4g(G + off);
                 zl = ld4g(Z + off);
+                if (drop.thr_gcn != 0u) {
+                    const float2 k01 = drop_keep2(drop.seed, drop.s_gcn, off, drop.thr_gcn, drop.inv_gcn);
+                    const float2 k23 = drop_keep2(drop.seed, drop.s_gcn, off + 2, drop.thr_gcn, drop.inv_gcn);
+                    dg.x *= k01.x; dg.y *= k01.y; dg.z *= k23.x; dg.w *= k23.y;
+                }
                 if (!first_layer) {
                     const float4 s4 = *reinterpret_cast<const float4*>(dGs + i * LDG + l * GD + c0);
                     dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
@@ -635,7 +663,15 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
             p[r] = 0.f; dp[r] = 0.f;
             if (r < NT8 && rv && j < n) {
                 dp[r] = dAs[i * LDA + j] + dr;
-                if (OUT != BK_OUT_DA) { p[r] = AtH[j * LDA + i] + AtL[j * LDA + i]; dot += dp[r] * p[r]; }
+                if (OUT != BK_OUT_DA) {
+                    if (drop.thr_att != 0u) {     // dP = dA * keep ; P itself comes from global (the planes hold A = P * keep)
+                        dp[r] *= drop_keep(drop.seed, drop.s_att, abase + i * n + j, drop.thr_att, drop.inv_att);
+                        p[r] = Ab[i * n + j];
+                    } else {
+                        p[r] = AtH[j * LDA + i] + AtL[j * LDA + i];
+                    }
+                    dot += dp[r] * p[r];
+                }
             }
         }
         if (OUT != BK_OUT_DA) dot = group8_sum(dot);
@@ -755,14 +791,14 @@ static int prepare_kernel(K kernel, size_t max_bytes, const char* name) {
 template <int GD, int DH, int MTC>
 static int launch_fwd_class(const gcgcn_batch* bt, int heads, int count, int first, const int* order, const float* A,
                             const float* q, float* P, float* Z, const float* E, const float* Winner, const float* x,
-                            float* G, float* F, float scale, cudaStream_t st) {
+                            float* G, float* F, float scale, const BlockDrop& drop, cudaStream_t st) {
     constexpr int layers = D / GD;
     const size_t smem = block_fwd_smem(16 * MTC, layers, GD);
     static bool ready = false;
     if (!ready) { GCGCN_TRY(prepare_kernel(block_fwd_kernel<GD, DH, MTC>, smem, "block_fwd")); ready = true; }
     block_fwd_kernel<GD, DH, MTC><<<dim3(count, heads), BK_THREADS, smem, st>>>(
         bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), A, q, P, Z, E, Winner, x, G, F, heads,
-        bt->total_pairs, order, first, scale);
+        bt->total_pairs, order, first, scale, drop);
     GCGCN_CHECK_LAUNCH(DH > 0 ? "block_fwd<mha>" : "block_fwd<given>");
     return GCGCN_OK;
 }
@@ -770,13 +806,13 @@ static int launch_fwd_class(const gcgcn_batch* bt, int heads, int count, int fir
 template <int GD, int DH>
 static int launch_fwd_all(const gcgcn_batch* bt, int heads, const float* A, const float* q, float* P, float* Z,
                           const float* E, const float* Winner, const float* x, float* G, float* F, float scale,
-                          cudaStream_t st) {
+                          const BlockDrop& drop, cudaStream_t st) {
     return for_each_size_class(bt, [&](int count, int first, int nmax, const int* order) -> int {
         switch ((nmax + 15) / 16) {
-            case 1: return launch_fwd_class<GD, DH, 1>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
-            case 2: return launch_fwd_class<GD, DH, 2>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
-            case 3: return launch_fwd_class<GD, DH, 3>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
-            case 4: return launch_fwd_class<GD, DH, 4>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, st);
+            case 1: return launch_fwd_class<GD, DH, 1>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, drop, st);
+            case 2: return launch_fwd_class<GD, DH, 2>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, drop, st);
+            case 3: return launch_fwd_class<GD, DH, 3>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, drop, st);
+            case 4: return launch_fwd_class<GD, DH, 4>(bt, heads, count, first, order, A, q, P, Z, E, Winner, x, G, F, scale, drop, st);
             default: return fail(GCGCN_ERR_UNSUPPORTED, "block_fwd: %d nodes > 64", nmax);
         }
     });
@@ -794,7 +830,7 @@ static int launch_winner_frag(const float* Winner, int heads, int layers, float*
 
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner_rowmajor, const float* x, float* G, float* F,
-                     float* frag_ws, cudaStream_t st) {
+                     float* frag_ws, const BlockDrop& drop, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
     GCGCN_TRY(launch_winner_frag(Winner_rowmajor, heads, layers, frag_ws, st));
     const float* Winner = frag_ws;                      // forward-ordered half
@@ -802,7 +838,7 @@ int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* 
     const int dh = A != nullptr ? 0 : D / heads;
     const float scale = dh > 0 ? 1.0f / sqrtf(static_cast<float>(dh)) : 1.f;
 #define GCGCN_BK_FWD(GD_, DH_) \
-    if (gd == GD_ && dh == DH_) return launch_fwd_all<GD_, DH_>(bt, heads, A, q, P, Z, E, Winner, x, G, F, scale, st);
+    if (gd == GD_ && dh == DH_) return launch_fwd_all<GD_, DH_>(bt, heads, A, q, P, Z, E, Winner, x, G, F, scale, drop, st);
     GCGCN_BK_FWD(64, 0)
     GCGCN_BK_FWD(64, 16)
     GCGCN_BK_FWD(64, 32)
@@ -816,14 +852,14 @@ int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* 
 template <int GD, int DH, int OUT, int MTC>
 static int launch_bwd_class(const gcgcn_batch* bt, int heads, int count, int first, const int* order, const float* A,
                             const float* q, const float* Z, const float* G, const float* Winner, const float* dF,
-                            float* dZ, float* dE, float* dOut, float scale, cudaStream_t st) {
+                            float* dZ, float* dE, float* dOut, float scale, const BlockDrop& drop, cudaStream_t st) {
     constexpr int layers = D / GD;
     const size_t smem = block_bwd_smem(16 * MTC, layers, GD);
     static bool ready = false;
     if (!ready) { GCGCN_TRY(prepare_kernel(block_bwd_kernel<GD, DH, OUT, MTC>, smem, "block_bwd")); ready = true; }
     block_bwd_kernel<GD, DH, OUT, MTC><<<dim3(count, heads), BK_THREADS, smem, st>>>(
         bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), A, q, Z, G, Winner, dF, dZ, dE, dOut, heads,
-        bt->total_pairs, order, first, scale);
+        bt->total_pairs, order, first, scale, drop);
     GCGCN_CHECK_LAUNCH(OUT == BK_OUT_DQ ? "block_bwd<dq>" : (OUT == BK_OUT_DS ? "block_bwd<dS>" : "block_bwd<dA>"));
     return GCGCN_OK;
 }
@@ -831,13 +867,13 @@ static int launch_bwd_class(const gcgcn_batch* bt, int heads, int count, int fir
 template <int GD, int DH, int OUT>
 static int launch_bwd_all(const gcgcn_batch* bt, int heads, const float* A, const float* q, const float* Z,
                           const float* G, const float* Winner, const float* dF, float* dZ, float* dE, float* dOut,
-                          float scale, cudaStream_t st) {
+                          float scale, const BlockDrop& drop, cudaStream_t st) {
     return for_each_size_class(bt, [&](int count, int first, int nmax, const int* order) -> int {
         switch ((nmax + 15) / 16) {
-            case 1: return launch_bwd_class<GD, DH, OUT, 1>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
-            case 2: return launch_bwd_class<GD, DH, OUT, 2>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
-            case 3: return launch_bwd_class<GD, DH, OUT, 3>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
-            case 4: return launch_bwd_class<GD, DH, OUT, 4>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+            case 1: return launch_bwd_class<GD, DH, OUT, 1>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, drop, st);
+            case 2: return launch_bwd_class<GD, DH, OUT, 2>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, drop, st);
+            case 3: return launch_bwd_class<GD, DH, OUT, 3>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, drop, st);
+            case 4: return launch_bwd_class<GD, DH, OUT, 4>(bt, heads, count, first, order, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, drop, st);
             default: return fail(GCGCN_ERR_UNSUPPORTED, "block_bwd: %d nodes > 64", nmax);
         }
     });
@@ -847,7 +883,7 @@ static int launch_bwd_all(const gcgcn_batch* bt, int heads, const float* A, cons
 // output); BK_OUT_DQ -> dOut = dq [total_nodes][128] (A = the MHA probabilities, q their query projection).
 int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode, const float* A, const float* q,
                      const float* Z, const float* G, const float* Winner_rowmajor, const float* dF, float* dZ, float* dE,
-                     float* dOut, float* frag_ws, cudaStream_t st) {
+                     float* dOut, float* frag_ws, const BlockDrop& drop, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
     GCGCN_TRY(launch_winner_frag(Winner_rowmajor, heads, layers, frag_ws, st));
     const float* Winner = frag_ws == nullptr ? nullptr : frag_ws + block_frag_floats(heads, layers) / 2;   // backward-ordered half
@@ -856,7 +892,7 @@ int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode,
     const float scale = dh > 0 ? 1.0f / sqrtf(static_cast<float>(dh)) : 1.f;
 #define GCGCN_BK_BWD(GD_, DH_, OUT_)                      \
     if (gd == GD_ && dh == DH_ && out_mode == OUT_)       \
-        return launch_bwd_all<GD_, DH_, OUT_>(bt, heads, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, st);
+        return launch_bwd_all<GD_, DH_, OUT_>(bt, heads, A, q, Z, G, Winner, dF, dZ, dE, dOut, scale, drop, st);
     GCGCN_BK_BWD(64, 0, BK_OUT_DA)
     GCGCN_BK_BWD(32, 0, BK_OUT_DA)
     GCGCN_BK_BWD(64, 0, BK_OUT_DS)

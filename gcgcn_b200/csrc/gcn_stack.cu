@@ -420,10 +420,10 @@ int launch_stack_bwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab,
 bool block_kernels_usable(const gcgcn_batch* bt, int heads, int layers, int slab, bool mha);
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
-                     float* frag_ws, cudaStream_t st);
+                     float* frag_ws, const BlockDrop& drop, cudaStream_t st);
 int launch_block_bwd(const gcgcn_batch* bt, int heads, int layers, int out_mode, const float* A, const float* q,
                      const float* Z, const float* G, const float* Winner, const float* dF, float* dZ, float* dE,
-                     float* dOut, float* frag_ws, cudaStream_t st);
+                     float* dOut, float* frag_ws, const BlockDrop& drop, cudaStream_t st);
 
 // the block configuration (ReLU + residual, no dropout mask, slab 128, n <= 64) has its own kernels (gcn_block.cu)
 static bool block_config(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* keep) {
@@ -436,7 +436,7 @@ int launch_stack_fwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
                      float* F, float* frag_ws, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
     if (block_config(bt, heads, layers, slab, flags, keep) && (frag_ws != nullptr || layers < 2))
-        return launch_block_fwd(bt, heads, layers, A, nullptr, nullptr, Z, E, Winner, x, G, F, frag_ws, st);
+        return launch_block_fwd(bt, heads, layers, A, nullptr, nullptr, Z, E, Winner, x, G, F, frag_ws, BlockDrop{}, st);
     if (stack_mma_usable(bt, layers, slab))
         return launch_stack_fwd_mma(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, F, st);
     if (layers < 1 || slab % layers != 0)
@@ -471,7 +471,8 @@ int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
                      const float* dF, float* dZ, float* dE, float* dA, float* frag_ws, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
     if (block_config(bt, heads, layers, slab, flags, keep) && (frag_ws != nullptr || layers < 2))
-        return launch_block_bwd(bt, heads, layers, /*BK_OUT_DA*/ 0, A, nullptr, Z, G, Winner, dF, dZ, dE, dA, frag_ws, st);
+        return launch_block_bwd(bt, heads, layers, /*BK_OUT_DA*/ 0, A, nullptr, Z, G, Winner, dF, dZ, dE, dA, frag_ws,
+                                BlockDrop{}, st);
     if (stack_mma_usable(bt, layers, slab))
         return launch_stack_bwd_mma(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, dA, st);
     if (layers < 1 || slab % layers != 0)

@@ -240,12 +240,29 @@ def block_supported(batch: RaggedBatch, heads: int, layers: int, mha: bool) -> b
     return bool(_lib.load().gcgcn_block_supported(batch.ref, heads, layers, int(mha)))
 
 
+def _drop_ref(drop):
+    """(seed, p_att, p_gcn) or None -> argument for a `const gcgcn_dropout*` parameter."""
+    if drop is None:
+        return None
+    import ctypes
+    seed, p_att, p_gcn = drop
+    return ctypes.byref(_lib.Dropout(int(seed) & 0xFFFFFFFFFFFFFFFF, float(p_att), float(p_gcn)))
+
+
+def dropout_mask(seed: int, stream_id: int, p: float, count: int, device) -> torch.Tensor:
+    """The keep-scale factors (0 or 1/(1-p)) the block kernels regenerate for one dropout stream."""
+    out = torch.empty(int(count), device=device, dtype=torch.float32)
+    _lib.call("gcgcn_dropout_mask", int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id), float(p), int(count), _p(out),
+              _stream(out.device))
+    return out
+
+
 class CaggcFn(Function):
     """CAGGC block without dropout masks: GATAttention + GraphConvolution on one pass over e
     (G:330-333) through gcgcn_caggc_fwd / gcgcn_caggc_bwd.  Returns (y, A) -- A is the GAT map."""
 
     @staticmethod
-    def forward(ctx, x, e, u, v, c, WnX, We, Winner, Wout, bout, batch: RaggedBatch, layers: int):
+    def forward(ctx, x, e, u, v, c, WnX, We, Winner, Wout, bout, batch: RaggedBatch, layers: int, drop=None):
         x = _cuda(x, "node_feat")
         e, dt = _edge(e, "edge_feat")
         u, v, c = _cuda(u, "u"), _cuda(v, "v"), _cuda(c, "c")
@@ -257,9 +274,9 @@ class CaggcFn(Function):
         y = torch.empty(batch.total_nodes, D, device=dev)
         ws, wsb = _ws_for(batch, 1, dev)
         _lib.call("gcgcn_caggc_fwd", batch.ref, layers, _p(x), _p(e), dt, _p(u), _p(v), _p(c), _p(WnX), _p(We),
-                  _p(Winner), _p(Wout), _p(bout), _p(y), _p(saved), ws, wsb, _stream(dev))
+                  _p(Winner), _p(Wout), _p(bout), _p(y), _p(saved), _drop_ref(drop), ws, wsb, _stream(dev))
         ctx.save_for_backward(x, e, u, v, WnX, We, Winner, Wout, saved)
-        ctx.cfg = (batch, layers, dt)
+        ctx.cfg = (batch, layers, dt, drop)
         att = saved[: batch.total_pairs * 4].view(torch.float32)      # P is the first slab of the arena
         ctx.mark_non_differentiable(att)
         return y, att
@@ -267,7 +284,7 @@ class CaggcFn(Function):
     @staticmethod
     def backward(ctx, dy, _datt):
         x, e, u, v, WnX, We, Winner, Wout, saved = ctx.saved_tensors
-        batch, layers, dt = ctx.cfg
+        batch, layers, dt, drop = ctx.cfg
         dev = x.device
         dy = _cuda(dy, "dy")
         dx, de = torch.empty_like(x), torch.empty_like(e)
@@ -278,8 +295,8 @@ class CaggcFn(Function):
         ws, wsb = _ws_for(batch, 1, dev)
         _lib.call("gcgcn_caggc_bwd", batch.ref, layers, _p(x), _p(e), dt, _p(u), _p(v), _p(WnX), _p(We), _p(Winner),
                   _p(Wout), _p(dy), _p(saved), _p(dx), _p(de), _p(du), _p(dv), _p(dc), _p(dWnX), _p(dWe),
-                  _p(dWinner), _p(dWout), _p(dbout), ws, wsb, _stream(dev))
-        return dx, de, du, dv, dc.reshape(()), dWnX, dWe, dWinner, dWout, dbout, None, None
+                  _p(dWinner), _p(dWout), _p(dbout), _drop_ref(drop), ws, wsb, _stream(dev))
+        return dx, de, du, dv, dc.reshape(()), dWnX, dWe, dWinner, dWout, dbout, None, None, None
 
 
 class MhaStackFn(Function):
@@ -287,7 +304,8 @@ class MhaStackFn(Function):
     softmax, its backward and dq inside the block kernels.  Returns (y, P [H, total_pairs])."""
 
     @staticmethod
-    def forward(ctx, x, ebar, Wq, bq, WnX, We, Winner, Wout, bout, batch: RaggedBatch, heads: int, layers: int):
+    def forward(ctx, x, ebar, Wq, bq, WnX, We, Winner, Wout, bout, batch: RaggedBatch, heads: int, layers: int,
+                drop=None):
         x, ebar = _cuda(x, "node_feat"), _cuda(ebar, "ebar")
         Wq, bq = _cuda(Wq, "Wq"), _cuda(bq, "bq")
         WnX, We, Wout, bout = _cuda(WnX, "WnX"), _cuda(We, "We"), _cuda(Wout, "Wout"), _cuda(bout, "bout")
@@ -299,16 +317,17 @@ class MhaStackFn(Function):
         y = torch.empty(M, D, device=dev)
         ws, wsb = _ws_for(batch, heads, dev)
         _lib.call("gcgcn_mha_stack_fwd", batch.ref, heads, layers, _p(x), _p(ebar), _p(Wq), _p(bq), _p(WnX), _p(We),
-                  _p(Winner), _p(Wout), _p(bout), _p(q), _p(P), _p(Z), _p(G), _p(F), _p(y), ws, wsb, _stream(dev))
+                  _p(Winner), _p(Wout), _p(bout), _p(q), _p(P), _p(Z), _p(G), _p(F), _p(y), _drop_ref(drop), ws, wsb,
+                  _stream(dev))
         ctx.save_for_backward(x, ebar, Wq, WnX, We, Winner, Wout, q, P, Z, G, F)
-        ctx.cfg = (batch, heads, layers)
+        ctx.cfg = (batch, heads, layers, drop)
         ctx.mark_non_differentiable(P)
         return y, P
 
     @staticmethod
     def backward(ctx, dy, _dP):
         x, ebar, Wq, WnX, We, Winner, Wout, q, P, Z, G, F = ctx.saved_tensors
-        batch, heads, layers = ctx.cfg
+        batch, heads, layers, drop = ctx.cfg
         dev = x.device
         dy = _cuda(dy, "dy")
         dx, debar = torch.empty_like(x), torch.empty_like(ebar)
@@ -319,8 +338,8 @@ class MhaStackFn(Function):
         ws, wsb = _ws_for(batch, heads, dev)
         _lib.call("gcgcn_mha_stack_bwd", batch.ref, heads, layers, _p(x), _p(ebar), _p(Wq), _p(WnX), _p(We),
                   _p(Winner), _p(Wout), _p(q), _p(P), _p(Z), _p(G), _p(F), _p(dy), _p(dx), _p(debar), _p(dWq),
-                  _p(dbq), _p(dWnX), _p(dWe), _p(dWinner), _p(dWout), _p(dbout), ws, wsb, _stream(dev))
-        return dx, debar, dWq, dbq, dWnX, dWe, dWinner, dWout, dbout, None, None, None
+                  _p(dbq), _p(dWnX), _p(dWe), _p(dWinner), _p(dWout), _p(dbout), _drop_ref(drop), ws, wsb, _stream(dev))
+        return dx, debar, dWq, dbq, dWnX, dWe, dWinner, dWout, dbout, None, None, None, None
 
 
 # ------------------------------------------------------------------------------- parameter packing

@@ -320,6 +320,7 @@ class GraphBlocks(nn.Module, _KeepMixin):
         # fused: route dropout-free passes through the block-level C-ABI entry points (gcgcn_caggc_*,
         # gcgcn_mha_stack_*) whose kernels keep the attention maps and their gradients on chip
         self.fused = True
+        self.last_drop = {"caggc": None, "maggc": None}    # (seed, p_att, p_gcn) of the last train-mode block calls
         self._side = {}
         if graph_hop != 2:
             raise _lib.GcgcnError("graph_hop = 2 (config/Config.py:71) is the only supported depth")
@@ -351,29 +352,43 @@ class GraphBlocks(nn.Module, _KeepMixin):
             ebar1.record_stream(main)
         gat, mha = self.get_weighted_adj_matrix, self.get_adj_matrix[0]
         cag, mag = self.graphcnn
-        # no dropout mask to inject into the kernels: use the block-level entry points
-        plain = not (self._dropping() or gat._dropping() or mha._dropping() or cag._dropping() or mag._dropping())
-        if plain and self.fused and not gat.apply_mask:
+        # Block-level entry points: no mask tensors.  In train mode their kernels regenerate the dropout keep
+        # factors from a per-call seed (drawn from torch's CPU generator, so torch.manual_seed reproduces a run);
+        # masks injected by a test (inject_keep) take the one-entry-point-per-module route instead.
+        injected = any(getattr(m, "_injected", None) for m in (self, gat, mha, cag, mag))
+        fusable = self.fused and not injected and not gat.apply_mask and x0.is_cuda
+        cag_ok = fusable and (not self.training or block_supported(batch, 1, cag.layer_num, False))
+        mag_ok = fusable and block_supported(batch, mag.head_num, mag.layer_num, True)
+
+        def draw(att_p, gcn_p):
+            if not self.training or (att_p <= 0.0 and gcn_p <= 0.0):
+                return None
+            return (int(torch.randint(0, 2 ** 62, (1,)).item()), att_p, gcn_p)
+
+        if cag_ok:
             u, v, c = gat.collapse()
             wn_x, w_e, winner = _pack_stack(cag.graphconv, 1, cag.layer_num, cag._g)
+            drop = draw(gat.dropout.p if gat.training else 0.0, cag.gcn_dropout.p if cag.training else 0.0)
+            self.last_drop["caggc"] = drop
             new, a0 = CaggcFn.apply(x0, e0, u, v, c, wn_x, w_e, winner, cag.linear_layer.weight,
-                                    cag.linear_layer.bias, batch, cag.layer_num)                # G:332-333
+                                    cag.linear_layer.bias, batch, cag.layer_num, drop)          # G:332-333
         else:
             a0, ebar0 = gat.forward_batched(x0, e0, batch, mask)                                # G:332
             new = cag.forward_batched(x0, ebar0, a0.view(1, -1), batch)                         # G:333
         y1 = self._blend(new, x0)
-        fuse_mha = plain and self.fused and block_supported(batch, mag.head_num, mag.layer_num, True)
-        a1 = None if fuse_mha else mha.forward_batched(y1, batch)                               # G:336
+        a1 = None if mag_ok else mha.forward_batched(y1, batch)                                 # G:336
         if ebar1 is None:
             ebar1 = EdgeMeanFn.apply(e1, batch)
         else:
             torch.cuda.current_stream(e1.device).wait_stream(self._side[e1.device])
-        if fuse_mha:
+        if mag_ok:
             wq = torch.cat([l.weight for l in mha.linears_q], 0)
             bq = torch.cat([l.bias for l in mha.linears_q], 0)
             wn_x, w_e, winner = _pack_stack(mag.graphconv, mag.head_num, mag.layer_num, mag._g)
+            drop = draw(mha.dropout.p if mha.training else 0.0, mag.gcn_dropout.p if mag.training else 0.0)
+            self.last_drop["maggc"] = drop
             new, a1 = MhaStackFn.apply(y1, ebar1, wq, bq, wn_x, w_e, winner, mag.linear_layer.weight,
-                                       mag.linear_layer.bias, batch, mag.head_num, mag.layer_num)  # G:336-337
+                                       mag.linear_layer.bias, batch, mag.head_num, mag.layer_num, drop)  # G:336-337
         else:
             new = mag.forward_batched(y1, ebar1, a1, batch)                                     # G:337
         y2 = self._blend(new, y1)

@@ -67,6 +67,22 @@ typedef struct gcgcn_batch {
     int32_t class_end[4];     /* cumulative counts in doc_order: n>48, n>32, n>16, n>0   */
 } gcgcn_batch;
 
+/* ---- train-mode dropout of the block-level entry points ------------------------------------------
+ * The reference drops attention probabilities (nn.Dropout(0.1), G:131, G:152 -> G:141, G:166) and each
+ * sub-layer's output copy (gcn_dropout 0.2, G:59, G:90 -> G:74, G:108).  The block kernels regenerate the
+ * keep-scale factors (0 or 1/(1-p)) from (seed, stream, element index) with a counter-based hash in forward AND
+ * backward, so no mask tensor exists; gcgcn_dropout_mask materialises a stream (tests compare this route with
+ * the keep-mask-in route of gcgcn_gat_fwd / gcgcn_mha_fwd / gcgcn_graphconv_stack_fwd element for element).
+ * Streams: 1 GAT attention [pairs], 2 CAGGC sub-layer outputs [rows*128], 3 MHA attention [heads*pairs],
+ * 4 MAGGC sub-layer outputs [rows*heads*128]; element index = row-major offset in that tensor.
+ * A NULL pointer (or both probabilities 0) means no dropout.                                       */
+typedef struct gcgcn_dropout {
+    uint64_t seed;
+    float p_att;    /* attention dropout probability, in [0, 1) */
+    float p_gcn;    /* sub-layer output dropout probability, in [0, 1) */
+} gcgcn_dropout;
+int gcgcn_dropout_mask(uint64_t seed, int32_t stream_id, float p, int64_t count, float* out, void* stream);
+
 /* ---- library ---------------------------------------------------------------------------- */
 const char* gcgcn_version(void);
 const char* gcgcn_last_error(void);
@@ -185,7 +201,7 @@ int gcgcn_mha_stack_fwd(const gcgcn_batch* bt, int32_t heads, int32_t layers,
                         const float* WnX, const float* We, const float* Winner,
                         const float* Wout, const float* bout,
                         float* q, float* P, float* Z, float* G, float* F, float* y,
-                        void* ws, size_t ws_bytes, void* stream);
+                        const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream);
 int gcgcn_mha_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers,
                         const float* x, const float* ebar, const float* Wq,
                         const float* WnX, const float* We, const float* Winner, const float* Wout,
@@ -193,7 +209,7 @@ int gcgcn_mha_stack_bwd(const gcgcn_batch* bt, int32_t heads, int32_t layers,
                         const float* F, const float* dy,
                         float* dx, float* debar, float* dWq, float* dbq,
                         float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
-                        void* ws, size_t ws_bytes, void* stream);
+                        const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- parameter packing for the stack entry points ----------------------------------------
  * The reference keeps one weights_node [128 + l*g, g] and one weights_edge [128, g] per GraphConv
@@ -225,30 +241,34 @@ int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const floa
 /* ---- block-level composites (SURVEY.md section 8b minimum set) ---------------------------
  * CAGGC = a2 + a4 sharing one pass over e0 (G:330-333); MAGGC = a5 + a6 (G:336-337).
  * They call the entry points above in order with buffers carved from `ws`; `saved` is a
- * caller-owned arena of gcgcn_block_saved_bytes(...) bytes that bwd reads back.            */
+ * caller-owned arena of gcgcn_block_saved_bytes(...) bytes that bwd reads back.  `dropout`
+ * (NULL = none) must be the same struct in fwd and bwd; it needs the block kernels
+ * (gcgcn_block_supported), otherwise GCGCN_ERR_UNSUPPORTED is returned.                    */
 size_t gcgcn_block_saved_bytes(int32_t total_nodes, int64_t total_pairs, int32_t heads);
 int gcgcn_caggc_fwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e,
                     int32_t edge_dtype, const float* u, const float* v, const float* c,
                     const float* WnX, const float* We, const float* Winner, const float* Wout,
-                    const float* bout, float* y, void* saved, void* ws, size_t ws_bytes,
-                    void* stream);
+                    const float* bout, float* y, void* saved, const gcgcn_dropout* dropout,
+                    void* ws, size_t ws_bytes, void* stream);
 int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const void* e,
                     int32_t edge_dtype, const float* u, const float* v,
                     const float* WnX, const float* We, const float* Winner, const float* Wout,
                     const float* dy, const void* saved, float* dx, void* de,
                     float* du, float* dv, float* dc, float* dWnX, float* dWe, float* dWinner,
-                    float* dWout, float* dbout, void* ws, size_t ws_bytes, void* stream);
+                    float* dWout, float* dbout, const gcgcn_dropout* dropout,
+                    void* ws, size_t ws_bytes, void* stream);
 int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x,
                     const void* e, int32_t edge_dtype, const float* Wq, const float* bq,
                     const float* WnX, const float* We, const float* Winner, const float* Wout,
-                    const float* bout, float* y, void* saved, void* ws, size_t ws_bytes,
-                    void* stream);
+                    const float* bout, float* y, void* saved, const gcgcn_dropout* dropout,
+                    void* ws, size_t ws_bytes, void* stream);
 int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const float* x,
                     int32_t edge_dtype, const float* Wq,
                     const float* WnX, const float* We, const float* Winner, const float* Wout,
                     const float* dy, const void* saved, float* dx, void* de,
                     float* dWq, float* dbq, float* dWnX, float* dWe, float* dWinner,
-                    float* dWout, float* dbout, void* ws, size_t ws_bytes, void* stream);
+                    float* dWout, float* dbout, const gcgcn_dropout* dropout,
+                    void* ws, size_t ws_bytes, void* stream);
 
 /* ---- dense projection used by the entry points above (exported for tests) ----------------
  * C = alpha * op(A) op(B) + beta * C (+ bias broadcast over rows), row-major float32.

@@ -54,9 +54,9 @@ def test_block_composites_match_the_module_route(variant):
         saved_m = _arena(lib.gcgcn_block_saved_bytes(M, P, heads))
         y1, y2 = torch.empty(M, 128, device=DEV), torch.empty(M, 128, device=DEV)
         _lib.call("gcgcn_caggc_fwd", bt.ref, layers, _p(xd), _p(e0d), _lib.F32, _p(u), _p(v), _p(c), _p(cw[0]),
-                  _p(cw[1]), _p(cw[2]), _p(cwo), _p(cbo), _p(y1), _p(saved_c), ws.data_ptr(), ws.numel(), st)
+                  _p(cw[1]), _p(cw[2]), _p(cwo), _p(cbo), _p(y1), _p(saved_c), None, ws.data_ptr(), ws.numel(), st)
         _lib.call("gcgcn_maggc_fwd", bt.ref, layers, heads, _p(y1), _p(e1d), _lib.F32, _p(wq), _p(bq), _p(mw[0]),
-                  _p(mw[1]), _p(mw[2]), _p(mwo), _p(mbo), _p(y2), _p(saved_m), ws.data_ptr(), ws.numel(), st)
+                  _p(mw[1]), _p(mw[2]), _p(mwo), _p(mbo), _p(y2), _p(saved_m), None, ws.data_ptr(), ws.numel(), st)
         assert_close(y1, ref["y1"], 1e-5, "caggc_fwd y1")
         assert_close(y2, ref["y2"], 1e-5, "maggc_fwd y2")
 
@@ -67,7 +67,7 @@ def test_block_composites_match_the_module_route(variant):
         g_m = [like(wq), torch.empty(128, device=DEV), like(mw[0]), like(mw[1]), like(mw[2]), like(mwo),
                torch.empty(128, device=DEV)]
         _lib.call("gcgcn_maggc_bwd", bt.ref, layers, heads, _p(y1), _lib.F32, _p(wq), _p(mw[0]), _p(mw[1]), _p(mw[2]),
-                  _p(mwo), _p(dy2), _p(saved_m), _p(dx1), _p(de1), *[_p(t) for t in g_m], ws.data_ptr(),
+                  _p(mwo), _p(dy2), _p(saved_m), _p(dx1), _p(de1), *[_p(t) for t in g_m], None, ws.data_ptr(),
                   ws.numel(), st)
         dy1_total = dy1 + dx1                       # y1 feeds the MAGGC block and the output (alpha = 1, G:339)
         dx0, de0 = torch.empty_like(xd), torch.empty_like(e0d)
@@ -75,7 +75,7 @@ def test_block_composites_match_the_module_route(variant):
         g_c = [like(cw[0]), like(cw[1]), like(cw[2]), like(cwo), torch.empty(128, device=DEV)]
         _lib.call("gcgcn_caggc_bwd", bt.ref, layers, _p(xd), _p(e0d), _lib.F32, _p(u), _p(v), _p(cw[0]), _p(cw[1]),
                   _p(cw[2]), _p(cwo), _p(dy1_total), _p(saved_c), _p(dx0), _p(de0), _p(du), _p(dv), _p(dc),
-                  *[_p(t) for t in g_c], ws.data_ptr(), ws.numel(), st)
+                  *[_p(t) for t in g_c], None, ws.data_ptr(), ws.numel(), st)
         torch.cuda.synchronize()
         assert_close(de1, ref["de1"], FP32_TOL, "maggc_bwd de1")
         assert_close(dx0, ref["dx0"], FP32_TOL, "caggc_bwd dx0")
@@ -97,4 +97,4 @@ def test_block_supported_reports_the_kernel_envelope():
     assert lib.gcgcn_block_supported(big.ref, 8, 2, 1) == 0          # > 64 nodes: per-op route
     x = torch.zeros(small.total_nodes, 128, device=DEV)
     with pytest.raises(_lib.GcgcnError):                              # and the fused entry point refuses, loudly
-        _lib.call("gcgcn_mha_stack_fwd", big.ref, 8, 2, *([_p(x)] * 15), None, 0, _stream(DEV))
+        _lib.call("gcgcn_mha_stack_fwd", big.ref, 8, 2, *([_p(x)] * 15), None, None, 0, _stream(DEV))
