@@ -113,6 +113,33 @@ def test_entity_count_sweep(n, heads, layers):
             assert_close(v, r["dparams"][k], 5 * FP32_TOL, f"n={n} d{k}")
 
 
+@pytest.mark.parametrize("layers,heads", [(2, 4), (4, 8), (2, 8), (4, 4)])
+def test_every_block_kernel_instantiation(layers, heads):
+    """The fused route for all four (sub-layer width, head width) combinations x all four size classes."""
+    gb, state = device_blocks(layers, heads)
+    sizes = [64, 50, 48, 33, 32, 17, 16, 9, 1]
+    docs = [S.make_doc(300 + i, n=n, L=32) for i, n in enumerate(sizes)]
+    before = _lib.launch_count()
+    res = run_blocks(gb, docs)
+    assert _lib.launch_count() - before >= 20
+    bt = res["bt"]
+    total = {}
+    for b, d in enumerate(docs):
+        r = oracle_blocks(d, state, layers, heads)
+        for k in ("y1", "y2", "dx0"):
+            assert_close(bt.split_nodes(res[k])[b], r[k], FP32_TOL, f"L{layers} H{heads} n={d.n} {k}")
+        for k in ("de0", "de1"):
+            assert_close(bt.split_pairs(res[k])[b], r[k], FP32_TOL, f"L{layers} H{heads} n={d.n} {k}")
+        for h in range(heads):
+            assert_close(bt.split_pairs(res["a1"][h])[b], r["a1"][h], 1e-5, f"n={d.n} a1[{h}]")
+        for k, v in r["dparams"].items():
+            if v is not None:
+                total[k] = total.get(k, 0) + v
+    for k, v in res["dparams"].items():
+        if v is not None:
+            assert_close(v, total[k], 5 * FP32_TOL, f"L{layers} H{heads} d{k}")
+
+
 def test_ragged_edge_cases():
     """n = 1, 2, 3 next to large documents, repeated sizes, documents in any order."""
     gb, state = device_blocks(2, 8)
