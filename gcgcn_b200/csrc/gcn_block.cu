@@ -456,16 +456,22 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     constexpr int NP = 16 * MTC, MT = MTC, NT8 = 2 * MTC, LDA = NP + 4, KI = (layers - 1) * GD, LDG = KI + 4;
     const int HD = DH > 0 ? (D / DHH) * S : heads * S;
 
-    float* AtH = smem;                 // [NP][LDA]  A transposed (AtH[j][i] + AtL[j][i] = A[i][j]), hi plane
-    float* AtL = AtH + NP * LDA;       //            lo plane
-    float* dAs = AtL + NP * LDA;       // [NP][LDA]  dA accumulated over the sub-layers (fp32)
-    float* dNh = dAs + NP * LDA;       // [NP][LDN]  dN_l = relu'(g_l) dG_l / r, hi / lo planes
+    // Shared memory is what limits residency here, so: the attention map is one fp32 plane (its fragments are
+    // split in registers), dA accumulates in registers across the sub-layers, and with two sub-layers the single
+    // parked dense-connect gradient lives in the (then dead) dN hi plane.
+    constexpr bool TWO = (layers == 2);
+    float* AtS = smem;                 // [NP][LDA]  A transposed: AtS[j][i] = A[i][j], fp32
+    float* dNh = AtS + NP * LDA;       // [NP][LDN]  dN_l = relu'(g_l) dG_l / r, hi / lo planes
     float* dNl = dNh + NP * LDN;
     float* Th = dNl + NP * LDN;        // [NP][LDN]  Z_l, then dZ_l, hi / lo planes
     float* Tl = Th + NP * LDN;
-    float* dGs = Tl + NP * LDN;        // [NP][LDG]  dense-connect gradient parked for sub-layers < l (fp32)
-    float* rs = dGs + NP * LDG;        // [NP]
+    float* rs = Tl + NP * LDN;         // [NP]
     float* drs = rs + NP;              // [NP]
+    // dA / dS scratch of the final phase [NP][LDA]: the tail of the (dead) T planes, or its own region when the
+    // head of the dN/T area is too small for the dq operands (sub-layer width 32)
+    float* dAs = TWO ? Tl + NP * LDN - NP * LDA : drs + NP;
+    float* dGs = TWO ? dNh : dAs + NP * LDA;      // [NP][LDG or LDN]  dense-connect gradient parked for sub-layers < l
+    constexpr int LDP = TWO ? LDN : LDG;          // its row stride
 
     const int tid = threadIdx.x;
     const LaneGeo L;
@@ -485,10 +491,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 float v = (i < n && j < n) ? Ab[i * n + j] : 0.f;
                 if (drop.thr_att != 0u && i < n && j < n)       // A = P * keep, regenerated (Ab then holds the softmax output P)
                     v *= drop_keep(drop.seed, drop.s_att, abase + i * n + j, drop.thr_att, drop.inv_att);
-                float hi, lo;
-                split_f(v, hi, lo);
-                AtH[j * LDA + i] = hi;
-                AtL[j * LDA + i] = lo;
+                AtS[j * LDA + i] = v;
                 sum += v;
             }
         }
@@ -498,6 +501,9 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     __syncthreads();
 
     const int cg = tid % CG, rg = tid / CG, c0 = cg * 4;
+    float cA[NTW_C][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW_C; ++nt) { cA[nt][0] = 0.f; cA[nt][1] = 0.f; cA[nt][2] = 0.f; cA[nt][3] = 0.f; }
 #pragma unroll
     for (int l = layers - 1; l >= 0; --l) {
         const float* wsrc = Wb + (static_cast<size_t>(h) * layers + l) * (KI * GD * 2);   // [m][ks][nt][4][32]
@@ -520,7 +526,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                     dg.x *= k01.x; dg.y *= k01.y; dg.z *= k23.x; dg.w *= k23.y;
                 }
                 if (!first_layer) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(dGs + i * LDG + l * GD + c0);
+                    const float4 s4 = *reinterpret_cast<const float4*>(dGs + i * LDP + l * GD + c0);
                     dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
                 }
                 dg.x = g4.x > 0.f ? dg.x : 0.f; dg.y = g4.y > 0.f ? dg.y : 0.f;
@@ -542,12 +548,11 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
             if (cg == 0 && i < n) drs[i] += drp;
         }
         __syncthreads();
-        // (c) dA += dN_l Z_l^T      (both operands K-contiguous: ldmatrix on either side)
+        // (c) dA += dN_l Z_l^T      (both operands K-contiguous: ldmatrix on either side; accumulators live in
+        //     registers across the sub-layers)
         if (L.warp < UNITS_C) {
             const int mt = L.warp / NG_C, jg = L.warp - mt * NG_C;
-            float c[NTW_C][4];
-#pragma unroll
-            for (int nt = 0; nt < NTW_C; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+            float (&c)[NTW_C][4] = cA;
             const float* pa = dNh + (16 * mt + L.a_row) * LDN + L.a_col;
             const float* pb = (L.b_lo ? Tl : Th) + (8 * NTW_C * jg + L.b_row) * LDN + L.b_col;
 #pragma unroll
@@ -562,15 +567,6 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                     mma3(c[nt], ah, al, bb[0], bb[1], bb[2], bb[3]);
                 }
             }
-#pragma unroll
-            for (int nt = 0; nt < NTW_C; ++nt)
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float2* p = reinterpret_cast<float2*>(dAs + (16 * mt + L.g + 8 * half) * LDA + 8 * (NTW_C * jg + nt) + 2 * L.t);
-                    float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
-                    if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
-                    *p = v;
-                }
         }
         // (b) dZ_l = A^T dN_l  -> T planes (for the dense-connect push-down) and global
         const int jt = L.warp / NG, ng = L.warp - jt * NG;
@@ -581,13 +577,19 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 #pragma unroll
             for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
             if (busy) {
-                const float* pa = AtH + (16 * jt + L.a_row) * LDA + L.a_col;
+                const float* pa = AtS + (16 * jt + L.a_row) * LDA + L.a_col;
                 const float* nb = dNh + L.t * LDN + col0 + L.g;
 #pragma unroll
                 for (int k0 = 0; k0 < NP; k0 += 8) {
                     uint32_t ah[4], al[4];
                     ldsm4(ah, pa + k0);
-                    ldsm4(al, pa + NP * LDA + k0);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float hi, lo;
+                        split_f(__uint_as_float(ah[e]), hi, lo);
+                        ah[e] = __float_as_uint(hi);
+                        al[e] = __float_as_uint(lo);
+                    }
 #pragma unroll
                     for (int nt = 0; nt < NTW; ++nt)
                         mma3(c[nt], ah, al, __float_as_uint(nb[k0 * LDN + 8 * nt]), __float_as_uint(nb[(k0 + 4) * LDN + 8 * nt]),
@@ -638,7 +640,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        float2* p = reinterpret_cast<float2*>(dGs + (16 * jt + L.g + 8 * half) * LDG + m * GD + col0 + 8 * nt + 2 * L.t);
+                        float2* p = reinterpret_cast<float2*>(dGs + (16 * jt + L.g + 8 * half) * LDP + m * GD + col0 + 8 * nt + 2 * L.t);
                         float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
                         if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
                         *p = v;
@@ -648,6 +650,16 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         __syncthreads();
     }
 
+    if (L.warp < UNITS_C) {            // dA accumulators -> shared scratch for the row-wise phase
+        const int mt = L.warp / NG_C, jg = L.warp - mt * NG_C;
+#pragma unroll
+        for (int nt = 0; nt < NTW_C; ++nt)
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+                *reinterpret_cast<float2*>(dAs + (16 * mt + L.g + 8 * half) * LDA + 8 * (NTW_C * jg + nt) + 2 * L.t) =
+                    make_float2(cA[nt][2 * half], cA[nt][2 * half + 1]);
+    }
+    __syncthreads();
     // ---- attention gradient leaves the CTA: rows in groups of 8 lanes ---------------------------
 #pragma unroll
     for (int r0 = 0; r0 < NP; r0 += 32) {
@@ -668,7 +680,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                         dp[r] *= drop_keep(drop.seed, drop.s_att, abase + i * n + j, drop.thr_att, drop.inv_att);
                         p[r] = Ab[i * n + j];
                     } else {
-                        p[r] = AtH[j * LDA + i] + AtL[j * LDA + i];
+                        p[r] = AtS[j * LDA + i];
                     }
                     dot += dp[r] * p[r];
                 }
@@ -746,8 +758,9 @@ static size_t block_fwd_smem(int np, int layers, int gd) {
 }
 static size_t block_bwd_smem(int np, int layers, int gd) {
     const int ki = (layers - 1) * gd;
-    return (3 * static_cast<size_t>(np) * (np + 4) + 4 * static_cast<size_t>(np) * (gd + 12) +
-            static_cast<size_t>(np) * (ki + 4) + 2 * np) * sizeof(float);
+    size_t fl = static_cast<size_t>(np) * (np + 4) + 4 * static_cast<size_t>(np) * (gd + 12) + 2 * np;
+    if (layers != 2) fl += static_cast<size_t>(np) * (np + 4) + static_cast<size_t>(np) * (ki + 4);   // dA scratch, parked dG
+    return fl * sizeof(float);
 }
 
 // Block kernels cover: documents of <= 64 nodes, slab 128 cut into 2 x 64 or 4 x 32 sub-layers, and -- when
