@@ -175,7 +175,7 @@ struct LaneGeo {
 // MTC = size class: every document of the launch is padded to NP = 16 MTC rows (compile-time strides, fully
 // unrolled tile loops -- with run-time strides the integer address arithmetic outweighed the MMAs 4:1).
 template <int GD, int DH, int MTC>
-__global__ void __launch_bounds__(BK_THREADS, 3)
+__global__ void __launch_bounds__(BK_THREADS, MTC <= 2 ? 4 : 3)
 block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
                  const float* __restrict__ A, const float* __restrict__ q, float* __restrict__ P,
                  float* __restrict__ Z, const float* __restrict__ E, const float* __restrict__ Wf,
@@ -437,7 +437,7 @@ block_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 // OUT = BK_OUT_DS: A is a softmax output; dS = A (dA - rowsum(dA A)) is written instead (GAT, one head).
 // OUT = BK_OUT_DQ: as DS, then dq_h = scale (dS + dS^T) q_h is written to the head slice of dq [rows][128].
 template <int GD, int DH, int OUT, int MTC>
-__global__ void __launch_bounds__(BK_THREADS, 3)
+__global__ void __launch_bounds__(BK_THREADS, MTC <= 2 ? 4 : 3)
 block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
                  const float* __restrict__ A, const float* __restrict__ q, const float* __restrict__ Z,
                  const float* __restrict__ G, const float* __restrict__ Wb, const float* __restrict__ dF,
