@@ -256,16 +256,17 @@ int launch_splitk_reduce(const float* partial, int splits, int M, int N, float a
 
 int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                    int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
-                   cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC);
+                   cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC, void* pre_ws,
+                   size_t pre_bytes);
 
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
-                size_t ws_bytes, cudaStream_t st) {
+                size_t ws_bytes, cudaStream_t st, void* pre_ws, size_t pre_bytes) {
     if (M <= 0 || N <= 0) return GCGCN_OK;
     if (K < 0) return fail(GCGCN_ERR_INVALID_ARG, "gemm: K < 0");
     int taken = 0;
     GCGCN_TRY(launch_gemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ws, ws_bytes, st, &taken,
-                             1, 0, 0, 0));
+                             1, 0, 0, 0, pre_ws, pre_bytes));
     if (taken) return GCGCN_OK;
     const int tiles = ceil_div(M, GM) * ceil_div(N, GN);
     int splits = 1;
@@ -308,11 +309,11 @@ int launch_gemm_batched(int ta, int tb, int M, int N, int K, float alpha, const 
     if (M <= 0 || N <= 0 || batch <= 0) return GCGCN_OK;
     int taken = 0;
     GCGCN_TRY(launch_gemm_tc(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, ws, ws_bytes, st, &taken,
-                             batch, sA, sB, sC));
+                             batch, sA, sB, sC, nullptr, 0));
     if (taken) return GCGCN_OK;
     for (int b = 0; b < batch; ++b)
         GCGCN_TRY(launch_gemm(ta, tb, M, N, K, alpha, A + b * sA, lda, B + b * sB, ldb, beta, C + b * sC, ldc, nullptr,
-                              ws, ws_bytes, st));
+                              ws, ws_bytes, st, nullptr, 0));
     return GCGCN_OK;
 }
 

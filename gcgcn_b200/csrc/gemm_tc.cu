@@ -51,6 +51,7 @@ struct TcArgs {
     float alpha, beta;
     int tiles_m, tiles_n, k_splits, k_per_split;
     const uint8_t* Bpre;            // != nullptr -> B operand pre-split into ready-to-copy stage blobs [tiles_n][kblocks]
+    const uint8_t* Apre;            // != nullptr -> A operand pre-split likewise, blobs [tiles_m][kblocks]
     int kblocks;                    // ceil(K / TC_BK), blob index stride of Bpre
     int batch;                      // independent products per launch (same shapes, strided operands)
     long long sA, sB, sC;           // element strides between consecutive products
@@ -224,7 +225,9 @@ __device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, con
 // producers' work, and the registers it frees double-buffer the A loads (two K blocks in flight per group).
 constexpr uint32_t TC_B_BLOB_BYTES = 2 * TC_PART_BYTES;     // B_hi part, B_lo part
 
-template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS, bool BPRE>
+// APRE: the mirror image for the weight-gradient products (K = every node row): the small [rows, 128] operand is
+// pre-split into blobs, the producers keep the wide M/N-contiguous operand (double-buffered), one tile per CTA.
+template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS, bool BPRE, bool APRE = false>
 __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const TcArgs args) {
     constexpr int TC_PRODUCER_WARPS = 4 * GROUPS, TC_MMA_WARP = 4 * GROUPS, TC_GROUPS = GROUPS;
     // (no integer round trip on this pointer: the compiler must keep seeing shared memory, or every
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(full_bar(s), BPRE ? 5 : 4);   // one arrive per producer warp (+ the expect_tx arrive of the B blob)
+            mbar_init(full_bar(s), (BPRE || APRE) ? 5 : 4);   // one arrive per producer warp (+ the expect_tx arrive of the blob)
             mbar_init(empty_bar(s), 1);   // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -308,8 +311,46 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
                 q += GROUPS;
             }
         }
+        if (APRE && static_cast<int>(blockIdx.x) < total_tiles) {
+            // (batch == 1, one tile per CTA)  q = K block within this CTA's K range
+            const int t = blockIdx.x, ks = t / tiles_mn, rem = t - ks * tiles_mn;
+            const int mtile = rem / args.tiles_n, n0 = (rem % args.tiles_n) * TC_BN;
+            const int kbeg = ks * args.k_per_split, kend = min(args.K, kbeg + args.k_per_split);
+            const int total_q = (kend - kbeg + TC_BK - 1) / TC_BK;
+            auto fetch = [&](int q, float4 (&v)[8]) {
+                fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, kbeg + q * TC_BK, kend, b_vec, tid, v);
+            };
+            auto commit = [&](int q, const float4 (&v)[8]) {
+                const int stage = q % TC_STAGES;
+                const uint32_t phase = (q / TC_STAGES) & 1;
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                uint8_t* stb = smem + size_t(stage) * TC_STAGE_BYTES;
+                if (tid == 0) {
+                    const uint8_t* blob = args.Apre + (static_cast<size_t>(mtile) * args.kblocks + kbeg / TC_BK + q) * TC_B_BLOB_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), TC_B_BLOB_BYTES);
+                    bulk_copy_g2s(smem_u32(stb), blob, TC_B_BLOB_BYTES, full_bar(stage));       // A_hi, A_lo parts
+                }
+                float* st = reinterpret_cast<float*>(stb);
+                store_operand<B_KCONTIG>(st + 2 * (TC_PART_BYTES / 4), st + 3 * (TC_PART_BYTES / 4), tid, v);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(stage));
+            };
+            float4 vb0[8], vb1[8];
+            int q = group;
+            if (q < total_q) fetch(q, vb0);
+            while (q < total_q) {
+                if (q + GROUPS < total_q) fetch(q + GROUPS, vb1);
+                commit(q, vb0);
+                q += GROUPS;
+                if (q >= total_q) break;
+                if (q + GROUPS < total_q) fetch(q + GROUPS, vb0);
+                commit(q, vb1);
+                q += GROUPS;
+            }
+        }
         int j = 0;                                   // running K-block index of this CTA
-        for (int t = blockIdx.x; !BPRE && t < total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; !BPRE && !APRE && t < total_tiles; t += gridDim.x) {
             const int bi = t / (tiles_mn * args.k_splits), tb = t - bi * (tiles_mn * args.k_splits);
             const int ks = tb / tiles_mn, rem = tb - ks * tiles_mn;
             const int m0 = (rem / args.tiles_n) * TC_BM, n0 = (rem % args.tiles_n) * TC_BN;
@@ -504,6 +545,11 @@ tc_presplit_b_kernel(const float* __restrict__ B, int ldb, int b_kcontig, int N,
     }
 }
 
+// bytes of the pre-split blob array of a [rows, <= 128] operand used as the short side of a weight-gradient GEMM
+size_t gemm_presplit_bytes(int rows) {
+    return static_cast<size_t>(ceil_div(rows < 0 ? 0 : rows, TC_BK)) * TC_B_BLOB_BYTES;
+}
+
 bool gemm_tc_bpre_enabled() {
     static int cached = -1;
     if (cached < 0) {
@@ -528,7 +574,8 @@ bool gemm_tc_enabled() {
 // returns 1 if the launch was taken by the tensor-core path, 0 if the caller should use the SIMT kernel
 int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                    int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
-                   cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC) {
+                   cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC, void* pre_ws,
+                   size_t pre_bytes) {
     *taken = 0;
     if (!gemm_tc_enabled() || K < 1 || batch < 1) return GCGCN_OK;
     if (static_cast<double>(M) * N * K * batch < 2.0e6) return GCGCN_OK;   // tiny: not worth a 128x128 tile
@@ -570,28 +617,44 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
         GCGCN_CHECK_LAUNCH("gemm_presplit_b");
         a.Bpre = static_cast<const uint8_t*>(ws);
     }
+    // weight gradients: short M (the [rows, 128] operand, transposed), K = every row, one tile per CTA after split-K
+    a.Apre = nullptr;
+    const size_t ablob_total = static_cast<size_t>(a.tiles_m) * a.kblocks * TC_B_BLOB_BYTES;
+    // (worth it only when several column tiles re-use the blobs: a 128-wide output reads the operand once anyway)
+    const bool apre = gemm_tc_bpre_enabled() && !bpre && batch == 1 && ta && !tb && K >= 8192 && M <= 2 * TC_BM &&
+                      a.tiles_n >= 2 &&
+                      tiles * splits <= sms && pre_ws != nullptr && ablob_total <= pre_bytes &&
+                      (reinterpret_cast<uintptr_t>(pre_ws) & 15) == 0;
+    if (apre) {
+        tc_presplit_b_kernel<<<a.tiles_m * a.kblocks, 256, 0, st>>>(A, lda, /*kcontig=*/0, M, K, a.kblocks,
+                                                                  static_cast<uint8_t*>(pre_ws));
+        GCGCN_CHECK_LAUNCH("gemm_presplit_a");
+        a.Apre = static_cast<const uint8_t*>(pre_ws);
+    }
     // op(A)[m,k]: stored [M][K] (K contiguous) when !ta, [K][M] when ta.
     // op(B)[k,n] as the N x K operand: stored [N][K] (K contiguous) when tb, [K][N] when !tb.
     const bool a_kc = !ta, b_kc = (tb != 0);
-#define GCGCN_TC_LAUNCH(AK, BK, G, PRE)                                                                  \
+#define GCGCN_TC_LAUNCH(AK, BK, G, ...)                                                                  \
     do {                                                                                                 \
         static bool attr_done = false;                                                                   \
         if (!attr_done) {                                                                                \
-            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, G, PRE>,                       \
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, G, __VA_ARGS__>,               \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                                    static_cast<int>(TC_SMEM_BYTES)), "gemm_tc smem"));   \
             attr_done = true;                                                                            \
         }                                                                                                \
-        gemm_tc_kernel<AK, BK, G, PRE><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);                   \
+        gemm_tc_kernel<AK, BK, G, __VA_ARGS__><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);           \
     } while (0)
-    if (bpre) GCGCN_TC_LAUNCH(true, true, 3, true);
+    if (apre) GCGCN_TC_LAUNCH(false, false, 2, false, true);
+    else if (bpre) GCGCN_TC_LAUNCH(true, true, 3, true);
     else if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3, false);
     else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3, false);
     else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3, false);
     else GCGCN_TC_LAUNCH(false, false, 2, false);
 #undef GCGCN_TC_LAUNCH
     timing_set_work(2.0 * M * N * K * batch);
-    GCGCN_CHECK_LAUNCH(bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
+    GCGCN_CHECK_LAUNCH(apre ? "gemm_tc_tn<presplit A>"
+                            : bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
                             : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));

@@ -447,7 +447,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_a=False, trans_b=False, bias=No
     N = b.shape[0] if trans_b else b.shape[1]
     if out is None:
         out = torch.zeros(M, N, device=a.device)
-    ws = workspace(a.device, 32 << 20)
+    ws = workspace(a.device, (24 << 20) + ((K + 31) // 32) * 33024 * ((M + 127) // 128) + 4096)
     _lib.call("gcgcn_gemm", int(trans_a), int(trans_b), M, N, K, float(alpha), _p(a), a.shape[1], _p(b),
               b.shape[1], float(beta), _p(out), out.shape[1], _p(bias), ws.data_ptr(), ws.numel(),
               _stream(a.device))
