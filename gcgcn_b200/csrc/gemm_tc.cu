@@ -31,8 +31,10 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_PLANE_BYTES = 128 * 16 + 16;               // UMMA leading (K) byte offset (odd multiple of 16 B)
 constexpr int TC_PART_BYTES = (TC_BK / 4) * TC_PLANE_BYTES; // one 128 x 32 fp32 operand part
 constexpr int TC_STAGE_BYTES = 4 * TC_PART_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_EPI_LD = 36;                               // epilogue transpose buffer: [32][36] floats per warp (144 B rows)
-constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;
+// epilogue transpose buffer: [32 rows][32 floats] per warp, the 16-byte chunk index XOR-swizzled with (row & 7) so that
+// both the row-per-lane stores and the 8-lanes-per-row loads are bank-conflict free without padding
+constexpr int TC_EPI_WARP_FLOATS = 32 * 32;
+constexpr int TC_EPI_BYTES = 4 * TC_EPI_WARP_FLOATS * 4;
 // GROUPS producer groups of 4 warps (one K block of global loads in flight each), then 1 MMA warp, then 4
 // epilogue warps (warp index 4*GROUPS+1.. so that warp % 4 covers the TMEM lane quarters 1,2,3,0).
 // Three groups for K-contiguous operands; two when both operands are transposed on the way in (the scalar
@@ -217,6 +219,100 @@ __device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, con
         int r, c;
         tile_coord<KCONTIG>(tid, i, r, c);
         split_store(hi, lo, c, r, v[i]);
+    }
+}
+
+// Epilogue of one 128 x 128 output tile for the warp that owns TMEM lane quarter `quarter`: tcgen05.ld gives
+// lane = row, register = column; a 32 x 32 block is transposed through a padded per-warp shared buffer so that every
+// global store instruction writes contiguous 128-byte row segments.  Arrives on tempty_bar_addr once the warp's
+// share of the accumulator is in registers.
+__device__ __forceinline__ void tc_epilogue_tile(const TcArgs& args, uint32_t tmem_base, int acc, uint32_t tempty_bar_addr,
+                                                 int quarter, float* stg, int m0, int n0, int bi, int ks, bool has_k,
+                                                 int lane, int chunk0 = 0, int chunks = TC_BN / 32) {
+    const int row_base = m0 + quarter * 32;
+    float* out_base;
+    int ldo;
+    if (args.partial != nullptr) {
+        out_base = args.partial + (static_cast<size_t>(bi) * args.k_splits + ks) * args.M * args.N;
+        ldo = args.N;
+    } else {
+        out_base = args.C + bi * args.sC;
+        ldo = args.ldc;
+    }
+    const int rows_valid = min(32, args.M - row_base);      // may be <= 0 for padding tiles
+    const bool final_out = args.partial == nullptr;
+    const bool vec = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_base) & 15) == 0) && (n0 + TC_BN <= args.N);
+#pragma unroll 1
+    for (int chunk = chunk0; chunk < chunk0 + chunks; ++chunk) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * TC_BN + chunk * 32);
+        tmem_ld32(taddr, v);
+        if (chunk == chunk0 + chunks - 1) {
+            // the accumulator is in registers now: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar_addr);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)          // lane = row; 16-byte chunk j/4 goes to slot (j/4) ^ (row & 7)
+            *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
+                has_k ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        if (vec) {
+            // lane -> (row = 4*it + lane/8, float4 column = lane%8): 4 rows x 128 contiguous bytes per store
+            const int c4 = (lane & 7) * 4, col = n0 + chunk * 32 + c4;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (final_out && args.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(args.bias + col);
+            // beta != 0: fetch the 8 old values first -- interleaved with the stores the compiler must keep
+            // each load behind the previous store (possible aliasing) and the epilogue becomes a chain of
+            // eight global round trips per 32-column chunk
+            float4 cold[8];
+            const bool rmw = final_out && args.beta != 0.f;
+            if (rmw) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = 4 * it + (lane >> 3);
+                    cold[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < rows_valid)
+                        cold[it] = *reinterpret_cast<const float4*>(out_base + static_cast<size_t>(row_base + rr) * ldo + col);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + (lane >> 3);
+                if (rr < rows_valid) {
+                    float4 val = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+                    float4* p = reinterpret_cast<float4*>(out_base + static_cast<size_t>(row_base + rr) * ldo + col);
+                    if (final_out) {
+                        val.x = val.x * args.alpha + bias4.x; val.y = val.y * args.alpha + bias4.y;
+                        val.z = val.z * args.alpha + bias4.z; val.w = val.w * args.alpha + bias4.w;
+                        if (rmw) {
+                            val.x += args.beta * cold[it].x; val.y += args.beta * cold[it].y;
+                            val.z += args.beta * cold[it].z; val.w += args.beta * cold[it].w;
+                        }
+                    }
+                    *p = val;
+                }
+            }
+        } else {
+            const int col = n0 + chunk * 32 + lane;
+            if (col < args.N) {
+                const float bias = (final_out && args.bias != nullptr) ? args.bias[col] : 0.f;
+                for (int rr = 0; rr < rows_valid; ++rr) {
+                    float val = stg[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+                    float* p = out_base + static_cast<size_t>(row_base + rr) * ldo + col;
+                    if (final_out) {
+                        val = val * args.alpha + bias;
+                        if (args.beta != 0.f) val += args.beta * (*p);
+                    }
+                    *p = val;
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -417,7 +513,7 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
         // per-warp shared buffer so that every global store instruction writes one contiguous 128-byte
         // row segment (lane = column) instead of 32 scattered 16-byte pieces.
         const int quarter = warp & 3;
-        float* stg = epi_stage + quarter * 32 * TC_EPI_LD;
+        float* stg = epi_stage + quarter * TC_EPI_WARP_FLOATS;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -427,91 +523,7 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
             const bool has_k = ks * args.k_per_split < args.K;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int row_base = m0 + quarter * 32;
-            float* out_base;
-            int ldo;
-            if (args.partial != nullptr) {
-                out_base = args.partial + (static_cast<size_t>(bi) * args.k_splits + ks) * args.M * args.N;
-                ldo = args.N;
-            } else {
-                out_base = args.C + bi * args.sC;
-                ldo = args.ldc;
-            }
-            const int rows_valid = min(32, args.M - row_base);      // may be <= 0 for padding tiles
-            const bool final_out = args.partial == nullptr;
-            const bool vec = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_base) & 15) == 0) && (n0 + TC_BN <= args.N);
-#pragma unroll 1
-            for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                       static_cast<uint32_t>(acc * TC_BN + chunk * 32);
-                tmem_ld32(taddr, v);
-                if (chunk == TC_BN / 32 - 1) {
-                    // the accumulator is in registers now: hand the TMEM buffer back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)          // lane = row: 144-byte row pitch -> conflict-free float4 stores
-                    *reinterpret_cast<float4*>(stg + lane * TC_EPI_LD + j) =
-                        has_k ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                            __uint_as_float(v[j + 3]))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncwarp();
-                if (vec) {
-                    // lane -> (row = 4*it + lane/8, float4 column = lane%8): 4 rows x 128 contiguous bytes per store
-                    const int c4 = (lane & 7) * 4, col = n0 + chunk * 32 + c4;
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (final_out && args.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(args.bias + col);
-                    // beta != 0: fetch the 8 old values first -- interleaved with the stores the compiler must keep
-                    // each load behind the previous store (possible aliasing) and the epilogue becomes a chain of
-                    // eight global round trips per 32-column chunk
-                    float4 cold[8];
-                    const bool rmw = final_out && args.beta != 0.f;
-                    if (rmw) {
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int rr = 4 * it + (lane >> 3);
-                            cold[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (rr < rows_valid)
-                                cold[it] = *reinterpret_cast<const float4*>(out_base + static_cast<size_t>(row_base + rr) * ldo + col);
-                        }
-                    }
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = 4 * it + (lane >> 3);
-                        if (rr < rows_valid) {
-                            float4 val = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_LD + c4);
-                            float4* p = reinterpret_cast<float4*>(out_base + static_cast<size_t>(row_base + rr) * ldo + col);
-                            if (final_out) {
-                                val.x = val.x * args.alpha + bias4.x; val.y = val.y * args.alpha + bias4.y;
-                                val.z = val.z * args.alpha + bias4.z; val.w = val.w * args.alpha + bias4.w;
-                                if (rmw) {
-                                    val.x += args.beta * cold[it].x; val.y += args.beta * cold[it].y;
-                                    val.z += args.beta * cold[it].z; val.w += args.beta * cold[it].w;
-                                }
-                            }
-                            *p = val;
-                        }
-                    }
-                } else {
-                    const int col = n0 + chunk * 32 + lane;
-                    if (col < args.N) {
-                        const float bias = (final_out && args.bias != nullptr) ? args.bias[col] : 0.f;
-                        for (int rr = 0; rr < rows_valid; ++rr) {
-                            float val = stg[rr * TC_EPI_LD + lane];
-                            float* p = out_base + static_cast<size_t>(row_base + rr) * ldo + col;
-                            if (final_out) {
-                                val = val * args.alpha + bias;
-                                if (args.beta != 0.f) val += args.beta * (*p);
-                            }
-                            *p = val;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, m0, n0, bi, ks, has_k, lane);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -519,6 +531,144 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
     tc_fence_before();
     __syncthreads();
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// ---- K <= 128 projections with a weight operand: resident row operand -------------------------------------
+// x W with W = [128, H*128]: the H column tiles of a 128-row tile share the row operand, so it is split ONCE per
+// row tile into a resident shared-memory copy (up to 4 K blocks x hi/lo) while the weight blobs stream through two
+// stages by bulk copy.  The producers work once per H tiles instead of once per tile; what remains is MMA issue
+// and the 64 KB-per-tile store.  Roles: warps 0-7 producers (two groups, K blocks g and g+2), warp 8 blob loader,
+// warp 9 MMA issuer, warps 10-13 epilogue (TMEM lane quarters 2,3,0,1).
+constexpr int RA_PRODUCER_WARPS = 8, RA_LOADER_WARP = 8, RA_MMA_WARP = 9, RA_EPI_WARPS = 4, RA_THREADS = (10 + RA_EPI_WARPS) * 32;
+constexpr int RA_KB = 4, RA_BSTAGES = 2;
+constexpr size_t RA_EPI_BYTES = size_t(RA_EPI_WARPS) * TC_EPI_WARP_FLOATS * 4;
+constexpr size_t RA_SMEM_BYTES = size_t(RA_KB) * 2 * TC_PART_BYTES + size_t(RA_BSTAGES) * TC_B_BLOB_BYTES + RA_EPI_BYTES +
+                                 768 /*align slack*/ + 256 /*barriers*/;
+static_assert(RA_SMEM_BYTES <= 227 * 1024, "resident-A kernel exceeds the shared memory of an SM");
+
+__global__ void __launch_bounds__(RA_THREADS, 1) gemm_tc_resa_kernel(const TcArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* a_res = smem;                                             // [RA_KB][A_hi part, A_lo part]
+    uint8_t* b_stage = smem + size_t(RA_KB) * 2 * TC_PART_BYTES;      // [RA_BSTAGES][B_hi part, B_lo part]
+    float* epi_stage = reinterpret_cast<float*>(b_stage + size_t(RA_BSTAGES) * TC_B_BLOB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_stage) + RA_EPI_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t a_full = bar0, a_empty = bar0 + 8;
+    auto b_full = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (6 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (8 + a); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, RA_PRODUCER_WARPS);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < RA_BSTAGES; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), RA_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == RA_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int kblocks = args.kblocks, tiles_n = args.tiles_n, tiles_m = args.tiles_m;
+
+    if (warp < RA_PRODUCER_WARPS) {
+        const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
+        const int group = warp >> 2, tid = threadIdx.x & 127;
+        int it = 0;
+        for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x, ++it) {
+            float4 va[2][8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int kb = group + 2 * hh;
+                if (kb < kblocks) fetch_operand<true>(args.A, args.lda, mi * TC_BM, args.M, kb * TC_BK, args.K, a_vec, tid, va[hh]);
+            }
+            mbar_wait(a_empty, (it & 1) ^ 1);            // the MMAs of the previous row tile have retired
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int kb = group + 2 * hh;
+                if (kb < kblocks) {
+                    float* st = reinterpret_cast<float*>(a_res + size_t(kb) * 2 * TC_PART_BYTES);
+                    store_operand<true>(st, st + TC_PART_BYTES / 4, tid, va[hh]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    } else if (warp == RA_LOADER_WARP) {
+        if (lane == 0) {
+            int q = 0;
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
+                for (int n = 0; n < tiles_n; ++n)
+                    for (int kb = 0; kb < kblocks; ++kb, ++q) {
+                        const int stage = q % RA_BSTAGES;
+                        mbar_wait(b_empty(stage), ((q / RA_BSTAGES) & 1) ^ 1);
+                        const uint8_t* blob = args.Bpre + (static_cast<size_t>(n) * kblocks + kb) * TC_B_BLOB_BYTES;
+                        mbar_arrive_expect_tx(b_full(stage), TC_B_BLOB_BYTES);
+                        bulk_copy_g2s(smem_u32(b_stage + size_t(stage) * TC_B_BLOB_BYTES), blob, TC_B_BLOB_BYTES, b_full(stage));
+                    }
+        }
+        __syncwarp();
+    } else if (warp == RA_MMA_WARP) {
+        if (lane == 0) {
+            int q = 0, acc = 0, it = 0;
+            uint32_t acc_phase = 0;
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x, ++it) {
+                mbar_wait(a_full, it & 1);
+                tc_fence_after();
+                for (int n = 0; n < tiles_n; ++n) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * TC_BN);
+                    uint32_t accumulate = 0;
+                    for (int kb = 0; kb < kblocks; ++kb, ++q) {
+                        const int stage = q % RA_BSTAGES;
+                        mbar_wait(b_full(stage), (q / RA_BSTAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(a_res + size_t(kb) * 2 * TC_PART_BYTES), a_lo = a_hi + TC_PART_BYTES;
+                        const uint32_t b_hi = smem_u32(b_stage + size_t(stage) * TC_B_BLOB_BYTES), b_lo = b_hi + TC_PART_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                            const uint32_t koff = kk * 2 * TC_PLANE_BYTES;
+                            umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), IDESC, accumulate);
+                            umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), IDESC, 1u);
+                            umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), IDESC, 1u);
+                            accumulate = 1u;
+                        }
+                        umma_commit(b_empty(stage));
+                    }
+                    umma_commit(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                umma_commit(a_empty);                    // the resident operand may be replaced once these retire
+            }
+        }
+        __syncwarp();
+    } else {
+        // RA_EPI_WARPS / 4 warps per TMEM lane quarter, each a share of the columns.  (8 warps were measured: no faster --
+        // with two 33 KB weight stages the MMA issuer waits on bulk-copy latency, not on the epilogue.)
+        const int quarter = warp & 3, ew = warp - (RA_MMA_WARP + 1);
+        constexpr int CH = (TC_BN / 32) / (RA_EPI_WARPS / 4);
+        float* stg = epi_stage + ew * TC_EPI_WARP_FLOATS;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
+            for (int n = 0; n < tiles_n; ++n) {
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, mi * TC_BM, n * TC_BN, 0, 0, true, lane,
+                                 (ew / 4) * CH, CH);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == RA_MMA_WARP) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
 // One blob per (128-column tile nt, 32-wide K block kb) of the N x K operand op(B)^T: exactly the B_hi / B_lo half of
@@ -645,7 +795,17 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
         }                                                                                                \
         gemm_tc_kernel<AK, BK, G, __VA_ARGS__><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);           \
     } while (0)
-    if (apre) GCGCN_TC_LAUNCH(false, false, 2, false, true);
+    static const bool resa_on = getenv("GCGCN_GEMM_RESA") == nullptr || getenv("GCGCN_GEMM_RESA")[0] != '0';
+    const bool resa = bpre && resa_on && a.kblocks <= RA_KB && a.tiles_n >= 2 && a.partial == nullptr;
+    if (resa) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_resa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(RA_SMEM_BYTES)), "gemm_tc_resa smem"));
+            attr_done = true;
+        }
+        gemm_tc_resa_kernel<<<std::min(sms, a.tiles_m), RA_THREADS, RA_SMEM_BYTES, st>>>(a);
+    } else if (apre) GCGCN_TC_LAUNCH(false, false, 2, false, true);
     else if (bpre) GCGCN_TC_LAUNCH(true, true, 3, true);
     else if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3, false);
     else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3, false);
@@ -653,7 +813,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     else GCGCN_TC_LAUNCH(false, false, 2, false);
 #undef GCGCN_TC_LAUNCH
     timing_set_work(2.0 * M * N * K * batch);
-    GCGCN_CHECK_LAUNCH(apre ? "gemm_tc_tn<presplit A>"
+    GCGCN_CHECK_LAUNCH(resa ? "gemm_tc_nn<resident A>" : apre ? "gemm_tc_tn<presplit A>"
                             : bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
                             : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1)
