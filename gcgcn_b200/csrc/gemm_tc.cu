@@ -671,6 +671,174 @@ __global__ void __launch_bounds__(RA_THREADS, 1) gemm_tc_resa_kernel(const TcArg
     if (warp == RA_MMA_WARP) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+// ---- K <= 128 projections, row operand resident in TENSOR MEMORY ------------------------------------------
+// Same idea as gemm_tc_resa_kernel, but the split row operand (128 rows x K <= 128, hi and lo) lives in TMEM
+// columns 256..511 (tcgen05.st from the producers' registers, row = lane) and is read by tcgen05.mma as the A
+// operand; shared memory then holds nothing but weight blobs: six 33 KB stages instead of two, which is what the
+// bulk-copy latency needs.  TMEM: accumulators [0,128) and [128,256), A_hi [256,384), A_lo [384,512).
+constexpr int TA_BSTAGES = 5, TA_EPI_WARPS = 8, TA_THREADS = (10 + TA_EPI_WARPS) * 32;
+constexpr size_t TA_EPI_BYTES = size_t(TA_EPI_WARPS) * TC_EPI_WARP_FLOATS * 4;
+constexpr size_t TA_SMEM_BYTES = size_t(TA_BSTAGES) * TC_B_BLOB_BYTES + TA_EPI_BYTES + 768 + 256;
+constexpr uint32_t TA_COL_AHI = 256, TA_COL_ALO = 384;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], 128 x 128 x 8 TF32
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TA_THREADS, 1) gemm_tc_tmema_kernel(const TcArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* b_stage = smem;                                           // [TA_BSTAGES][B_hi part, B_lo part]
+    float* epi_stage = reinterpret_cast<float*>(b_stage + size_t(TA_BSTAGES) * TC_B_BLOB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_stage) + TA_EPI_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * TA_BSTAGES);
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t a_full = bar0, a_empty = bar0 + 8;
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (4 + a); };
+    auto b_full = [&](int s) { return bar0 + 8u * (6 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (6 + TA_BSTAGES + s); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, RA_PRODUCER_WARPS);
+        mbar_init(a_empty, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TA_EPI_WARPS); }
+        for (int i = 0; i < TA_BSTAGES; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        fence_barrier_init();
+    }
+    if (warp == RA_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int kblocks = args.kblocks, tiles_n = args.tiles_n, tiles_m = args.tiles_m;
+
+    if (warp < RA_PRODUCER_WARPS) {
+        // warp -> TMEM lane quarter (warp & 3) and K half (warp >> 2); lane = row of the quarter
+        const int quarter = warp & 3, khalf = warp >> 2;
+        const bool a_vec = (args.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
+        int it = 0;
+        for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x, ++it) {
+            const int row = mi * TC_BM + quarter * 32 + lane;
+            const float* src = args.A + static_cast<size_t>(row) * args.lda;
+            mbar_wait(a_empty, (it & 1) ^ 1);            // the MMAs of the previous row tile have retired
+            tc_fence_after();
+#pragma unroll 1
+            for (int c16 = 0; c16 < 4; ++c16) {
+                const int k0 = khalf * 64 + c16 * 16;
+                if (k0 >= kblocks * TC_BK) break;          // columns beyond the K blocks in use are never read
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float t[4];
+                    if (row < args.M && a_vec && k0 + j + 4 <= args.K) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + k0 + j);
+                        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) t[e] = (row < args.M && k0 + j + e < args.K) ? src[k0 + j + e] : 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = __float_as_uint(t[e]) & 0xffffe000u;
+                        hi[j + e] = h;
+                        lo[j + e] = __float_as_uint(t[e] - __uint_as_float(h));
+                    }
+                }
+                const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+                tmem_st16(lane_base + TA_COL_AHI + k0, hi);
+                tmem_st16(lane_base + TA_COL_ALO + k0, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    } else if (warp == RA_LOADER_WARP) {
+        if (lane == 0) {
+            int q = 0;
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
+                for (int n = 0; n < tiles_n; ++n)
+                    for (int kb = 0; kb < kblocks; ++kb, ++q) {
+                        const int stage = q % TA_BSTAGES;
+                        mbar_wait(b_empty(stage), ((q / TA_BSTAGES) & 1) ^ 1);
+                        const uint8_t* blob = args.Bpre + (static_cast<size_t>(n) * kblocks + kb) * TC_B_BLOB_BYTES;
+                        mbar_arrive_expect_tx(b_full(stage), TC_B_BLOB_BYTES);
+                        bulk_copy_g2s(smem_u32(b_stage + size_t(stage) * TC_B_BLOB_BYTES), blob, TC_B_BLOB_BYTES, b_full(stage));
+                    }
+        }
+        __syncwarp();
+    } else if (warp == RA_MMA_WARP) {
+        if (lane == 0) {
+            int q = 0, acc = 0, it = 0;
+            uint32_t acc_phase = 0;
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x, ++it) {
+                mbar_wait(a_full, it & 1);
+                tc_fence_after();
+                for (int n = 0; n < tiles_n; ++n) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * TC_BN);
+                    uint32_t accumulate = 0;
+                    for (int kb = 0; kb < kblocks; ++kb, ++q) {
+                        const int stage = q % TA_BSTAGES;
+                        mbar_wait(b_full(stage), (q / TA_BSTAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t b_hi = smem_u32(b_stage + size_t(stage) * TC_B_BLOB_BYTES), b_lo = b_hi + TC_PART_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                            const uint32_t koff = kk * 2 * TC_PLANE_BYTES;
+                            const uint32_t acol = static_cast<uint32_t>(kb * TC_BK + kk * 8);
+                            umma_tf32_ts(d_tmem, tmem_base + TA_COL_ALO + acol, make_desc(b_hi + koff), IDESC, accumulate);
+                            umma_tf32_ts(d_tmem, tmem_base + TA_COL_AHI + acol, make_desc(b_lo + koff), IDESC, 1u);
+                            umma_tf32_ts(d_tmem, tmem_base + TA_COL_AHI + acol, make_desc(b_hi + koff), IDESC, 1u);
+                            accumulate = 1u;
+                        }
+                        umma_commit(b_empty(stage));
+                    }
+                    umma_commit(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                umma_commit(a_empty);                    // the resident operand may be replaced once these retire
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3, ew = warp - (RA_MMA_WARP + 1);
+        constexpr int CH = (TC_BN / 32) / (TA_EPI_WARPS / 4);
+        float* stg = epi_stage + ew * TC_EPI_WARP_FLOATS;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
+            for (int n = 0; n < tiles_n; ++n) {
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, mi * TC_BM, n * TC_BN, 0, 0, true, lane,
+                                 (ew / 4) * CH, CH);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == RA_MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
 // One blob per (128-column tile nt, 32-wide K block kb) of the N x K operand op(B)^T: exactly the B_hi / B_lo half of
 // a shared-memory stage (8 chunk planes of [128 rows][16 B] + pad each), so the GEMM moves it with one bulk copy.
 __global__ void __launch_bounds__(256)
@@ -797,7 +965,16 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     } while (0)
     static const bool resa_on = getenv("GCGCN_GEMM_RESA") == nullptr || getenv("GCGCN_GEMM_RESA")[0] != '0';
     const bool resa = bpre && resa_on && a.kblocks <= RA_KB && a.tiles_n >= 2 && a.partial == nullptr;
-    if (resa) {
+    static const bool tmema_on = getenv("GCGCN_GEMM_TMEMA") == nullptr || getenv("GCGCN_GEMM_TMEMA")[0] != '0';   // =0: shared-memory resident-A kernel
+    if (resa && tmema_on && !ta) {
+        static bool attr_done2 = false;
+        if (!attr_done2) {
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_tmema smem"));
+            attr_done2 = true;
+        }
+        gemm_tc_tmema_kernel<<<std::min(sms, a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
+    } else if (resa) {
         static bool attr_done = false;
         if (!attr_done) {
             GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_resa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -813,7 +990,8 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     else GCGCN_TC_LAUNCH(false, false, 2, false);
 #undef GCGCN_TC_LAUNCH
     timing_set_work(2.0 * M * N * K * batch);
-    GCGCN_CHECK_LAUNCH(resa ? "gemm_tc_nn<resident A>" : apre ? "gemm_tc_tn<presplit A>"
+    GCGCN_CHECK_LAUNCH(resa ? ((tmema_on && !ta) ? "gemm_tc_nn<A in TMEM>" : "gemm_tc_nn<resident A>")
+                            : apre ? "gemm_tc_tn<presplit A>"
                             : bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
                             : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1)
