@@ -63,6 +63,8 @@ int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const flo
 int pair_dis_warps();
 int launch_pack_stack(const float* const* wn_ptrs, const float* const* we_ptrs, int heads, int layers, int slab,
                       float* WnX, float* We, float* Winner, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, long long count, float lr, float b1, float b2,
+                float eps, float wd, float gscale, int step, cudaStream_t st);
 int launch_unpack_stack(const float* dWnX, const float* dWe, const float* dWinner, int heads, int layers, int slab,
                         float* dwn_flat, float* dwe_flat, cudaStream_t st);
 
@@ -760,6 +762,24 @@ int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const floa
 }
 
 // ---- dense projection ------------------------------------------------------------------------
+int gcgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                    int32_t step, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(count >= 0 && step >= 1, "adam_step: count >= 0 and step >= 1 required");
+    GCGCN_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps > 0.f, "adam_step: bad betas/eps");
+    if (count == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(params, "params"));
+    GCGCN_TRY(check_device_ptr(grads, "grads"));
+    GCGCN_TRY(check_device_ptr(exp_avg, "exp_avg"));
+    GCGCN_TRY(check_device_ptr(exp_avg_sq, "exp_avg_sq"));
+    GCGCN_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                    reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+                  "adam_step: buffers must be 16-byte aligned");
+    return launch_adam(params, grads, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                       step, static_cast<cudaStream_t>(stream));
+}
+
 int gcgcn_gemm(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K, float alpha, const float* A,
                int32_t lda, const float* B, int32_t ldb, float beta, float* C, int32_t ldc, const float* bias,
                void* ws, size_t ws_bytes, void* stream) {

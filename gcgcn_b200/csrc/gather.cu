@@ -39,7 +39,10 @@ int launch_csr_gather(const float* src, const int* ptr, const int* idx, const fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// pair gather forward: one warp per (pair, side) output row of feat_w + dis_w floats
+// pair gather forward: one warp per pair writes both output rows (h and t side) of feat_w + dis_w floats.
+// All index loads of a pair are issued together, then all row loads (CH float4 per lane and side), then the
+// stores: 2*CH independent 16-byte loads in flight per lane instead of a idx -> row -> store chain per row.
+template <int CH>
 __global__ void __launch_bounds__(256)
 pair_gather_fwd_kernel(const float4* __restrict__ feat, int fw4, const float4* __restrict__ dis, int dw4,
                        const int* __restrict__ h_idx, const int* __restrict__ t_idx,
@@ -49,17 +52,31 @@ pair_gather_fwd_kernel(const float4* __restrict__ feat, int fw4, const float4* _
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const int ow4 = fw4 + dw4;
-    for (long long item = warp; item < 2 * total_pairs; item += nwarps) {
-        const bool tail = item >= total_pairs;
-        const long long p = tail ? item - total_pairs : item;
-        const int node = tail ? t_idx[p] : h_idx[p];
-        const float4* frow = feat + static_cast<size_t>(node) * fw4;
-        const float4* drow = nullptr;
-        if (dw4 > 0) drow = dis + static_cast<size_t>(tail ? dis_t[p] : dis_h[p]) * dw4;
-        float* orow = (tail ? out_t : out_h) + static_cast<size_t>(p) * ow4 * 4;
-        for (int q = lane; q < ow4; q += WARP) {
-            const float4 v = q < fw4 ? frow[q] : drow[q - fw4];
-            Vec4<float>::store(orow + q * 4, v);
+    for (long long p = warp; p < total_pairs; p += nwarps) {
+        const float4* fh = feat + static_cast<size_t>(h_idx[p]) * fw4;
+        const float4* ft = feat + static_cast<size_t>(t_idx[p]) * fw4;
+        const float4* dh = dw4 > 0 ? dis + static_cast<size_t>(dis_h[p]) * dw4 : nullptr;
+        const float4* dt = dw4 > 0 ? dis + static_cast<size_t>(dis_t[p]) * dw4 : nullptr;
+        float* oh = out_h + static_cast<size_t>(p) * ow4 * 4;
+        float* ot = out_t + static_cast<size_t>(p) * ow4 * 4;
+        for (int q0 = 0; q0 < ow4; q0 += CH * WARP) {
+            float4 vh[CH], vt[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int q = q0 + c * WARP + lane;
+                if (q < ow4) {
+                    vh[c] = q < fw4 ? __ldg(fh + q) : __ldg(dh + (q - fw4));
+                    vt[c] = q < fw4 ? __ldg(ft + q) : __ldg(dt + (q - fw4));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int q = q0 + c * WARP + lane;
+                if (q < ow4) {
+                    Vec4<float>::store(oh + q * 4, vh[c]);
+                    Vec4<float>::store(ot + q * 4, vt[c]);
+                }
+            }
         }
     }
 }
@@ -79,10 +96,12 @@ pair_gather_bwd_feat_kernel(const int* __restrict__ node_ptr, const long long* _
     const long long p0 = pair_ptr[b];
     for (int q = threadIdx.x; q < fw4; q += blockDim.x) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
         for (int i = 0; i < n; ++i) {
             const float4 v = Vec4<float>::load(dout_h + (static_cast<size_t>(p0 + static_cast<long long>(i) * n + k) * ow4 + q) * 4);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
+#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const float4 v = Vec4<float>::load(dout_t + (static_cast<size_t>(p0 + static_cast<long long>(k) * n + j) * ow4 + q) * 4);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -110,11 +129,32 @@ pair_gather_bwd_dis_kernel(const float* __restrict__ dout_h, const float* __rest
     const long long p0 = gw * pairs_per_warp;
     const long long p1 = min(total_pairs, p0 + pairs_per_warp);
     const int ow = fw + dw;
-    for (long long p = p0; p < p1; ++p) {
-        const int kh = dis_h[p], kt = dis_t[p];
+    // eight pairs per trip: their index and gradient loads are issued together, the shared-memory updates then
+    // run in pair order (fixed summation order); the chain per pair was global load -> shared read-modify-write
+    constexpr int U = 8;
+    for (long long p = p0; p < p1; p += U) {
+        int kh[U], kt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pp = min(p + u, p1 - 1);
+            kh[u] = dis_h[pp];
+            kt[u] = dis_t[pp];
+        }
         for (int c = lane; c < dw; c += WARP) {
-            acc[kh * dw + c] += dout_h[static_cast<size_t>(p) * ow + fw + c];
-            acc[kt * dw + c] += dout_t[static_cast<size_t>(p) * ow + fw + c];
+            float vh[U], vt[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long pp = min(p + u, p1 - 1);
+                vh[u] = __ldg(dout_h + static_cast<size_t>(pp) * ow + fw + c);
+                vt[u] = __ldg(dout_t + static_cast<size_t>(pp) * ow + fw + c);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p + u < p1) {
+                    acc[kh[u] * dw + c] += vh[u];
+                    acc[kt[u] * dw + c] += vt[u];
+                }
+            }
         }
     }
     __syncwarp();
@@ -125,11 +165,14 @@ int launch_pair_gather_fwd(const gcgcn_batch* bt, const float* feat, int feat_w,
                            int dis_w, const int* h_idx, const int* t_idx, const int* dis_h,
                            const int* dis_t, float* out_h, float* out_t, cudaStream_t st) {
     if (bt->total_pairs == 0) return GCGCN_OK;
-    const long long warps = 2 * bt->total_pairs;
-    const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, static_cast<long long>(sm_count()) * 16));
-    pair_gather_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(feat), feat_w / 4,
-                                                   reinterpret_cast<const float4*>(dis), dis_w / 4, h_idx,
-                                                   t_idx, dis_h, dis_t, out_h, out_t, bt->total_pairs);
+    const long long warps = bt->total_pairs;
+    const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, static_cast<long long>(sm_count()) * 8));
+    const int ow4 = (feat_w + dis_w) / 4;
+    auto kern = ow4 <= WARP ? pair_gather_fwd_kernel<1> : ow4 <= 2 * WARP ? pair_gather_fwd_kernel<2>
+                                                                         : pair_gather_fwd_kernel<4>;
+    kern<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(feat), feat_w / 4,
+                                 reinterpret_cast<const float4*>(dis), dis_w / 4, h_idx, t_idx, dis_h, dis_t,
+                                 out_h, out_t, bt->total_pairs);
     GCGCN_CHECK_LAUNCH("pair_gather_fwd");
     return GCGCN_OK;
 }

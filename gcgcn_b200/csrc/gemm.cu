@@ -199,6 +199,48 @@ splitk_reduce4_kernel(const float* __restrict__ partial, int splits, int M, int 
     *c = v;
 }
 
+// few outputs, many partials (weight gradients: one 128 x 128 tile split ~144 ways): 32 float4 columns x 8 split
+// lanes per block so that a 16 K-element reduction runs on 128 blocks instead of 16; the 8 lane sums are
+// combined in lane order (deterministic)
+__global__ void __launch_bounds__(256)
+splitk_reduce4_wide_kernel(const float* __restrict__ partial, int splits, int M, int N, float alpha, float beta,
+                           float* __restrict__ C, int ldc, const float* __restrict__ bias, long long batch_stride_c) {
+    __shared__ float4 sm[8][32];
+    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+    const size_t idx = static_cast<size_t>(blockIdx.x) * 32 + cx;
+    const size_t total4 = static_cast<size_t>(M) * N / 4;
+    const float4* part = reinterpret_cast<const float4*>(partial) + static_cast<size_t>(blockIdx.y) * splits * total4;
+    C += static_cast<size_t>(blockIdx.y) * batch_stride_c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < total4) {
+#pragma unroll 4
+        for (int p = sy; p < splits; p += 8) {
+            const float4 u = part[static_cast<size_t>(p) * total4 + idx];
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        }
+    }
+    sm[sy][cx] = a;
+    __syncthreads();
+    if (sy != 0 || idx >= total4) return;
+#pragma unroll
+    for (int y = 1; y < 8; ++y) {
+        const float4 u = sm[y][cx];
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+    }
+    const int m = static_cast<int>(idx / (N / 4)), n = static_cast<int>(idx - static_cast<size_t>(m) * (N / 4)) * 4;
+    float4 v = make_float4(alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w);
+    if (bias != nullptr) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias + n);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    }
+    float4* c = reinterpret_cast<float4*>(C + static_cast<size_t>(m) * ldc + n);
+    if (beta != 0.f) {
+        const float4 cur = *c;
+        v.x += beta * cur.x; v.y += beta * cur.y; v.z += beta * cur.z; v.w += beta * cur.w;
+    }
+    *c = v;
+}
+
 // column sums of a row-major [M, N] matrix (bias gradients), two deterministic stages
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ldx, int rows_per_block,
@@ -243,7 +285,10 @@ int launch_splitk_reduce(const float* partial, int splits, int M, int N, float a
     const bool vec = N % 4 == 0 && ldc % 4 == 0 && sC % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(partial) & 15) == 0 &&
                      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-    if (vec) {
+    if (vec && splits >= 16 && total / 4 <= 64 * 1024) {
+        dim3 grid(ceil_div(total / 4, 32), batch);
+        splitk_reduce4_wide_kernel<<<grid, 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias, sC);
+    } else if (vec) {
         dim3 grid(ceil_div(total / 4, 256), batch);
         splitk_reduce4_kernel<<<grid, 256, 0, st>>>(partial, splits, M, N, alpha, beta, C, ldc, bias, sC);
     } else {

@@ -77,6 +77,74 @@ class GradBucket:
                     g.copy_(v)
 
 
+class FlatTrainer:
+    """Config 5's optimiser state: parameters, gradients and both Adam moments each live in ONE flat fp32
+    buffer, the module's parameters and their ``.grad`` are views into them.
+
+    * autograd accumulates straight into the gradient bucket (``p.grad`` pre-exists as a view), so a step
+      needs no pack / unpack copies: ``zero_grad()`` is one memset, ``all_reduce()`` one NCCL message,
+      ``step()`` one fused kernel (``gcgcn_adam_step``, torch.optim.Adam semantics as at C:300);
+    * parameters that never get a gradient (``linears_k``, G:137) stay out of the bucket when ``skip`` names
+      them -- their ``.grad`` stays ``None`` like in the reference.
+
+    No CPU path: ``step()`` on CPU tensors raises ``GcgcnError``.
+    """
+
+    def __init__(self, module: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, skip: Sequence[str] = ("linears_k",)):
+        named = [(n, p) for n, p in module.named_parameters()
+                 if p.requires_grad and not any(s in n for s in skip)]
+        if not named:
+            raise ValueError("no trainable parameters")
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        dev = self.params[0].device
+        self.sizes = [p.numel() for p in self.params]
+        # every view starts on a 16-byte boundary so the float4 kernel and NCCL see aligned slices
+        self.offsets, off = [], 0
+        for s in self.sizes:
+            self.offsets.append(off)
+            off += (s + 3) // 4 * 4
+        self.numel = off
+        self.flat_params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)          # gradient bucket
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.steps = 0
+        with torch.no_grad():
+            for p, o, s in zip(self.params, self.offsets, self.sizes):
+                view = self.flat_params[o:o + s].view_as(p)
+                view.copy_(p)
+                p.data = view
+                p.grad = self.flat[o:o + s].view_as(p)
+
+    @property
+    def nbytes(self) -> int:
+        return self.numel * 4
+
+    def zero_grad(self):
+        self.flat.zero_()
+        for p, o, s in zip(self.params, self.offsets, self.sizes):      # re-attach if someone set grad = None
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
+                p.grad = self.flat[o:o + s].view_as(p)
+
+    def all_reduce(self, group=None, async_op: bool = False):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    def step(self, grad_scale: float = 1.0):
+        from . import _lib
+        if not self.flat.is_cuda:
+            raise _lib.GcgcnError("FlatTrainer.step: gcgcn_b200 has no CPU path (parameters must live on a B200)")
+        self.steps += 1
+        stream = torch.cuda.current_stream(self.flat.device).cuda_stream
+        _lib.call("gcgcn_adam_step", self.flat_params.data_ptr(), self.flat.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), self.numel, self.lr, self.betas[0], self.betas[1], self.eps,
+                  self.weight_decay, grad_scale, self.steps, stream)
+
+
 def all_reduce_gradients(params: Iterable[torch.nn.Parameter], group=None, average: bool = False,
                          bucket: Optional[GradBucket] = None) -> GradBucket:
     """Sum (or average) gradients over the ranks of ``group`` with one bucketed all-reduce."""

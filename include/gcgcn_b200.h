@@ -270,6 +270,16 @@ int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
                     float* dWout, float* dbout, const gcgcn_dropout* dropout,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* ---- training step of config 5 (new work: the reference has no multi-GPU path) ----
+ * Fused Adam over ONE flat float32 buffer holding every hot-path parameter, with the semantics of
+ * torch.optim.Adam as the reference's trainer constructs it (config/Config.py:300: lr only, betas
+ * (0.9, 0.999), eps 1e-8, weight_decay 0).  `grads` is the (all-reduced) flat gradient bucket,
+ * grad_scale is folded in (1/world_size or 1/documents), `step` counts from 1.  In place on
+ * params / exp_avg / exp_avg_sq; all four buffers 16-byte aligned.                              */
+int gcgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                    int32_t step, void* stream);
+
 /* ---- dense projection used by the entry points above (exported for tests) ----------------
  * C = alpha * op(A) op(B) + beta * C (+ bias broadcast over rows), row-major float32.
  * trans_a / trans_b: 0 = as stored, 1 = transposed.  K may be huge (weight gradients reduce

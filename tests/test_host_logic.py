@@ -114,3 +114,30 @@ def test_shard_documents_balances_pair_counts():
         assert sorted(i for s in shards for i in s) == list(range(1200))
         loads = [int((sizes[s] ** 2).sum()) for s in shards]
         assert max(loads) - min(loads) <= 42 * 42
+
+
+def test_flat_trainer_views_and_cpu_step_is_an_error():
+    """Host logic of config 5's trainer: parameters and gradients become views of two flat buffers (16-byte
+    aligned slices), autograd accumulates into the bucket in place, and step() on CPU raises (no CPU path)."""
+    import pytest
+    from gcgcn_b200 import _lib
+    from gcgcn_b200.modules import GraphBlocks
+    from gcgcn_b200.sharding import FlatTrainer
+    torch.manual_seed(0)
+    gb = GraphBlocks(2, 8)
+    before = {n: p.detach().clone() for n, p in gb.named_parameters()}
+    tr = FlatTrainer(gb)
+    assert sum(tr.sizes) == 545921 and tr.numel % 4 == 0 and all(o % 4 == 0 for o in tr.offsets)
+    for n, p in gb.named_parameters():
+        assert torch.equal(p.detach(), before[n])
+        if "linears_k" in n:
+            assert p.grad is None
+        else:
+            assert p.data_ptr() - tr.flat_params.data_ptr() == p.grad.data_ptr() - tr.flat.data_ptr()
+    w = gb.graphcnn[0].linear_layer.weight
+    (w.sum() * 3.0).backward()
+    assert float(tr.flat.sum()) == 3.0 * w.numel()          # landed in the bucket, no pack step
+    tr.zero_grad()
+    assert float(tr.flat.abs().sum()) == 0.0 and w.grad.data_ptr() >= tr.flat.data_ptr()
+    with pytest.raises(_lib.GcgcnError):
+        tr.step()
