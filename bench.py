@@ -70,6 +70,19 @@ def parse():
     return ap.parse_args()
 
 
+def claim_stdout():
+    """Send everything libraries print to stdout (NCCL's version banner, ...) to stderr and return an emit(text)
+    that writes to the real stdout: the bench prints exactly ONE line there."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text: str):
+        sys.stdout.flush()
+        os.write(real, (text + "\n").encode())
+    return emit
+
+
 # ------------------------------------------------------------------------------- CPU oracle arm
 def cpu_oracle_rate(variant: str, seconds: float, max_passes: int = 1000, warmup: int = 1):
     """graphs/s of the CPU oracle, documents one at a time like the reference trainer (C:339),
@@ -327,6 +340,7 @@ def run_gpu_arm(args):
     from gcgcn_b200.modules import GraphBlocks
     from gcgcn_b200.sharding import GradBucket
 
+    emit = claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -578,8 +592,7 @@ def run_gpu_arm(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": top, "cpu_baseline": cpu,
         "aux": aux,
     }
-    sys.stdout.flush()
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -603,6 +616,7 @@ def run_training_arm(args):
     from gcgcn_b200.modules import GraphBlocks
     from gcgcn_b200.sharding import FlatTrainer
 
+    emit = claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -722,7 +736,7 @@ def run_training_arm(args):
                      "path_note": "SURVEY 8d algorithmic bytes of all documents / pass time / GPUs vs the measured HBM peak"},
         "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def main():

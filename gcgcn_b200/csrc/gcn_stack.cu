@@ -10,7 +10,13 @@
 // This kernel owns everything that couples the rows of one document: A Z_l, the row
 // normalisation, relu, the dense-connect recurrence and the residual.  The n x n map is streamed
 // through shared memory in 64-row tiles, so n up to 256 fits one CTA.
+//
+// The three O(n^2 g) products -- A Z_l forward, dN Z^T and A^T dN backward -- run on the tensor cores
+// (mma.sync m16n8k8 TF32 with the 3xTF32 split of mma_tf32.cuh, fp32 parity); the row-local O(n g^2)
+// dense-connect products and the element-wise epilogues stay on the CUDA cores.  This is the path of
+// config 4's 128/256-entity graphs; DocRED-sized graphs (n <= 64) take gcn_block.cu / gcn_stack_mma.cu.
 #include "common.cuh"
+#include "mma_tf32.cuh"
 
 namespace gcgcn {
 
@@ -22,7 +28,9 @@ struct StackCfg {
     static constexpr int CG = GD / 4;            // 4-column groups per sub-layer slab
     static constexpr int NRG = ST_THREADS / CG;  // row groups
     static constexpr int RT = ST_TR / NRG;       // rows per thread
-    static constexpr int LDZ = GD + 4;           // padded row stride (keeps 16 B alignment)
+    static constexpr int LDZ = GD + 8;           // forward Z tile: stride == 8 (mod 32), conflict-free B fragments
+    static constexpr int LDB = GD + 4;           // backward dN / Z tiles: stride == 4 (mod 8), A and B^T fragments
+    static constexpr int NT = GD / 16;           // 8-column MMA tiles per warp (4 row tiles x 2 column groups)
     static_assert(RT >= 1 && RT * NRG == ST_TR, "tile shape");
 };
 
@@ -37,12 +45,24 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 }
 
 // load rows [row0, row0+ST_TR) of the document's n x n map into As[ST_TR][lda]; rows >= n are zero
+// (columns n .. k8-1, the K padding of the MMA loop, are zero as well)
 __device__ __forceinline__ void load_att_tile(float* As, int lda, const float* __restrict__ Ab, int n,
                                               int row0) {
     const int rows = min(ST_TR, n - row0);
-    for (int t = threadIdx.x; t < ST_TR * n; t += ST_THREADS) {
-        int ii = t / n, j = t - ii * n;
-        As[ii * lda + j] = (ii < rows) ? Ab[static_cast<size_t>(row0 + ii) * n + j] : 0.f;
+    const int k8 = (n + 7) & ~7;
+    for (int t = threadIdx.x; t < ST_TR * k8; t += ST_THREADS) {
+        int ii = t / k8, j = t - ii * k8;
+        As[ii * lda + j] = (ii < rows && j < n) ? Ab[static_cast<size_t>(row0 + ii) * n + j] : 0.f;
+    }
+}
+
+// the same tile transposed, AsT[j][ii] = A[row0 + ii][j] for j < np16 (zero outside the document)
+__device__ __forceinline__ void load_att_tile_t(float* AsT, int ldt, const float* __restrict__ Ab, int n,
+                                                int row0, int np16) {
+    const int rows = min(ST_TR, n - row0);
+    for (int t = threadIdx.x; t < ST_TR * np16; t += ST_THREADS) {
+        int ii = t / np16, j = t - ii * np16;
+        AsT[j * ldt + ii] = (ii < rows && j < n) ? Ab[static_cast<size_t>(row0 + ii) * n + j] : 0.f;
     }
 }
 
@@ -75,7 +95,8 @@ gcn_stack_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restri
     const int HD = heads * S;
     const int KI = (layers - 1) * GD;
     const int LDG = KI + 1;
-    const int lda = n | 1;
+    const int k8 = (n + 7) & ~7;        // K of the A Z_l product, zero padded
+    const int lda = k8 + 4;             // == 4 (mod 8): conflict-free A fragments
     const int ntiles = (n + ST_TR - 1) / ST_TR;
     const int npad = ntiles * ST_TR;
 
@@ -127,51 +148,48 @@ gcn_stack_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restri
             }
         }
         __syncthreads();
-        // (2) out rows = (E + A Z_l) / r, tile of 64 attention rows at a time
-        for (int pb = 0; pb < ntiles; ++pb) {
-            load_att_tile(As, lda, Ab, n, pb * ST_TR);
-            __syncthreads();
-            float4 acc[C::RT];
+        // (2) out rows = (E + A Z_l) / r, tile of 64 attention rows at a time on the tensor cores:
+        //     warp (mt, ng) owns rows 16 mt .. 16 mt + 15 of the tile and columns ng * GD/2 .. + GD/2 - 1
+        {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+            const int mt = warp >> 1, ng = warp & 1;
+            const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+            for (int pb = 0; pb < ntiles; ++pb) {
+                load_att_tile(As, lda, Ab, n, pb * ST_TR);
+                __syncthreads();
+                float c[C::NT][4];
+                zero_frag<C::NT>(c);
+                warp_gemm<C::NT, false>(c, k8 / 8, As + (16 * mt) * lda, lda, Zl + 8 * C::NT * ng, C::LDZ);
 #pragma unroll
-            for (int a = 0; a < C::RT; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float* arow = As + (rg * C::RT) * lda;
-            for (int j = 0; j < n; ++j) {
-                float4 z = ld4(Zl + j * C::LDZ + c0);
-#pragma unroll
-                for (int a = 0; a < C::RT; ++a) fma4(acc[a], arow[a * lda + j], z);
-            }
-#pragma unroll
-            for (int a = 0; a < C::RT; ++a) {
-                const int i = pb * ST_TR + rg * C::RT + a;
-                if (i < n) {
-                    const size_t off = static_cast<size_t>(node0 + i) * HD + col;
-                    const float4 e4 = ld4(E + off);
+                for (int half = 0; half < 2; ++half) {
+                    const int i = pb * ST_TR + 16 * mt + g + 8 * half;
+                    if (i >= n) continue;
                     const float r = rs[i];
-                    float4 o;
-                    o.x = (e4.x + acc[a].x) / r; o.y = (e4.y + acc[a].y) / r;
-                    o.z = (e4.z + acc[a].z) / r; o.w = (e4.w + acc[a].w) / r;
-                    if (relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f);
-                        o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+                    for (int nt = 0; nt < C::NT; ++nt) {
+                        const int cw = 8 * C::NT * ng + 8 * nt + 2 * t;
+                        const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + cw;
+                        const float2 e2 = ld2g(E + off);
+                        float2 o;
+                        o.x = (e2.x + c[nt][2 * half]) / r;
+                        o.y = (e2.y + c[nt][2 * half + 1]) / r;
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                        *reinterpret_cast<float2*>(G + off) = o;
+                        if (l < layers - 1) {
+                            float* gs = Gs + i * LDG + kin + cw;
+                            gs[0] = o.x; gs[1] = o.y;
+                        }
+                        float2 f = o;
+                        if (keep != nullptr) { const float2 k2 = ld2g(keep + off); f.x *= k2.x; f.y *= k2.y; }
+                        if (resid) {
+                            const float2 x2 = ld2g(x + static_cast<size_t>(node0 + i) * S + l * GD + cw);
+                            f.x += x2.x; f.y += x2.y;
+                        }
+                        *reinterpret_cast<float2*>(F + off) = f;
                     }
-                    st4(G + off, o);
-                    if (l < layers - 1) {
-                        float* gs = Gs + i * LDG + kin + c0;
-                        gs[0] = o.x; gs[1] = o.y; gs[2] = o.z; gs[3] = o.w;
-                    }
-                    float4 f = o;
-                    if (keep != nullptr) {
-                        const float4 k4 = ld4(keep + off);
-                        f.x *= k4.x; f.y *= k4.y; f.z *= k4.z; f.w *= k4.w;
-                    }
-                    if (resid) {
-                        const float4 x4 = ld4(x + static_cast<size_t>(node0 + i) * S + l * GD + c0);
-                        f.x += x4.x; f.y += x4.y; f.z += x4.z; f.w += x4.w;
-                    }
-                    st4(F + off, f);
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
 }
@@ -198,15 +216,16 @@ gcn_stack_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restri
     if (n == 0) return;
     const int S = layers * GD;   // per-head slab width (= 128 inside the conv blocks)
     const int HD = heads * S;
-    const int lda = n | 1;
+    const int np16 = (n + 15) & ~15;    // M of the A^T dN product
+    constexpr int LDT = ST_TR + 4;      // transposed attention tile: == 4 (mod 8)
     const int ntiles = (n + ST_TR - 1) / ST_TR;
     const int npad = ntiles * ST_TR;
 
     float* dNs = smem;                                       // [npad][LDZ]  dN_l = dOut / r
-    float* Ts = dNs + static_cast<size_t>(npad) * C::LDZ;    // [npad][LDZ]  Z_l, later dZ_l
-    float* WT = Ts + static_cast<size_t>(npad) * C::LDZ;     // [(layers-1)][GD][GD] transposed slices
-    float* As = WT + static_cast<size_t>(layers - 1) * GD * GD;  // [ST_TR][lda]
-    float* rs = As + static_cast<size_t>(ST_TR) * lda;       // [n]
+    float* Ts = dNs + static_cast<size_t>(npad) * C::LDB;    // [npad][LDZ]  Z_l, later dZ_l
+    float* WT = Ts + static_cast<size_t>(npad) * C::LDB;     // [(layers-1)][GD][GD] transposed slices
+    float* AsT = WT + static_cast<size_t>(layers - 1) * GD * GD;  // [np16][LDT]  AsT[j][ii] = A[tile row ii][j]
+    float* rs = AsT + static_cast<size_t>(np16) * LDT;       // [n]
     float* drs = rs + n;                                     // [n]
 
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
@@ -261,84 +280,71 @@ gcn_stack_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restri
                     drp = -(dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
                     zl = ld4(Z + off);
                 }
-                st4(dNs + (pb * ST_TR + rg * C::RT + a) * C::LDZ + c0, dn);
-                st4(Ts + (pb * ST_TR + rg * C::RT + a) * C::LDZ + c0, zl);
+                st4(dNs + (pb * ST_TR + rg * C::RT + a) * C::LDB + c0, dn);
+                st4(Ts + (pb * ST_TR + rg * C::RT + a) * C::LDB + c0, zl);
 #pragma unroll
                 for (int o = C::CG / 2; o > 0; o >>= 1) drp += __shfl_xor_sync(0xffffffffu, drp, o);
                 if (cg == 0 && i < n) drs[i] += drp;
             }
         }
         __syncthreads();
-        // (c) dA rows += dN_l Z_l^T (+ dr at the last processed sub-layer)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+        // (c) dA rows += dN_l Z_l^T (+ dr at the last processed sub-layer): 64 x 64 blocks on the tensor cores,
+        //     warp (mt, ng) owns rows 16 mt .. + 15 and columns 32 ng .. + 31 of a block
         {
-            const int ig = threadIdx.x >> 4, jg = threadIdx.x & 15;
+            const int mt = warp >> 1, ng = warp & 1;
             for (int pb = 0; pb < ntiles; ++pb) {
                 for (int jp = 0; jp < ntiles; ++jp) {
-                    float acc[4][4];
+                    float c[4][4];
+                    zero_frag<4>(c);
+                    warp_gemm<4, true>(c, GD / 8, dNs + (pb * ST_TR + 16 * mt) * C::LDB, C::LDB,
+                                       Ts + (jp * ST_TR + 32 * ng) * C::LDB, C::LDB);
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[a][q] = 0.f;
-                    const float* dn0 = dNs + (pb * ST_TR + ig * 4) * C::LDZ;
-                    const float* z0 = Ts + (jp * ST_TR + jg) * C::LDZ;
-#pragma unroll 4
-                    for (int c = 0; c < GD; c += 4) {
-                        float4 dn[4], zz[4];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) dn[a] = ld4(dn0 + a * C::LDZ + c);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) zz[q] = ld4(z0 + q * 16 * C::LDZ + c);
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) acc[a][q] += dot4(dn[a], zz[q]);
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const int i = pb * ST_TR + ig * 4 + a;
+                    for (int half = 0; half < 2; ++half) {
+                        const int i = pb * ST_TR + 16 * mt + g + 8 * half;
                         if (i >= n) continue;
                         const float dr = (l == 0) ? drs[i] : 0.f;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int j = jp * ST_TR + jg + 16 * q;
-                            if (j >= n) continue;
-                            float* p = dAb + static_cast<size_t>(i) * n + j;
-                            float val = acc[a][q] + dr;
-                            if (l != layers - 1) val += *p;
-                            *p = val;
+                        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int j = jp * ST_TR + 32 * ng + 8 * nt + 2 * t + e;
+                                if (j >= n) continue;
+                                float* p = dAb + static_cast<size_t>(i) * n + j;
+                                float val = c[nt][2 * half + e] + dr;
+                                if (l != layers - 1) val += *p;
+                                *p = val;
+                            }
                         }
                     }
                 }
             }
         }
         __syncthreads();
-        // (b) dZ_l = A^T dN_l, accumulated over attention tiles into Ts (Z_l is no longer needed)
-        for (int t = threadIdx.x; t < npad * C::LDZ; t += ST_THREADS) Ts[t] = 0.f;
+        // (b) dZ_l = A^T dN_l, accumulated over attention tiles into Ts (Z_l is no longer needed): per tile,
+        //     C[j][c] += sum_ii AsT[j][ii] dN[tile row ii][c]; unit u = (row tile of j, column group) stays with
+        //     one warp over all tiles, so the read-modify-write of Ts needs no extra barrier
+        for (int idx = threadIdx.x; idx < npad * C::LDB; idx += ST_THREADS) Ts[idx] = 0.f;
         for (int pb = 0; pb < ntiles; ++pb) {
             __syncthreads();
-            load_att_tile(As, lda, Ab, n, pb * ST_TR);
+            load_att_tile_t(AsT, LDT, Ab, n, pb * ST_TR, np16);
             __syncthreads();
-            for (int jp = 0; jp < ntiles; ++jp) {
-                float4 acc[C::RT];
+            for (int u = warp; u < (np16 / 16) * 2; u += ST_THREADS / WARP) {
+                const int mt = u >> 1, ng = u & 1;
+                float* tc = Ts + (16 * mt) * C::LDB + 8 * C::NT * ng;
+                float c[C::NT][4];
 #pragma unroll
-                for (int a = 0; a < C::RT; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int j0 = jp * ST_TR + rg * C::RT;
-                if (j0 < n) {
-                    for (int ii = 0; ii < ST_TR; ++ii) {
-                        const float4 dn = ld4(dNs + (pb * ST_TR + ii) * C::LDZ + c0);
-#pragma unroll
-                        for (int a = 0; a < C::RT; ++a)
-                            fma4(acc[a], As[ii * lda + min(j0 + a, n - 1)], dn);
-                    }
+                for (int nt = 0; nt < C::NT; ++nt) {
+                    const float2 lo = *reinterpret_cast<const float2*>(tc + g * C::LDB + 8 * nt + 2 * t);
+                    const float2 hi = *reinterpret_cast<const float2*>(tc + (g + 8) * C::LDB + 8 * nt + 2 * t);
+                    c[nt][0] = lo.x; c[nt][1] = lo.y; c[nt][2] = hi.x; c[nt][3] = hi.y;
                 }
+                warp_gemm<C::NT, false>(c, ST_TR / 8, AsT + (16 * mt) * LDT, LDT,
+                                        dNs + (pb * ST_TR) * C::LDB + 8 * C::NT * ng, C::LDB);
 #pragma unroll
-                for (int a = 0; a < C::RT; ++a) {
-                    if (j0 + a < n) {
-                        float* p = Ts + (j0 + a) * C::LDZ + c0;
-                        float4 cur = ld4(p);
-                        cur.x += acc[a].x; cur.y += acc[a].y; cur.z += acc[a].z; cur.w += acc[a].w;
-                        st4(p, cur);
-                    }
+                for (int nt = 0; nt < C::NT; ++nt) {
+                    *reinterpret_cast<float2*>(tc + g * C::LDB + 8 * nt + 2 * t) = make_float2(c[nt][0], c[nt][1]);
+                    *reinterpret_cast<float2*>(tc + (g + 8) * C::LDB + 8 * nt + 2 * t) = make_float2(c[nt][2], c[nt][3]);
                 }
             }
         }
@@ -350,18 +356,18 @@ gcn_stack_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restri
             for (int a = 0; a < C::RT; ++a) {
                 const int j = jp * ST_TR + rg * C::RT + a;
                 if (j < n)
-                    st4(dZ + static_cast<size_t>(node0 + j) * HD + col, ld4(Ts + j * C::LDZ + c0));
+                    st4(dZ + static_cast<size_t>(node0 + j) * HD + col, ld4(Ts + j * C::LDB + c0));
             }
             for (int m = 0; m < l; ++m) {
                 float4 acc[C::RT];
 #pragma unroll
                 for (int a = 0; a < C::RT; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* wt = WT + static_cast<size_t>(m) * GD * GD + c0;
-                const float* trow = Ts + (jp * ST_TR + rg * C::RT) * C::LDZ;
+                const float* trow = Ts + (jp * ST_TR + rg * C::RT) * C::LDB;
                 for (int c = 0; c < GD; ++c) {
                     const float4 w = ld4(wt + c * GD);
 #pragma unroll
-                    for (int a = 0; a < C::RT; ++a) fma4(acc[a], trow[a * C::LDZ + c], w);
+                    for (int a = 0; a < C::RT; ++a) fma4(acc[a], trow[a * C::LDB + c], w);
                 }
 #pragma unroll
                 for (int a = 0; a < C::RT; ++a) {
@@ -386,14 +392,14 @@ gcn_stack_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restri
 static size_t stack_fwd_smem(int n, int layers, int gd) {
     int npad = ((n + ST_TR - 1) / ST_TR) * ST_TR;
     int ki = (layers - 1) * gd;
-    size_t fl = static_cast<size_t>(npad) * (gd + 4) + static_cast<size_t>(n) * (ki + 1) +
-                static_cast<size_t>(ST_TR) * (n | 1) + 4 + static_cast<size_t>(ki) * gd + n;
+    size_t fl = static_cast<size_t>(npad) * (gd + 8) + static_cast<size_t>(n) * (ki + 1) +
+                static_cast<size_t>(ST_TR) * (((n + 7) & ~7) + 4) + 4 + static_cast<size_t>(ki) * gd + n;
     return fl * sizeof(float);
 }
 static size_t stack_bwd_smem(int n, int layers, int gd) {
     int npad = ((n + ST_TR - 1) / ST_TR) * ST_TR;
     size_t fl = 2 * static_cast<size_t>(npad) * (gd + 4) + static_cast<size_t>(layers - 1) * gd * gd +
-                static_cast<size_t>(ST_TR) * (n | 1) + 2 * static_cast<size_t>(n);
+                static_cast<size_t>((n + 15) & ~15) * (ST_TR + 4) + 2 * static_cast<size_t>(n);
     return fl * sizeof(float);
 }
 
