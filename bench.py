@@ -19,6 +19,14 @@ events recorded by the library on the launching stream during the timed region) 
 path (`path_*`: SURVEY section 8d algorithmic bytes per document / step time).  `cpu_baseline` is
 the oracle (CPU restatement of the reference, pinned bit-exact to it) timed on this box's cores.
 
+`aux` holds the separately timed mention->entity pooling and classifier-side pair gathers (own
+bytes, own roofline fraction).
+
+    python bench.py --train-docs 100000 [--micro K]     (torchrun for N > 1)
+times BASELINE.json configs[4] instead: one pass of doc-sharded training over 100 000 synthetic documents
+(forward+backward per micro-batch, ONE NCCL all-reduce of the flat gradient bucket, ONE fused Adam kernel per
+optimiser step; strong scaling), see run_training_arm.
+
 --impl reference times that same CPU oracle as its own arm (the reference is PyTorch code that
 cannot travel to the GPU box; oracle/gcgcn_oracle.py issues the same ATen ops).
 """
@@ -62,7 +70,7 @@ def parse():
                     "(100000 in BASELINE.json), sharded by micro-batch over the ranks, one fused Adam step per "
                     "micro-batch per rank after one NCCL all-reduce of the flat gradient bucket; --steps is ignored "
                     "(the timed region is the whole pass over the documents)")
-    ap.add_argument("--micro", type=int, default=6240, help="documents per micro-batch per rank with --train-docs")
+    ap.add_argument("--micro", type=int, default=6252, help="documents per micro-batch per rank with --train-docs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the separate pooling / pair-gather timings")

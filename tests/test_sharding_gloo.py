@@ -14,7 +14,7 @@ from helpers import PREFIXES, blocks_state, oracle_blocks, sub
 from gcgcn_b200 import synthetic as S
 from gcgcn_b200.batch import shard_documents
 from gcgcn_b200.modules import GraphBlocks
-from gcgcn_b200.sharding import GradBucket, all_reduce_gradients, local_documents
+from gcgcn_b200.sharding import FlatTrainer, GradBucket, all_reduce_gradients, local_documents
 
 DOC_IDS = [2, 5, 8, 9, 10, 11]        # n = 28, 19, 14, 11, 8, 5
 LAYERS, HEADS = 2, 8
@@ -90,3 +90,37 @@ def test_bucket_is_one_contiguous_message():
     bucket.flat.mul_(2)
     bucket.unpack()
     assert all(float(p.grad.mean()) == 2.0 for p in gb.parameters())
+
+
+def _trainer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    gb, state = blocks_state(LAYERS, HEADS)
+    tr = FlatTrainer(gb)
+    tr.zero_grad()
+    # this rank's oracle gradients, accumulated the way autograd does it: in place into the pre-existing .grad views
+    for i in [DOC_IDS[k] for k in local_documents([S.DOC_N[i % 12] for i in DOC_IDS], rank, world)]:
+        r = oracle_blocks(S.make_doc(i), state, LAYERS, HEADS)
+        for name, p in gb.named_parameters():
+            g = r["dparams"].get(name)
+            if g is not None and p.grad is not None:
+                p.grad.add_(g)
+    tr.all_reduce()                       # config 5's only collective: one message, no pack / unpack copies
+    torch.save({"flat": tr.flat.clone(), "names": tr.names, "offsets": tr.offsets, "sizes": tr.sizes},
+               os.path.join(out_dir, f"trainer{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_trainer_bucket_all_reduce_two_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    gb, state = blocks_state(LAYERS, HEADS)
+    _local_grads(gb, state, DOC_IDS)
+    got = [torch.load(tmp_path / f"trainer{r}.pt") for r in range(2)]
+    assert torch.equal(got[0]["flat"], got[1]["flat"])
+    assert all("linears_k" not in n for n in got[0]["names"])
+    want = dict(gb.named_parameters())
+    for n, o, sz in zip(got[0]["names"], got[0]["offsets"], got[0]["sizes"]):
+        assert torch.allclose(got[0]["flat"][o:o + sz].view_as(want[n]), want[n].grad, rtol=1e-5, atol=1e-5), n
