@@ -119,6 +119,43 @@ def cpu_oracle_rate(variant: str, seconds: float, max_passes: int = 1000, warmup
                                        f"fwd+bwd, one document at a time, median pass {med * 1e3:.1f} ms"}
 
 
+def cuda_oracle_rate(variant: str, dev, passes: int = 5):
+    """the reference's own PyTorch path on the B200 itself -- the oracle's ATen ops (the same
+    calls the reference modules make, pinned bit-exact to them) issued eagerly on `dev`, documents one at a time
+    like the reference trainer (C:339), fwd+bwd, inputs resident on the device, CUDA_LAUNCH_BLOCKING unset.
+    A reported baseline (about 1000 library launches per document), not a path of this package."""
+    import torch
+    from helpers import blocks_state, oracle_blocks
+    from gcgcn_b200 import synthetic
+    import copy
+
+    layers, heads = VARIANTS[variant]
+    _, state = blocks_state(layers, heads)
+    state = {k: v.to(dev) for k, v in state.items()}
+    docs = []
+    for d in synthetic.make_batch():
+        d = copy.copy(d)
+        d.x0, d.e0, d.e1, d.adj = d.x0.to(dev), d.e0.to(dev), d.e1.to(dev), d.adj.to(dev)
+        docs.append(d)
+
+    def one_pass():
+        for d in docs:
+            oracle_blocks(d, state, layers, heads, device=dev)
+
+    one_pass()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(passes):
+        one_pass()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    sec = ev0.elapsed_time(ev1) * 1e-3 / passes
+    return {"value": len(docs) / sec, "unit": UNIT, "kind": "port on cuda (eager ATen ops of the reference modules)",
+            "sample": f"{passes} passes over the 12-document batch, fwd+bwd, one document at a time, "
+                      f"{sec * 1e3:.1f} ms per pass (CUDA events)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -581,7 +618,7 @@ def run_gpu_arm(args):
     if not args.no_cpu_baseline:
         rate, info = cpu_oracle_rate(args.variant, args.cpu_seconds)
         cpu = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"],
-               "host_cpus": info["host_cpus"]}
+               "host_cpus": info["host_cpus"], "reference_eager_cuda": cuda_oracle_rate(args.variant, dev)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

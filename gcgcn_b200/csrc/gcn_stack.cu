@@ -423,6 +423,15 @@ int launch_stack_bwd_mma(const gcgcn_batch* bt, int heads, int layers, int slab,
                          const float* Z, const float* G, const float* Winner, const float* keep, const float* dF,
                          float* dZ, float* dE, float* dA, cudaStream_t st);
 
+// row-tiled tensor-core versions for 65 <= max n <= 256, gcn_stack_tiled.cu
+bool stack_tiled_usable(const gcgcn_batch* bt, int layers, int slab);
+int launch_stack_fwd_tiled(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                           float* Z, const float* E, const float* Winner, const float* keep, const float* x,
+                           float* G, float* F, cudaStream_t st);
+int launch_stack_bwd_tiled(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                           const float* Z, const float* G, const float* Winner, const float* keep, const float* dF,
+                           float* dZ, float* dE, float* dA, cudaStream_t st);
+
 bool block_kernels_usable(const gcgcn_batch* bt, int heads, int layers, int slab, bool mha);
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
@@ -445,6 +454,8 @@ int launch_stack_fwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
         return launch_block_fwd(bt, heads, layers, A, nullptr, nullptr, Z, E, Winner, x, G, F, frag_ws, BlockDrop{}, st);
     if (stack_mma_usable(bt, layers, slab))
         return launch_stack_fwd_mma(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, F, st);
+    if (stack_tiled_usable(bt, layers, slab))
+        return launch_stack_fwd_tiled(bt, heads, layers, slab, flags, A, Z, E, Winner, keep, x, G, F, st);
     if (layers < 1 || slab % layers != 0)
         return fail(GCGCN_ERR_UNSUPPORTED, "layer_num %d must divide the output width %d", layers, slab);
     const int gd = slab / layers;
@@ -481,6 +492,8 @@ int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
                                 BlockDrop{}, st);
     if (stack_mma_usable(bt, layers, slab))
         return launch_stack_bwd_mma(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, dA, st);
+    if (stack_tiled_usable(bt, layers, slab))
+        return launch_stack_bwd_tiled(bt, heads, layers, slab, flags, A, Z, G, Winner, keep, dF, dZ, dE, dA, st);
     if (layers < 1 || slab % layers != 0)
         return fail(GCGCN_ERR_UNSUPPORTED, "layer_num %d must divide the output width %d", layers, slab);
     const int gd = slab / layers;

@@ -1,0 +1,448 @@
+// Dense-connected GraphConv stack for LARGE graphs (65..256 entities: BASELINE.json configs[3], the
+// 128 / 256-entity sweep): one CTA per (document, head, 32-row tile) and one launch per sub-layer.
+//
+// Same contract and math as gcn_stack.cu (G:36-50 inside G:67-76 / G:103-113).  That kernel gives one CTA a
+// whole (document, head): at n = 256 it owns 220 KB of shared memory, so one CTA of eight warps per SM walks
+// load -> barrier -> product -> barrier phases with nothing to overlap them, and a batch offers only
+// documents x heads CTAs (44 for the one-head CAGGC block of the 256-entity point).  Here the rows of the
+// n x n attention map are cut into 32-row tiles:
+//   forward, launch l:   G_l[tile] = relu((E_l + A[tile,:] Z_l) / r),  F_l[tile],  then the row-local dense
+//                        connection  Z_{l+1}[tile] = Zx_{l+1}[tile] + g_{<=l}[tile] Winner_{l+1}
+//   backward, launch "rows" l:  dN_l[tile] (= dE_l), dr, and  dA[tile,:] (+)= dN_l[tile] Z_l^T
+//   backward, launch "cols" l:  dZ_l[tile] = A[:,tile]^T dN_l,  then the row-local push-down into dZ slabs m < l
+// The cross-row dependencies (every row tile needs all rows of Z_l, every column tile all rows of dN_l) are
+// carried by the kernel boundaries; each CTA keeps one [n, g] operand (<= 74 KB) and one 32-row tile
+// (<= 33 KB) in shared memory, so two CTAs share an SM and 4-8x more of them are in flight.
+// All products run on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split of mma_tf32.cuh: fp32 parity).
+#include "common.cuh"
+#include "mma_tf32.cuh"
+
+namespace gcgcn {
+
+constexpr int TL_THREADS = 256;
+constexpr int TL_WARPS = TL_THREADS / WARP;
+constexpr int TL_ROWS = 32;     // rows of the attention map per CTA
+
+template <int GD>
+struct TileCfg {
+    static constexpr int LDZ = GD + 8;      // [k][n] operands (B fragments): stride == 8 (mod 32)
+    static constexpr int LDB = GD + 4;      // [m][k] / [n][k] operands (A and B^T fragments): stride == 4 (mod 8)
+    static constexpr int NT = GD / 32;      // 8-column tiles per warp: 2 row tiles x 4 column groups of GD / 4
+    static constexpr int CG = GD / 4;       // float4 column groups of a slab
+};
+
+__device__ __forceinline__ float4 tl_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// forward, sub-layer l
+template <int GD>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+stack_tile_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                      const float* __restrict__ A, float* __restrict__ Z, const float* __restrict__ E,
+                      const float* __restrict__ Winner, const float* __restrict__ keep, const float* __restrict__ x,
+                      float* __restrict__ G, float* __restrict__ F, int l, int layers, int heads, int flags,
+                      long long total_pairs) {
+    using C = TileCfg<GD>;
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * TL_ROWS;
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    if (row0 >= n) return;
+    const int S = layers * GD, HD = heads * S;
+    const int k8 = (n + 7) & ~7, lda = k8 + 4;
+    const int kin = (l + 1) * GD, ldg = kin + 4;            // dense-connect inputs of sub-layer l + 1
+    const int tile_floats = max(TL_ROWS * lda, TL_ROWS * (S + 4));
+
+    float* Zl = smem;                                       // [k8][LDZ]   Z_l, all rows of the document
+    float* As = Zl + static_cast<size_t>(k8) * C::LDZ;      // [32][lda]   attention rows of the tile; later g_{<=l}
+    float* rs = As + tile_floats;                           // [32]        row normalisers
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const float* Ab = A + static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+    const bool relu = flags & GCGCN_STACK_RELU, resid = flags & GCGCN_STACK_RESIDUAL;
+
+    for (int idx = tid; idx < k8 * C::CG; idx += TL_THREADS) {
+        const int i = idx / C::CG, c4 = (idx - i * C::CG) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) v = tl_ld4(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4);
+        *reinterpret_cast<float4*>(Zl + i * C::LDZ + c4) = v;
+    }
+    for (int idx = tid; idx < TL_ROWS * k8; idx += TL_THREADS) {
+        const int ii = idx / k8, j = idx - ii * k8;
+        As[ii * lda + j] = (row0 + ii < n && j < n) ? Ab[static_cast<size_t>(row0 + ii) * n + j] : 0.f;
+    }
+    __syncthreads();
+    for (int ii = warp; ii < TL_ROWS; ii += TL_WARPS) {     // r_i = rowsum + [rowsum == 0]   (G:47-49)
+        float s = 0.f;
+        for (int j = lane; j < k8; j += WARP) s += As[ii * lda + j];
+        s = warp_sum(s);
+        if (lane == 0) rs[ii] = s + (s == 0.f ? 1.f : 0.f);
+    }
+    __syncthreads();
+
+    // out = (E + A Z_l) / r : warp (mt, ng) owns rows 16 mt .. + 15 and columns ng GD/4 .. + GD/4 - 1
+    const int mt = warp >> 2, ng = warp & 3;
+    float c[C::NT][4];
+    zero_frag<C::NT>(c);
+    warp_gemm<C::NT, false>(c, k8 / 8, As + (16 * mt) * lda, lda, Zl + 8 * C::NT * ng, C::LDZ);
+    float2 o[2][C::NT];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int ii = 16 * mt + g + 8 * half, i = row0 + ii;
+        const float r = rs[ii];
+#pragma unroll
+        for (int nt = 0; nt < C::NT; ++nt) {
+            o[half][nt] = make_float2(0.f, 0.f);
+            if (i >= n) continue;
+            const int cw = 8 * C::NT * ng + 8 * nt + 2 * t;
+            const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + cw;
+            const float2 e2 = ld2g(E + off);
+            float2 v;
+            v.x = (e2.x + c[nt][2 * half]) / r;
+            v.y = (e2.y + c[nt][2 * half + 1]) / r;
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+            *reinterpret_cast<float2*>(G + off) = v;
+            o[half][nt] = v;
+            float2 f = v;
+            if (keep != nullptr) { const float2 k2 = ld2g(keep + off); f.x *= k2.x; f.y *= k2.y; }
+            if (resid) {
+                const float2 x2 = ld2g(x + static_cast<size_t>(node0 + i) * S + l * GD + cw);
+                f.x += x2.x; f.y += x2.y;
+            }
+            *reinterpret_cast<float2*>(F + off) = f;
+        }
+    }
+    if (l + 1 >= layers) return;
+
+    // dense connection of the next sub-layer for the rows of this tile (row-local, G:72-73):
+    //   Z_{l+1}[tile] = Zx_{l+1}[tile] + [g_0 .. g_l][tile] Winner_{l+1}[0 : (l+1) GD]
+    __syncthreads();                                        // every warp is done with the attention rows
+    float* Gt = As;                                         // [32][ldg]
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int ii = 16 * mt + g + 8 * half;
+#pragma unroll
+        for (int nt = 0; nt < C::NT; ++nt) {
+            const int cw = 8 * C::NT * ng + 8 * nt + 2 * t;
+            *reinterpret_cast<float2*>(Gt + ii * ldg + l * GD + cw) = o[half][nt];
+        }
+    }
+    for (int idx = tid; idx < TL_ROWS * l * C::CG; idx += TL_THREADS) {     // g_m, m < l, from earlier launches
+        const int ii = idx / (l * C::CG), c4 = (idx - ii * (l * C::CG)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + ii < n) v = tl_ld4(G + static_cast<size_t>(node0 + row0 + ii) * HD + static_cast<size_t>(h) * S + c4);
+        *reinterpret_cast<float4*>(Gt + ii * ldg + c4) = v;
+    }
+    __syncthreads();
+    const size_t nextbase = static_cast<size_t>(h) * S + (l + 1) * GD;
+    const float* wsrc = Winner + (static_cast<size_t>(h) * layers + (l + 1)) * S * GD;
+#pragma unroll
+    for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = row0 + 16 * mt + g + 8 * half;
+            float2 v = make_float2(0.f, 0.f);
+            if (i < n) v = ld2g(Z + static_cast<size_t>(node0 + i) * HD + nextbase + 8 * C::NT * ng + 8 * nt + 2 * t);
+            c[nt][2 * half] = v.x;
+            c[nt][2 * half + 1] = v.y;
+        }
+    warp_gemm<C::NT, false>(c, kin / 8, Gt + (16 * mt) * ldg, ldg, wsrc + 8 * C::NT * ng, GD);
+#pragma unroll
+    for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = row0 + 16 * mt + g + 8 * half;
+            if (i >= n) continue;
+            *reinterpret_cast<float2*>(Z + static_cast<size_t>(node0 + i) * HD + nextbase + 8 * C::NT * ng + 8 * nt + 2 * t) =
+                make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward "rows", sub-layer l: dN_l (= dE_l) and dr for the rows of the tile, dA[tile, :] (+)= dN_l Z_l^T
+template <int GD>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                           const float* __restrict__ A, const float* __restrict__ Z, const float* __restrict__ G,
+                           const float* __restrict__ keep, const float* __restrict__ dF,
+                           const float* __restrict__ dZ, float* __restrict__ dE, float* __restrict__ dA, int l,
+                           int layers, int heads, int flags, long long total_pairs) {
+    using C = TileCfg<GD>;
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * TL_ROWS;
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    if (row0 >= n) return;
+    const int S = layers * GD, HD = heads * S;
+    const int n64 = (n + 63) & ~63;
+
+    float* Ts = smem;                                        // [n64][LDB]  Z_l, all rows (B^T operand)
+    float* dNs = Ts + static_cast<size_t>(n64) * C::LDB;     // [32][LDB]   dN_l of the tile
+    float* rs = dNs + TL_ROWS * C::LDB;                      // [32]
+    float* drs = rs + TL_ROWS;                               // [32]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const float* Ab = A + abase;
+    float* dAb = dA + abase;
+    const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+    const bool relu = flags & GCGCN_STACK_RELU;
+
+    for (int ii = warp; ii < TL_ROWS; ii += TL_WARPS) {      // row normalisers straight from global memory
+        float s = 0.f;
+        if (row0 + ii < n)
+            for (int j = lane; j < n; j += WARP) s += Ab[static_cast<size_t>(row0 + ii) * n + j];
+        s = warp_sum(s);
+        if (lane == 0) { rs[ii] = s + (s == 0.f ? 1.f : 0.f); drs[ii] = 0.f; }
+    }
+    for (int idx = tid; idx < n64 * C::CG; idx += TL_THREADS) {
+        const int i = idx / C::CG, c4 = (idx - i * C::CG) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) v = tl_ld4(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4);
+        *reinterpret_cast<float4*>(Ts + i * C::LDB + c4) = v;
+    }
+    __syncthreads();
+
+    // (a) row-local: dG_l -> dOut -> dN_l (shared + dE), dr.  CG threads per row; a warp covers 32 / CG rows.
+    //     At l == 0 the dr shares of the sub-layers above (their dN = dE and g are final) are folded in.
+    constexpr int RPP = TL_THREADS / C::CG;
+    const int cg = tid % C::CG, rg = tid / C::CG, c0 = cg * 4;
+    for (int ii = rg; ii < TL_ROWS; ii += RPP) {
+        const int i = row0 + ii;
+        float4 dn = make_float4(0.f, 0.f, 0.f, 0.f);
+        float drp = 0.f;
+        if (i < n) {
+            const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + c0;
+            float4 dg = tl_ld4(dF + off);
+            if (keep != nullptr) {
+                const float4 k4 = tl_ld4(keep + off);
+                dg.x *= k4.x; dg.y *= k4.y; dg.z *= k4.z; dg.w *= k4.w;
+            }
+            if (l < layers - 1) {
+                const float4 s4 = tl_ld4(dZ + off);          // what the sub-layers above pushed down to g_l
+                dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
+            }
+            const float4 g4 = tl_ld4(G + off);
+            if (relu) {
+                dg.x = g4.x > 0.f ? dg.x : 0.f; dg.y = g4.y > 0.f ? dg.y : 0.f;
+                dg.z = g4.z > 0.f ? dg.z : 0.f; dg.w = g4.w > 0.f ? dg.w : 0.f;
+            }
+            const float r = rs[ii];
+            dn.x = dg.x / r; dn.y = dg.y / r; dn.z = dg.z / r; dn.w = dg.w / r;
+            *reinterpret_cast<float4*>(dE + off) = dn;
+            drp = -(dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
+            if (l == 0) {
+                for (int m = 1; m < layers; ++m) {
+                    const size_t om = static_cast<size_t>(node0 + i) * HD + static_cast<size_t>(h) * S + m * GD + c0;
+                    const float4 dm = tl_ld4(dE + om), gm = tl_ld4(G + om);
+                    drp -= dm.x * gm.x + dm.y * gm.y + dm.z * gm.z + dm.w * gm.w;
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(dNs + ii * C::LDB + c0) = dn;
+#pragma unroll
+        for (int s = C::CG / 2; s > 0; s >>= 1) drp += __shfl_xor_sync(0xffffffffu, drp, s);
+        if (cg == 0) drs[ii] = drp;
+    }
+    __syncthreads();
+
+    // (c) dA[tile, :] (+)= dN_l Z_l^T (+ dr at l == 0), 64 columns per trip: warp (mt, ng) owns rows 16 mt .. + 15
+    //     and columns 16 ng .. + 15 of the trip
+    const int mt = warp & 1, ng = warp >> 1;
+    for (int jp = 0; jp < n64; jp += 64) {
+        float c[2][4];
+        zero_frag<2>(c);
+        warp_gemm<2, true>(c, GD / 8, dNs + (16 * mt) * C::LDB, C::LDB, Ts + (jp + 16 * ng) * C::LDB, C::LDB);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int ii = 16 * mt + g + 8 * half, i = row0 + ii;
+            if (i >= n) continue;
+            const float dr = (l == 0) ? drs[ii] : 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = jp + 16 * ng + 8 * nt + 2 * t + e;
+                    if (j >= n) continue;
+                    float* p = dAb + static_cast<size_t>(i) * n + j;
+                    float val = c[nt][2 * half + e] + dr;
+                    if (l != layers - 1) val += *p;
+                    *p = val;
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward "cols", sub-layer l: dZ_l[tile] = A[:, tile]^T dN_l, then the dense-connect push-down of those rows
+template <int GD>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                           const float* __restrict__ A, const float* __restrict__ Winner,
+                           const float* __restrict__ dE, float* __restrict__ dZ, int l, int layers, int heads,
+                           long long total_pairs) {
+    using C = TileCfg<GD>;
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * TL_ROWS;
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    if (j0 >= n) return;
+    const int S = layers * GD, HD = heads * S;
+    const int k8 = (n + 7) & ~7, ldt = k8 + 4;
+
+    float* dNs = smem;                                       // [k8][LDZ]   dN_l, all rows (B operand)
+    float* AsT = dNs + static_cast<size_t>(k8) * C::LDZ;     // [32][ldt]   AsT[jj][i] = A[i][j0 + jj]
+    float* Tt = AsT;                                         // [32][LDB]   dZ_l of the tile (push-down A operand),
+                                                             //             over the attention tile once it is consumed
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const float* Ab = A + static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+
+    for (int idx = tid; idx < k8 * C::CG; idx += TL_THREADS) {
+        const int i = idx / C::CG, c4 = (idx - i * C::CG) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) v = tl_ld4(dE + static_cast<size_t>(node0 + i) * HD + colbase + c4);
+        *reinterpret_cast<float4*>(dNs + i * C::LDZ + c4) = v;
+    }
+    for (int idx = tid; idx < TL_ROWS * k8; idx += TL_THREADS) {       // lanes along j: 128-byte global reads
+        const int i = idx / TL_ROWS, jj = idx - i * TL_ROWS;
+        AsT[jj * ldt + i] = (i < n && j0 + jj < n) ? Ab[static_cast<size_t>(i) * n + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+
+    const int mt = warp >> 2, ng = warp & 3;
+    float c[C::NT][4];
+    zero_frag<C::NT>(c);
+    warp_gemm<C::NT, false>(c, k8 / 8, AsT + (16 * mt) * ldt, ldt, dNs + 8 * C::NT * ng, C::LDZ);
+    __syncthreads();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int jj = 16 * mt + g + 8 * half, j = j0 + jj;
+#pragma unroll
+        for (int nt = 0; nt < C::NT; ++nt) {
+            const int cw = 8 * C::NT * ng + 8 * nt + 2 * t;
+            const float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+            *reinterpret_cast<float2*>(Tt + jj * C::LDB + cw) = v;
+            if (j < n) *reinterpret_cast<float2*>(dZ + static_cast<size_t>(node0 + j) * HD + colbase + cw) = v;
+        }
+    }
+    if (l == 0) return;
+    __syncthreads();
+    // dG_m[j][c'] (+)= sum_c dZ_l[j][c] Wn_l[128 + m GD + c'][c]  for m < l  (the slab of dZ that sub-layer m reads)
+    const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
+    for (int m = 0; m < l; ++m) {
+        zero_frag<C::NT>(c);
+        warp_gemm<C::NT, true>(c, GD / 8, Tt + (16 * mt) * C::LDB, C::LDB,
+                               wsrc + (static_cast<size_t>(m) * GD + 8 * C::NT * ng) * GD, GD);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int j = j0 + 16 * mt + g + 8 * half;
+            if (j >= n) continue;
+#pragma unroll
+            for (int nt = 0; nt < C::NT; ++nt) {
+                float* p = dZ + static_cast<size_t>(node0 + j) * HD + static_cast<size_t>(h) * S + m * GD +
+                           8 * C::NT * ng + 8 * nt + 2 * t;
+                float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
+                if (l != layers - 1) {
+                    const float2 cur = *reinterpret_cast<const float2*>(p);
+                    v.x += cur.x; v.y += cur.y;
+                }
+                *reinterpret_cast<float2*>(p) = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static size_t tile_fwd_smem(int n, int layers, int gd) {
+    const int k8 = (n + 7) & ~7, s = layers * gd;
+    const size_t tile = static_cast<size_t>(TL_ROWS) * std::max(k8 + 4, s + 4);
+    return (static_cast<size_t>(k8) * (gd + 8) + tile + TL_ROWS) * sizeof(float);
+}
+static size_t tile_rows_smem(int n, int gd) {
+    const int n64 = (n + 63) & ~63;
+    return (static_cast<size_t>(n64 + TL_ROWS) * (gd + 4) + 2 * TL_ROWS) * sizeof(float);
+}
+static size_t tile_cols_smem(int n, int gd) {
+    const int k8 = (n + 7) & ~7;
+    return (static_cast<size_t>(k8) * (gd + 8) + static_cast<size_t>(TL_ROWS) * std::max(k8 + 4, gd + 4)) * sizeof(float);
+}
+
+// graphs of 65 .. 256 entities with sub-layer width 32 or 64 (GCGCN_STACK=simt keeps gcn_stack.cu)
+bool stack_tiled_usable(const gcgcn_batch* bt, int layers, int slab) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("GCGCN_STACK");
+        enabled = (e != nullptr && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+    }
+    if (!enabled || layers < 1 || slab % layers != 0) return false;
+    const int gd = slab / layers;
+    return bt->max_nodes > 64 && bt->max_nodes <= 256 && bt->num_docs <= 65535 && (gd == 32 || gd == 64);
+}
+
+template <typename K>
+static int tile_smem_attr(K kernel, size_t bytes, const char* name) {
+    if (bytes > 227 * 1024) return fail(GCGCN_ERR_UNSUPPORTED, "%s: %zu bytes of shared memory (> 227 KB)", name, bytes);
+    if (bytes > 48 * 1024)
+        return cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(bytes)), name);
+    return GCGCN_OK;
+}
+
+int launch_stack_fwd_tiled(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                           float* Z, const float* E, const float* Winner, const float* keep, const float* x,
+                           float* G, float* F, cudaStream_t st) {
+    const int gd = slab / layers, nmax = bt->max_nodes;
+    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
+    const dim3 grid(ceil_div(nmax, TL_ROWS), heads, bt->num_docs);
+    const size_t smem = tile_fwd_smem(nmax, layers, gd);
+    if (gd == 64) GCGCN_TRY(tile_smem_attr(stack_tile_fwd_kernel<64>, smem, "stack_tile_fwd"));
+    else GCGCN_TRY(tile_smem_attr(stack_tile_fwd_kernel<32>, smem, "stack_tile_fwd"));
+    for (int l = 0; l < layers; ++l) {
+        if (gd == 64)
+            stack_tile_fwd_kernel<64><<<grid, TL_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F, l,
+                                                                     layers, heads, flags, bt->total_pairs);
+        else
+            stack_tile_fwd_kernel<32><<<grid, TL_THREADS, smem, st>>>(bt->node_ptr, pp, A, Z, E, Winner, keep, x, G, F, l,
+                                                                     layers, heads, flags, bt->total_pairs);
+        GCGCN_CHECK_LAUNCH("gcn_stack_tile_fwd");
+    }
+    return GCGCN_OK;
+}
+
+int launch_stack_bwd_tiled(const gcgcn_batch* bt, int heads, int layers, int slab, int flags, const float* A,
+                           const float* Z, const float* G, const float* Winner, const float* keep, const float* dF,
+                           float* dZ, float* dE, float* dA, cudaStream_t st) {
+    const int gd = slab / layers, nmax = bt->max_nodes;
+    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
+    const dim3 grid(ceil_div(nmax, TL_ROWS), heads, bt->num_docs);
+    const size_t smem_r = tile_rows_smem(nmax, gd), smem_c = tile_cols_smem(nmax, gd);
+    if (gd == 64) {
+        GCGCN_TRY(tile_smem_attr(stack_tile_bwd_rows_kernel<64>, smem_r, "stack_tile_bwd_rows"));
+        GCGCN_TRY(tile_smem_attr(stack_tile_bwd_cols_kernel<64>, smem_c, "stack_tile_bwd_cols"));
+    } else {
+        GCGCN_TRY(tile_smem_attr(stack_tile_bwd_rows_kernel<32>, smem_r, "stack_tile_bwd_rows"));
+        GCGCN_TRY(tile_smem_attr(stack_tile_bwd_cols_kernel<32>, smem_c, "stack_tile_bwd_cols"));
+    }
+    for (int l = layers - 1; l >= 0; --l) {
+        if (gd == 64)
+            stack_tile_bwd_rows_kernel<64><<<grid, TL_THREADS, smem_r, st>>>(bt->node_ptr, pp, A, Z, G, keep, dF, dZ, dE,
+                                                                           dA, l, layers, heads, flags, bt->total_pairs);
+        else
+            stack_tile_bwd_rows_kernel<32><<<grid, TL_THREADS, smem_r, st>>>(bt->node_ptr, pp, A, Z, G, keep, dF, dZ, dE,
+                                                                           dA, l, layers, heads, flags, bt->total_pairs);
+        GCGCN_CHECK_LAUNCH("gcn_stack_tile_bwd_rows");
+        if (gd == 64)
+            stack_tile_bwd_cols_kernel<64><<<grid, TL_THREADS, smem_c, st>>>(bt->node_ptr, pp, A, Winner, dE, dZ, l, layers,
+                                                                           heads, bt->total_pairs);
+        else
+            stack_tile_bwd_cols_kernel<32><<<grid, TL_THREADS, smem_c, st>>>(bt->node_ptr, pp, A, Winner, dE, dZ, l, layers,
+                                                                           heads, bt->total_pairs);
+        GCGCN_CHECK_LAUNCH("gcn_stack_tile_bwd_cols");
+    }
+    return GCGCN_OK;
+}
+
+}  // namespace gcgcn

@@ -50,18 +50,20 @@ def upstream(doc_id, shape1, shape2):
     return torch.randn(shape1, generator=gen), torch.randn(shape2, generator=gen)
 
 
-def oracle_blocks(doc, state, layers, heads, keep=None, backward=True, apply_mask=False):
-    """Run the oracle hop glue on one document; returns outputs and gradients (CPU)."""
-    ps = {k: v.detach().clone().requires_grad_(backward) for k, v in state.items()}
-    x0 = doc.x0.float().clone().requires_grad_(backward)
-    e0 = doc.e0.float().clone().requires_grad_(backward)
-    e1 = doc.e1.float().clone().requires_grad_(backward)
-    r = O.graph_blocks(x0, e0, e1, doc.adj, sub(ps, PREFIXES[0]), sub(ps, PREFIXES[1]), sub(ps, PREFIXES[2]),
+def oracle_blocks(doc, state, layers, heads, keep=None, backward=True, apply_mask=False, device=None):
+    """Run the oracle hop glue on one document; returns outputs and gradients (CPU; `device` runs the same
+    ATen ops elsewhere -- bench.py's "reference PyTorch path on the B200" leg)."""
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    ps = {k: v.detach().clone().to(dev).requires_grad_(backward) for k, v in state.items()}
+    x0 = doc.x0.float().clone().to(dev).requires_grad_(backward)
+    e0 = doc.e0.float().clone().to(dev).requires_grad_(backward)
+    e1 = doc.e1.float().clone().to(dev).requires_grad_(backward)
+    r = O.graph_blocks(x0, e0, e1, doc.adj.to(dev), sub(ps, PREFIXES[0]), sub(ps, PREFIXES[1]), sub(ps, PREFIXES[2]),
                        sub(ps, PREFIXES[3]), layers, heads, 1.0, keep, apply_mask)
     out = {k: (v.detach() if torch.is_tensor(v) else [t.detach() for t in v]) for k, v in r.items()}
     if backward:
         dy1, dy2 = upstream(doc.doc_id, r["y1"].shape, r["y2"].shape)
-        ((r["y1"] * dy1).sum() + (r["y2"] * dy2).sum()).backward()
+        ((r["y1"] * dy1.to(dev)).sum() + (r["y2"] * dy2.to(dev)).sum()).backward()
         out.update(dx0=x0.grad, de0=e0.grad, de1=e1.grad,
                    dparams={k: v.grad for k, v in ps.items()})
     return out

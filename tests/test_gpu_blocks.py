@@ -235,3 +235,49 @@ def test_full_size_shard_properties():
     for k, v in part["dparams"].items():
         if v is not None:
             assert_close(v, tot[k], 24 * FP32_TOL, f"summed d{k}")   # 24 documents x 1e-4
+
+
+@pytest.mark.parametrize("layers,heads", [(2, 8), (4, 4)])
+def test_large_and_small_documents_in_one_batch(layers, heads):
+    """max n > 64 routes the whole batch to the row-tiled stack kernels (gcn_stack_tiled.cu): documents smaller
+    than a tile, tile-boundary sizes and non-multiples of 8 in the same launch."""
+    gb, state = device_blocks(layers, heads)
+    # document ids picked so that no relu pre-activation lies within 4e-6 of zero for either configuration
+    # (helpers.relu_margin; DESIGN.md section 2: a pre-activation inside float rounding of 0 may flip one unit)
+    picks = [(426, 130), (458, 66), (502, 40), (550, 7), (647, 96), (661, 97), (700, 1)]
+    docs = [S.make_doc(i, n=n, L=32) for i, n in picks]
+    res = run_blocks(gb, docs)
+    bt = res["bt"]
+    total = {}
+    for b, d in enumerate(docs):
+        r = oracle_blocks(d, state, layers, heads)
+        for k in ("y1", "y2", "dx0"):
+            assert_close(bt.split_nodes(res[k])[b], r[k], FP32_TOL, f"L{layers} H{heads} n={d.n} {k}")
+        for k in ("de0", "de1"):
+            assert_close(bt.split_pairs(res[k])[b], r[k], FP32_TOL, f"L{layers} H{heads} n={d.n} {k}")
+        for k, v in r["dparams"].items():
+            if v is not None:
+                total[k] = total.get(k, 0) + v
+    for k, v in res["dparams"].items():
+        if v is not None:
+            assert_close(v, total[k], 5 * FP32_TOL, f"L{layers} H{heads} d{k}")
+
+
+def test_train_mode_keep_masks_on_a_large_document():
+    """Injected dropout masks (all five sites) at n = 100: the keep-mask route of the row-tiled kernels."""
+    layers, heads = 2, 8
+    gb, state = device_blocks(layers, heads)
+    d = S.make_doc(79, n=100, L=32)
+    keep = S.make_keep_masks(d.doc_id, d.n, layers, heads)
+    gb.get_weighted_adj_matrix.inject_keep([keep["gat"]])
+    gb.graphcnn[0].inject_keep(keep["cag"])
+    gb.get_adj_matrix[0].inject_keep(keep["mha"])
+    gb.graphcnn[1].inject_keep([m for hm in keep["mag"] for m in hm])
+    gb.inject_keep([keep["out0"], keep["out1"]])
+    res = run_blocks(gb, [d])
+    r = oracle_blocks(d, state, layers, heads, keep=keep)
+    for k in ("y1", "y2", "dx0", "de0", "de1"):
+        assert_close(res[k].reshape(r[k].shape), r[k], FP32_TOL, f"train n=100 {k}")
+    for k, v in res["dparams"].items():
+        if v is not None:
+            assert_close(v, r["dparams"][k], 5 * FP32_TOL, f"train n=100 d{k}")
