@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--tile", type=int, default=512, help="12-document batches per GPU per step")
     ap.add_argument("--nodes", type=int, default=0, help="configs[3] entity-count sweep: every document has this many "
                                                          "entities (128 / 256 in the sweep); 0 = the DocRED-shaped batch")
-    ap.add_argument("--docs", type=int, default=0, help="documents per GPU per step with --nodes (default: ~3 GB of edges)")
+    ap.add_argument("--docs", type=int, default=0, help="documents per GPU per step with --nodes (default: 6 GB per edge tensor)")
     ap.add_argument("--heads", type=int, default=0, help="override head_num (4 / 8 in the sweep)")
     ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of the captured pass instead of eager launches")
     ap.add_argument("--train", action="store_true", help="module.train(): dropout keep-masks drawn by torch every step "
@@ -411,7 +411,7 @@ def run_gpu_arm(args):
         gb.train()
     if args.nodes:
         import numpy as np
-        ndoc = args.docs or max(1, int(1.5e9 // (args.nodes * args.nodes * 128 * (4 if args.dtype == "fp32" else 2))))
+        ndoc = args.docs or max(1, int(6e9 // (args.nodes * args.nodes * 128 * (4 if args.dtype == "fp32" else 2))))
         sizes = np.full(ndoc, args.nodes, dtype=np.int64)
     else:
         sizes = synthetic.shard_doc_sizes(12 * args.tile)

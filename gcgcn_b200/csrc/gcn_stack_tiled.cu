@@ -32,6 +32,78 @@ struct TileCfg {
 };
 
 __device__ __forceinline__ float4 tl_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// 16-byte global -> shared copies that do not pass through registers: a CTA issues all loads of its operand tiles
+// back to back and waits once (the scalar load -> store loops exposed one L2 round trip per unrolled batch)
+__device__ __forceinline__ void tl_cp16(float* smem_dst, const float* gsrc) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tl_cp_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void tl_zero4(float* p) { *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// all rows [0, rows) of one sub-layer slab (GD columns at `src`, row stride HD) -> dst[rows_pad][ld], zero padded
+template <int GD>
+__device__ __forceinline__ void load_slab_rows(float* dst, int ld, const float* __restrict__ src, int HD, int rows,
+                                               int rows_pad) {
+    constexpr int CG = GD / 4;
+    for (int idx = threadIdx.x; idx < rows_pad * CG; idx += TL_THREADS) {
+        const int i = idx / CG, c4 = (idx - i * CG) * 4;
+        if (i < rows) tl_cp16(dst + i * ld + c4, src + static_cast<size_t>(i) * HD + c4);
+        else tl_zero4(dst + i * ld + c4);
+    }
+}
+
+// rows [row0, row0 + 32) x columns [0, k8) of the document's n x n map -> As[32][lda], zero outside the document.
+// vec: n % 4 == 0 and the map starts on a 16-byte boundary.
+__device__ __forceinline__ void load_att_rows(float* As, int lda, const float* __restrict__ Ab, int n, int k8, int row0,
+                                              bool vec) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ii = warp; ii < TL_ROWS; ii += TL_WARPS) {
+        const bool row_ok = row0 + ii < n;
+        const float* src = Ab + static_cast<size_t>(row0 + ii) * n;
+        float* dst = As + ii * lda;
+        if (vec) {
+            for (int c4 = lane * 4; c4 < k8; c4 += 4 * WARP) {
+                if (row_ok && c4 < n) tl_cp16(dst + c4, src + c4);
+                else tl_zero4(dst + c4);
+            }
+        } else {
+            for (int j = lane; j < k8; j += WARP) dst[j] = (row_ok && j < n) ? src[j] : 0.f;
+        }
+    }
+}
+
+// C[16 x 8 NT] += A^T-stored product: A(m, k) = pa[k * lda + m] (the attention tile as it lies in memory, rows = k),
+// B(k, n) = pb[k * ldb + n]; 3xTF32 like warp_gemm.  lda == 8 (mod 32) keeps the A fragment loads conflict-free.
+template <int NT>
+__device__ __forceinline__ void warp_gemm_at(float (&c)[NT][4], int ksteps, const float* __restrict__ pa, int lda,
+                                             const float* __restrict__ pb, int ldb) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* a0 = pa + t * lda + g;
+    const float* b0 = pb + t * ldb + g;
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+        uint32_t ah[4], al[4];
+        split_tf32(a0[0], ah[0], al[0]);
+        split_tf32(a0[8], ah[1], al[1]);
+        split_tf32(a0[4 * lda], ah[2], al[2]);
+        split_tf32(a0[4 * lda + 8], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t bh[2], bl[2];
+            split_tf32(b0[nt * 8], bh[0], bl[0]);
+            split_tf32(b0[nt * 8 + 4 * ldb], bh[1], bl[1]);
+            mma_tf32(c[nt], al, bh);
+            mma_tf32(c[nt], ah, bl);
+            mma_tf32(c[nt], ah, bh);
+        }
+        a0 += 8 * lda;
+        b0 += 8 * ldb;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // forward, sub-layer l
@@ -62,16 +134,11 @@ stack_tile_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restr
     const size_t colbase = static_cast<size_t>(h) * S + l * GD;
     const bool relu = flags & GCGCN_STACK_RELU, resid = flags & GCGCN_STACK_RESIDUAL;
 
-    for (int idx = tid; idx < k8 * C::CG; idx += TL_THREADS) {
-        const int i = idx / C::CG, c4 = (idx - i * C::CG) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) v = tl_ld4(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4);
-        *reinterpret_cast<float4*>(Zl + i * C::LDZ + c4) = v;
-    }
-    for (int idx = tid; idx < TL_ROWS * k8; idx += TL_THREADS) {
-        const int ii = idx / k8, j = idx - ii * k8;
-        As[ii * lda + j] = (row0 + ii < n && j < n) ? Ab[static_cast<size_t>(row0 + ii) * n + j] : 0.f;
-    }
+    const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const bool vec = (n & 3) == 0 && (abase & 3) == 0;
+    load_slab_rows<GD>(Zl, C::LDZ, Z + static_cast<size_t>(node0) * HD + colbase, HD, n, k8);
+    load_att_rows(As, lda, Ab, n, k8, row0, vec);
+    tl_cp_wait_all();
     __syncthreads();
     for (int ii = warp; ii < TL_ROWS; ii += TL_WARPS) {     // r_i = rowsum + [rowsum == 0]   (G:47-49)
         float s = 0.f;
@@ -170,7 +237,9 @@ stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __
                            int layers, int heads, int flags, long long total_pairs) {
     using C = TileCfg<GD>;
     extern __shared__ __align__(16) float smem[];
-    const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * TL_ROWS;
+    constexpr int TR = 64;      // rows per CTA here: the [n, g] operand is the only large tile, so 64 rows still leave
+                                // room for two CTAs per SM and halve the per-row cost of loading it
+    const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * TR;
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (row0 >= n) return;
@@ -178,9 +247,9 @@ stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __
     const int n64 = (n + 63) & ~63;
 
     float* Ts = smem;                                        // [n64][LDB]  Z_l, all rows (B^T operand)
-    float* dNs = Ts + static_cast<size_t>(n64) * C::LDB;     // [32][LDB]   dN_l of the tile
-    float* rs = dNs + TL_ROWS * C::LDB;                      // [32]
-    float* drs = rs + TL_ROWS;                               // [32]
+    float* dNs = Ts + static_cast<size_t>(n64) * C::LDB;     // [64][LDB]   dN_l of the tile
+    float* rs = dNs + TR * C::LDB;                           // [64]
+    float* drs = rs + TR;                                    // [64]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
@@ -189,26 +258,32 @@ stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __
     const size_t colbase = static_cast<size_t>(h) * S + l * GD;
     const bool relu = flags & GCGCN_STACK_RELU;
 
-    for (int ii = warp; ii < TL_ROWS; ii += TL_WARPS) {      // row normalisers straight from global memory
+    load_slab_rows<GD>(Ts, C::LDB, Z + static_cast<size_t>(node0) * HD + colbase, HD, n, n64);
+    const bool vec = (n & 3) == 0 && (abase & 3) == 0;
+    for (int ii = warp; ii < TR; ii += TL_WARPS) {           // row normalisers straight from global memory
         float s = 0.f;
-        if (row0 + ii < n)
-            for (int j = lane; j < n; j += WARP) s += Ab[static_cast<size_t>(row0 + ii) * n + j];
+        if (row0 + ii < n) {
+            const float* arow = Ab + static_cast<size_t>(row0 + ii) * n;
+            if (vec) {
+                for (int j = lane * 4; j < n; j += 4 * WARP) {
+                    const float4 v = tl_ld4(arow + j);
+                    s += (v.x + v.y) + (v.z + v.w);
+                }
+            } else {
+                for (int j = lane; j < n; j += WARP) s += arow[j];
+            }
+        }
         s = warp_sum(s);
         if (lane == 0) { rs[ii] = s + (s == 0.f ? 1.f : 0.f); drs[ii] = 0.f; }
     }
-    for (int idx = tid; idx < n64 * C::CG; idx += TL_THREADS) {
-        const int i = idx / C::CG, c4 = (idx - i * C::CG) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) v = tl_ld4(Z + static_cast<size_t>(node0 + i) * HD + colbase + c4);
-        *reinterpret_cast<float4*>(Ts + i * C::LDB + c4) = v;
-    }
+    tl_cp_wait_all();
     __syncthreads();
 
     // (a) row-local: dG_l -> dOut -> dN_l (shared + dE), dr.  CG threads per row; a warp covers 32 / CG rows.
     //     At l == 0 the dr shares of the sub-layers above (their dN = dE and g are final) are folded in.
     constexpr int RPP = TL_THREADS / C::CG;
     const int cg = tid % C::CG, rg = tid / C::CG, c0 = cg * 4;
-    for (int ii = rg; ii < TL_ROWS; ii += RPP) {
+    for (int ii = rg; ii < TR; ii += RPP) {
         const int i = row0 + ii;
         float4 dn = make_float4(0.f, 0.f, 0.f, 0.f);
         float drp = 0.f;
@@ -248,28 +323,41 @@ stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __
     __syncthreads();
 
     // (c) dA[tile, :] (+)= dN_l Z_l^T (+ dr at l == 0), 64 columns per trip: warp (mt, ng) owns rows 16 mt .. + 15
-    //     and columns 16 ng .. + 15 of the trip
-    const int mt = warp & 1, ng = warp >> 1;
+    //     and columns 32 ng .. + 31 of the trip.  The values to accumulate onto are fetched before the product.
+    const int mt = warp & 3, ng = warp >> 2;
+    const bool accumulate = l != layers - 1;
+    const bool pair_ok = (n & 1) == 0 && (abase & 1) == 0;       // (j, j + 1) pairs are 8-byte aligned
     for (int jp = 0; jp < n64; jp += 64) {
-        float c[2][4];
-        zero_frag<2>(c);
-        warp_gemm<2, true>(c, GD / 8, dNs + (16 * mt) * C::LDB, C::LDB, Ts + (jp + 16 * ng) * C::LDB, C::LDB);
+        float2 cur[2][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                cur[half][nt] = make_float2(0.f, 0.f);
+                const int i = row0 + 16 * mt + g + 8 * half, j = jp + 32 * ng + 8 * nt + 2 * t;
+                if (!accumulate || i >= n || j >= n) continue;
+                const float* p = dAb + static_cast<size_t>(i) * n + j;
+                if (pair_ok) cur[half][nt] = *reinterpret_cast<const float2*>(p);
+                else { cur[half][nt].x = p[0]; if (j + 1 < n) cur[half][nt].y = p[1]; }
+            }
+        float c[4][4];
+        zero_frag<4>(c);
+        warp_gemm<4, true>(c, GD / 8, dNs + (16 * mt) * C::LDB, C::LDB, Ts + (jp + 32 * ng) * C::LDB, C::LDB);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int ii = 16 * mt + g + 8 * half, i = row0 + ii;
             if (i >= n) continue;
             const float dr = (l == 0) ? drs[ii] : 0.f;
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = jp + 16 * ng + 8 * nt + 2 * t + e;
-                    if (j >= n) continue;
-                    float* p = dAb + static_cast<size_t>(i) * n + j;
-                    float val = c[nt][2 * half + e] + dr;
-                    if (l != layers - 1) val += *p;
-                    *p = val;
-                }
+            for (int nt = 0; nt < 4; ++nt) {
+                const int j = jp + 32 * ng + 8 * nt + 2 * t;
+                if (j >= n) continue;
+                float* p = dAb + static_cast<size_t>(i) * n + j;
+                const float2 v = make_float2(c[nt][2 * half] + dr + cur[half][nt].x,
+                                             c[nt][2 * half + 1] + dr + cur[half][nt].y);
+                if (pair_ok) *reinterpret_cast<float2*>(p) = v;
+                else { p[0] = v.x; if (j + 1 < n) p[1] = v.y; }
+            }
         }
     }
 }
@@ -289,33 +377,39 @@ stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __
     const int n = node_ptr[b + 1] - node0;
     if (j0 >= n) return;
     const int S = layers * GD, HD = heads * S;
-    const int k8 = (n + 7) & ~7, ldt = k8 + 4;
+    const int k8 = (n + 7) & ~7;
+    constexpr int LDU = TL_ROWS + 8;                         // == 8 (mod 32): conflict-free transposed-A fragments
 
     float* dNs = smem;                                       // [k8][LDZ]   dN_l, all rows (B operand)
-    float* AsT = dNs + static_cast<size_t>(k8) * C::LDZ;     // [32][ldt]   AsT[jj][i] = A[i][j0 + jj]
-    float* Tt = AsT;                                         // [32][LDB]   dZ_l of the tile (push-down A operand),
+    float* AsU = dNs + static_cast<size_t>(k8) * C::LDZ;     // [k8][LDU]   AsU[i][jj] = A[i][j0 + jj], as it lies in memory
+    float* Tt = AsU;                                         // [32][LDB]   dZ_l of the tile (push-down A operand),
                                                              //             over the attention tile once it is consumed
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const float* Ab = A + static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const float* Ab = A + abase;
     const size_t colbase = static_cast<size_t>(h) * S + l * GD;
+    const bool vec = (n & 3) == 0 && (abase & 3) == 0;
 
-    for (int idx = tid; idx < k8 * C::CG; idx += TL_THREADS) {
-        const int i = idx / C::CG, c4 = (idx - i * C::CG) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) v = tl_ld4(dE + static_cast<size_t>(node0 + i) * HD + colbase + c4);
-        *reinterpret_cast<float4*>(dNs + i * C::LDZ + c4) = v;
+    load_slab_rows<GD>(dNs, C::LDZ, dE + static_cast<size_t>(node0) * HD + colbase, HD, n, k8);
+    for (int idx = tid; idx < k8 * (TL_ROWS / 4); idx += TL_THREADS) {   // 8 lanes per row of the tile: 128-byte reads
+        const int i = idx >> 3, c4 = (idx & 7) * 4;
+        float* dst = AsU + i * LDU + c4;
+        const float* src = Ab + static_cast<size_t>(i) * n + j0 + c4;
+        if (i < n && vec && j0 + c4 < n) {
+            tl_cp16(dst, src);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[e] = (i < n && j0 + c4 + e < n) ? src[e] : 0.f;
+        }
     }
-    for (int idx = tid; idx < TL_ROWS * k8; idx += TL_THREADS) {       // lanes along j: 128-byte global reads
-        const int i = idx / TL_ROWS, jj = idx - i * TL_ROWS;
-        AsT[jj * ldt + i] = (i < n && j0 + jj < n) ? Ab[static_cast<size_t>(i) * n + j0 + jj] : 0.f;
-    }
+    tl_cp_wait_all();
     __syncthreads();
 
     const int mt = warp >> 2, ng = warp & 3;
     float c[C::NT][4];
     zero_frag<C::NT>(c);
-    warp_gemm<C::NT, false>(c, k8 / 8, AsT + (16 * mt) * ldt, ldt, dNs + 8 * C::NT * ng, C::LDZ);
+    warp_gemm_at<C::NT>(c, k8 / 8, AsU + 16 * mt, LDU, dNs + 8 * C::NT * ng, C::LDZ);
     __syncthreads();
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -363,11 +457,12 @@ static size_t tile_fwd_smem(int n, int layers, int gd) {
 }
 static size_t tile_rows_smem(int n, int gd) {
     const int n64 = (n + 63) & ~63;
-    return (static_cast<size_t>(n64 + TL_ROWS) * (gd + 4) + 2 * TL_ROWS) * sizeof(float);
+    return (static_cast<size_t>(n64 + 64) * (gd + 4) + 2 * 64) * sizeof(float);
 }
 static size_t tile_cols_smem(int n, int gd) {
     const int k8 = (n + 7) & ~7;
-    return (static_cast<size_t>(k8) * (gd + 8) + static_cast<size_t>(TL_ROWS) * std::max(k8 + 4, gd + 4)) * sizeof(float);
+    return (static_cast<size_t>(k8) * (gd + 8) +
+            std::max(static_cast<size_t>(k8) * (TL_ROWS + 8), static_cast<size_t>(TL_ROWS) * (gd + 4))) * sizeof(float);
 }
 
 // graphs of 65 .. 256 entities with sub-layer width 32 or 64 (GCGCN_STACK=simt keeps gcn_stack.cu)
@@ -418,6 +513,7 @@ int launch_stack_bwd_tiled(const gcgcn_batch* bt, int heads, int layers, int sla
     const int gd = slab / layers, nmax = bt->max_nodes;
     const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
     const dim3 grid(ceil_div(nmax, TL_ROWS), heads, bt->num_docs);
+    const dim3 grid_r(ceil_div(nmax, 64), heads, bt->num_docs);
     const size_t smem_r = tile_rows_smem(nmax, gd), smem_c = tile_cols_smem(nmax, gd);
     if (gd == 64) {
         GCGCN_TRY(tile_smem_attr(stack_tile_bwd_rows_kernel<64>, smem_r, "stack_tile_bwd_rows"));
@@ -428,10 +524,10 @@ int launch_stack_bwd_tiled(const gcgcn_batch* bt, int heads, int layers, int sla
     }
     for (int l = layers - 1; l >= 0; --l) {
         if (gd == 64)
-            stack_tile_bwd_rows_kernel<64><<<grid, TL_THREADS, smem_r, st>>>(bt->node_ptr, pp, A, Z, G, keep, dF, dZ, dE,
+            stack_tile_bwd_rows_kernel<64><<<grid_r, TL_THREADS, smem_r, st>>>(bt->node_ptr, pp, A, Z, G, keep, dF, dZ, dE,
                                                                            dA, l, layers, heads, flags, bt->total_pairs);
         else
-            stack_tile_bwd_rows_kernel<32><<<grid, TL_THREADS, smem_r, st>>>(bt->node_ptr, pp, A, Z, G, keep, dF, dZ, dE,
+            stack_tile_bwd_rows_kernel<32><<<grid_r, TL_THREADS, smem_r, st>>>(bt->node_ptr, pp, A, Z, G, keep, dF, dZ, dE,
                                                                            dA, l, layers, heads, flags, bt->total_pairs);
         GCGCN_CHECK_LAUNCH("gcn_stack_tile_bwd_rows");
         if (gd == 64)
