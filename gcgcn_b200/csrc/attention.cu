@@ -144,9 +144,14 @@ int launch_mha_fwd(const gcgcn_batch* bt, int heads, const float* q, const float
     return GCGCN_OK;
 }
 
+// row-tiled tensor-core version for 65 <= max n <= 256 (gcn_stack_tiled.cu)
+bool mha_bwd_tiled_usable(const gcgcn_batch* bt, int heads);
+int launch_mha_bwd_tiled(const gcgcn_batch* bt, int heads, const float* q, const float* dS, float* dq, cudaStream_t st);
+
 int launch_mha_bwd(const gcgcn_batch* bt, int heads, const float* q, const float* dS, float* dq,
                    cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
+    if (mha_bwd_tiled_usable(bt, heads)) return launch_mha_bwd_tiled(bt, heads, q, dS, dq, st);
     const int dh = D / heads;
     const float scale = 1.0f / sqrtf(static_cast<float>(dh));
     const size_t smem = mha_smem(bt->max_nodes, dh);

@@ -382,8 +382,6 @@ stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __
 
     float* dNs = smem;                                       // [k8][LDZ]   dN_l, all rows (B operand)
     float* AsU = dNs + static_cast<size_t>(k8) * C::LDZ;     // [k8][LDU]   AsU[i][jj] = A[i][j0 + jj], as it lies in memory
-    float* Tt = AsU;                                         // [32][LDB]   dZ_l of the tile (push-down A operand),
-                                                             //             over the attention tile once it is consumed
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
@@ -410,7 +408,16 @@ stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __
     float c[C::NT][4];
     zero_frag<C::NT>(c);
     warp_gemm_at<C::NT>(c, k8 / 8, AsU + 16 * mt, LDU, dNs + 8 * C::NT * ng, C::LDZ);
-    __syncthreads();
+    __syncthreads();                                         // both operand tiles are consumed
+    // push-down operands take over the buffer at offsets that do not depend on this document's size:
+    // Wt [l GD][LDB] (rows m GD + c' of Wn_l's dense-connect part, B^T operand), then Tt [32][LDB] = dZ_l of the tile
+    float* Wt = smem;
+    float* Tt = smem + l * GD * C::LDB;
+    const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
+    for (int idx = tid; idx < l * GD * C::CG; idx += TL_THREADS) {
+        const int r = idx / C::CG, c4 = (idx - r * C::CG) * 4;
+        tl_cp16(Wt + r * C::LDB + c4, wsrc + static_cast<size_t>(r) * GD + c4);
+    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int jj = 16 * mt + g + 8 * half, j = j0 + jj;
@@ -418,18 +425,30 @@ stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __
         for (int nt = 0; nt < C::NT; ++nt) {
             const int cw = 8 * C::NT * ng + 8 * nt + 2 * t;
             const float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
-            *reinterpret_cast<float2*>(Tt + jj * C::LDB + cw) = v;
+            if (l > 0) *reinterpret_cast<float2*>(Tt + jj * C::LDB + cw) = v;
             if (j < n) *reinterpret_cast<float2*>(dZ + static_cast<size_t>(node0 + j) * HD + colbase + cw) = v;
         }
     }
     if (l == 0) return;
+    // dG_m[j][c'] (+)= sum_c dZ_l[j][c] Wn_l[128 + m GD + c'][c]  for m < l  (the slab of dZ that sub-layer m reads);
+    // what is accumulated onto is fetched before the product
+    float2 cur[2][C::NT];
+    tl_cp_wait_all();
     __syncthreads();
-    // dG_m[j][c'] (+)= sum_c dZ_l[j][c] Wn_l[128 + m GD + c'][c]  for m < l  (the slab of dZ that sub-layer m reads)
-    const float* wsrc = Winner + (static_cast<size_t>(h) * layers + l) * S * GD;
     for (int m = 0; m < l; ++m) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int nt = 0; nt < C::NT; ++nt) {
+                const int j = j0 + 16 * mt + g + 8 * half;
+                cur[half][nt] = make_float2(0.f, 0.f);
+                if (l != layers - 1 && j < n)
+                    cur[half][nt] = *reinterpret_cast<const float2*>(dZ + static_cast<size_t>(node0 + j) * HD +
+                                                                     static_cast<size_t>(h) * S + m * GD +
+                                                                     8 * C::NT * ng + 8 * nt + 2 * t);
+            }
         zero_frag<C::NT>(c);
-        warp_gemm<C::NT, true>(c, GD / 8, Tt + (16 * mt) * C::LDB, C::LDB,
-                               wsrc + (static_cast<size_t>(m) * GD + 8 * C::NT * ng) * GD, GD);
+        warp_gemm<C::NT, true>(c, GD / 8, Tt + (16 * mt) * C::LDB, C::LDB, Wt + (m * GD + 8 * C::NT * ng) * C::LDB, C::LDB);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int j = j0 + 16 * mt + g + 8 * half;
@@ -438,12 +457,8 @@ stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __
             for (int nt = 0; nt < C::NT; ++nt) {
                 float* p = dZ + static_cast<size_t>(node0 + j) * HD + static_cast<size_t>(h) * S + m * GD +
                            8 * C::NT * ng + 8 * nt + 2 * t;
-                float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
-                if (l != layers - 1) {
-                    const float2 cur = *reinterpret_cast<const float2*>(p);
-                    v.x += cur.x; v.y += cur.y;
-                }
-                *reinterpret_cast<float2*>(p) = v;
+                *reinterpret_cast<float2*>(p) = make_float2(c[nt][2 * half] + cur[half][nt].x,
+                                                            c[nt][2 * half + 1] + cur[half][nt].y);
             }
         }
     }
@@ -453,16 +468,18 @@ stack_tile_bwd_cols_kernel(const int* __restrict__ node_ptr, const long long* __
 static size_t tile_fwd_smem(int n, int layers, int gd) {
     const int k8 = (n + 7) & ~7, s = layers * gd;
     const size_t tile = static_cast<size_t>(TL_ROWS) * std::max(k8 + 4, s + 4);
-    return (static_cast<size_t>(k8) * (gd + 8) + tile + TL_ROWS) * sizeof(float);
+    const int kin = (layers - 1) * gd;                                       // recycled: Ws [kin][gd+8] + Gt [32][kin+4]
+    const size_t recycled = static_cast<size_t>(kin) * (gd + 8) + static_cast<size_t>(TL_ROWS) * (kin + 4);
+    return std::max(static_cast<size_t>(k8) * (gd + 8) + tile + TL_ROWS, recycled) * sizeof(float);
 }
 static size_t tile_rows_smem(int n, int gd) {
     const int n64 = (n + 63) & ~63;
     return (static_cast<size_t>(n64 + 64) * (gd + 4) + 2 * 64) * sizeof(float);
 }
-static size_t tile_cols_smem(int n, int gd) {
+static size_t tile_cols_smem(int n, int layers, int gd) {
     const int k8 = (n + 7) & ~7;
-    return (static_cast<size_t>(k8) * (gd + 8) +
-            std::max(static_cast<size_t>(k8) * (TL_ROWS + 8), static_cast<size_t>(TL_ROWS) * (gd + 4))) * sizeof(float);
+    const size_t recycled = static_cast<size_t>((layers - 1) * gd + TL_ROWS) * (gd + 4);   // Wt + Tt
+    return std::max(static_cast<size_t>(k8) * (gd + 8) + static_cast<size_t>(k8) * (TL_ROWS + 8), recycled) * sizeof(float);
 }
 
 // graphs of 65 .. 256 entities with sub-layer width 32 or 64 (GCGCN_STACK=simt keeps gcn_stack.cu)
@@ -514,7 +531,7 @@ int launch_stack_bwd_tiled(const gcgcn_batch* bt, int heads, int layers, int sla
     const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
     const dim3 grid(ceil_div(nmax, TL_ROWS), heads, bt->num_docs);
     const dim3 grid_r(ceil_div(nmax, 64), heads, bt->num_docs);
-    const size_t smem_r = tile_rows_smem(nmax, gd), smem_c = tile_cols_smem(nmax, gd);
+    const size_t smem_r = tile_rows_smem(nmax, gd), smem_c = tile_cols_smem(nmax, layers, gd);
     if (gd == 64) {
         GCGCN_TRY(tile_smem_attr(stack_tile_bwd_rows_kernel<64>, smem_r, "stack_tile_bwd_rows"));
         GCGCN_TRY(tile_smem_attr(stack_tile_bwd_cols_kernel<64>, smem_c, "stack_tile_bwd_cols"));
@@ -538,6 +555,93 @@ int launch_stack_bwd_tiled(const gcgcn_batch* bt, int heads, int layers, int sla
                                                                            heads, bt->total_pairs);
         GCGCN_CHECK_LAUNCH("gcn_stack_tile_bwd_cols");
     }
+    return GCGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MHA backward for large graphs: dq_h[tile] = scale (dS + dS^T)[tile, :] q_h   (G:136-138 backward; key = query).
+// attention.cu's kernel walks dS^T with stride-n scalar reads (32 lines per warp instruction) and gives a whole
+// (document, head) to one CTA; here a CTA takes 32 rows, reads its row tile dS[tile, :] and its column tile
+// dS[:, tile] as they lie in memory (16-byte async copies) and runs both products on the tensor cores, the second
+// one with transposed-A fragment loads.
+template <int DH>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+mha_bwd_tile_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr,
+                    const float* __restrict__ q, const float* __restrict__ dS, float* __restrict__ dq,
+                    long long total_pairs, float scale) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TL_ROWS;
+    const int node0 = node_ptr[b];
+    const int n = node_ptr[b + 1] - node0;
+    if (i0 >= n) return;
+    const int k8 = (n + 7) & ~7, lda = k8 + 4;
+    constexpr int LDQ = DH + 8, LDU = TL_ROWS + 8;
+
+    float* Qs = smem;                                        // [k8][LDQ]   q_h, all rows
+    float* As = Qs + static_cast<size_t>(k8) * LDQ;          // [32][lda]   dS[tile, :]
+    float* AsU = As + TL_ROWS * lda;                         // [k8][LDU]   dS[:, tile]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
+    const float* Sb = dS + abase;
+    const bool vec = (n & 3) == 0 && (abase & 3) == 0;
+
+    for (int idx = tid; idx < k8 * (DH / 4); idx += TL_THREADS) {
+        const int j = idx / (DH / 4), c4 = (idx - j * (DH / 4)) * 4;
+        if (j < n) tl_cp16(Qs + j * LDQ + c4, q + static_cast<size_t>(node0 + j) * D + h * DH + c4);
+        else tl_zero4(Qs + j * LDQ + c4);
+    }
+    load_att_rows(As, lda, Sb, n, k8, i0, vec);
+    for (int idx = tid; idx < k8 * (TL_ROWS / 4); idx += TL_THREADS) {
+        const int i = idx >> 3, c4 = (idx & 7) * 4;
+        float* dst = AsU + i * LDU + c4;
+        const float* src = Sb + static_cast<size_t>(i) * n + i0 + c4;
+        if (i < n && vec && i0 + c4 < n) {
+            tl_cp16(dst, src);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[e] = (i < n && i0 + c4 + e < n) ? src[e] : 0.f;
+        }
+    }
+    tl_cp_wait_all();
+    __syncthreads();
+
+    const int mt = warp & 1, ng = warp >> 1;                 // 2 row tiles x up to 4 column tiles of 8
+    if (ng >= DH / 8) return;
+    float c[1][4];
+    zero_frag<1>(c);
+    warp_gemm<1, false>(c, k8 / 8, As + (16 * mt) * lda, lda, Qs + 8 * ng, LDQ);
+    warp_gemm_at<1>(c, k8 / 8, AsU + 16 * mt, LDU, Qs + 8 * ng, LDQ);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int i = i0 + 16 * mt + g + 8 * half;
+        if (i >= n) continue;
+        *reinterpret_cast<float2*>(dq + static_cast<size_t>(node0 + i) * D + h * DH + 8 * ng + 2 * t) =
+            make_float2(c[0][2 * half] * scale, c[0][2 * half + 1] * scale);
+    }
+}
+
+bool mha_bwd_tiled_usable(const gcgcn_batch* bt, int heads) {
+    const int dh = D / heads;
+    return bt->max_nodes > 64 && bt->max_nodes <= 256 && bt->num_docs <= 65535 && (dh == 16 || dh == 32);
+}
+
+int launch_mha_bwd_tiled(const gcgcn_batch* bt, int heads, const float* q, const float* dS, float* dq,
+                         cudaStream_t st) {
+    const int dh = D / heads, nmax = bt->max_nodes, k8 = (nmax + 7) & ~7;
+    const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+    const size_t smem = (static_cast<size_t>(k8) * (dh + 8) + static_cast<size_t>(TL_ROWS) * (k8 + 4) +
+                         static_cast<size_t>(k8) * (TL_ROWS + 8)) * sizeof(float);
+    const dim3 grid(ceil_div(nmax, TL_ROWS), heads, bt->num_docs);
+    const long long* pp = reinterpret_cast<const long long*>(bt->pair_ptr);
+    if (dh == 16) {
+        GCGCN_TRY(tile_smem_attr(mha_bwd_tile_kernel<16>, smem, "mha_bwd_tile"));
+        mha_bwd_tile_kernel<16><<<grid, TL_THREADS, smem, st>>>(bt->node_ptr, pp, q, dS, dq, bt->total_pairs, scale);
+    } else {
+        GCGCN_TRY(tile_smem_attr(mha_bwd_tile_kernel<32>, smem, "mha_bwd_tile"));
+        mha_bwd_tile_kernel<32><<<grid, TL_THREADS, smem, st>>>(bt->node_ptr, pp, q, dS, dq, bt->total_pairs, scale);
+    }
+    GCGCN_CHECK_LAUNCH("mha_bwd_tile");
     return GCGCN_OK;
 }
 
