@@ -259,6 +259,39 @@ stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __
     const bool relu = flags & GCGCN_STACK_RELU;
 
     load_slab_rows<GD>(Ts, C::LDB, Z + static_cast<size_t>(node0) * HD + colbase, HD, n, n64);
+    // (a), loads: everything the row-local phase needs from global memory is requested now, while the Z_l tile is
+    // still in flight -- dG_l (dF, keep, what the sub-layers above pushed down), g_l, and at l == 0 the dr shares of
+    // the sub-layers above (their dN = dE and g are final).  CG threads per row, NI rows per thread.
+    constexpr int RPP = TL_THREADS / C::CG, NI = TR / RPP;
+    const int cg = tid % C::CG, rg = tid / C::CG, c0 = cg * 4;
+    float4 dgv[NI], g4v[NI];
+    float upper[NI];
+#pragma unroll
+    for (int u = 0; u < NI; ++u) {
+        const int i = row0 + rg + u * RPP;
+        dgv[u] = g4v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        upper[u] = 0.f;
+        if (i >= n) continue;
+        const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + c0;
+        float4 dg = tl_ld4(dF + off);
+        if (keep != nullptr) {
+            const float4 k4 = tl_ld4(keep + off);
+            dg.x *= k4.x; dg.y *= k4.y; dg.z *= k4.z; dg.w *= k4.w;
+        }
+        if (l < layers - 1) {
+            const float4 s4 = tl_ld4(dZ + off);
+            dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
+        }
+        dgv[u] = dg;
+        g4v[u] = tl_ld4(G + off);
+        if (l == 0) {
+            for (int m = 1; m < layers; ++m) {
+                const size_t om = static_cast<size_t>(node0 + i) * HD + static_cast<size_t>(h) * S + m * GD + c0;
+                const float4 dm = tl_ld4(dE + om), gm = tl_ld4(G + om);
+                upper[u] -= dm.x * gm.x + dm.y * gm.y + dm.z * gm.z + dm.w * gm.w;
+            }
+        }
+    }
     const bool vec = (n & 3) == 0 && (abase & 3) == 0;
     for (int ii = warp; ii < TR; ii += TL_WARPS) {           // row normalisers straight from global memory
         float s = 0.f;
@@ -279,41 +312,23 @@ stack_tile_bwd_rows_kernel(const int* __restrict__ node_ptr, const long long* __
     tl_cp_wait_all();
     __syncthreads();
 
-    // (a) row-local: dG_l -> dOut -> dN_l (shared + dE), dr.  CG threads per row; a warp covers 32 / CG rows.
-    //     At l == 0 the dr shares of the sub-layers above (their dN = dE and g are final) are folded in.
-    constexpr int RPP = TL_THREADS / C::CG;
-    const int cg = tid % C::CG, rg = tid / C::CG, c0 = cg * 4;
-    for (int ii = rg; ii < TR; ii += RPP) {
-        const int i = row0 + ii;
+    // (a), arithmetic: dOut = relu'(g) dG ; dN_l = dOut / r (shared + dE) ; dr = -sum_c dN g
+#pragma unroll
+    for (int u = 0; u < NI; ++u) {
+        const int ii = rg + u * RPP, i = row0 + ii;
         float4 dn = make_float4(0.f, 0.f, 0.f, 0.f);
         float drp = 0.f;
         if (i < n) {
-            const size_t off = static_cast<size_t>(node0 + i) * HD + colbase + c0;
-            float4 dg = tl_ld4(dF + off);
-            if (keep != nullptr) {
-                const float4 k4 = tl_ld4(keep + off);
-                dg.x *= k4.x; dg.y *= k4.y; dg.z *= k4.z; dg.w *= k4.w;
-            }
-            if (l < layers - 1) {
-                const float4 s4 = tl_ld4(dZ + off);          // what the sub-layers above pushed down to g_l
-                dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
-            }
-            const float4 g4 = tl_ld4(G + off);
+            float4 dg = dgv[u];
+            const float4 g4 = g4v[u];
             if (relu) {
                 dg.x = g4.x > 0.f ? dg.x : 0.f; dg.y = g4.y > 0.f ? dg.y : 0.f;
                 dg.z = g4.z > 0.f ? dg.z : 0.f; dg.w = g4.w > 0.f ? dg.w : 0.f;
             }
             const float r = rs[ii];
             dn.x = dg.x / r; dn.y = dg.y / r; dn.z = dg.z / r; dn.w = dg.w / r;
-            *reinterpret_cast<float4*>(dE + off) = dn;
-            drp = -(dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
-            if (l == 0) {
-                for (int m = 1; m < layers; ++m) {
-                    const size_t om = static_cast<size_t>(node0 + i) * HD + static_cast<size_t>(h) * S + m * GD + c0;
-                    const float4 dm = tl_ld4(dE + om), gm = tl_ld4(G + om);
-                    drp -= dm.x * gm.x + dm.y * gm.y + dm.z * gm.z + dm.w * gm.w;
-                }
-            }
+            *reinterpret_cast<float4*>(dE + static_cast<size_t>(node0 + i) * HD + colbase + c0) = dn;
+            drp = upper[u] - (dn.x * g4.x + dn.y * g4.y + dn.z * g4.z + dn.w * g4.w);
         }
         *reinterpret_cast<float4*>(dNs + ii * C::LDB + c0) = dn;
 #pragma unroll
