@@ -63,6 +63,8 @@ int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const flo
 int pair_dis_warps();
 int launch_pack_stack(const float* const* wn_ptrs, const float* const* we_ptrs, int heads, int layers, int slab,
                       float* WnX, float* We, float* Winner, cudaStream_t st);
+int launch_expand_pair_context(const int* slots, int num_slots, int n, int S, int L, int dis_plus, unsigned char* sen,
+                               long long* pos_h, long long* pos_t, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long count, float lr, float b1, float b2,
                 float eps, float wd, float gscale, int step, cudaStream_t st);
 int launch_unpack_stack(const float* dWnX, const float* dWe, const float* dWinner, int heads, int layers, int slab,
@@ -762,6 +764,21 @@ int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const floa
 }
 
 // ---- dense projection ------------------------------------------------------------------------
+int gcgcn_expand_pair_context(const int32_t* slots, int32_t num_slots, int32_t n, int32_t max_num, int32_t length,
+                              int32_t dis_plus, uint8_t* sen_matrix, int64_t* pos_matrix_h, int64_t* pos_matrix_t,
+                              void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(num_slots >= 0 && n >= 0 && max_num >= 0 && length >= 0, "expand_pair_context: negative size");
+    if (static_cast<size_t>(n) * n * max_num * length == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(sen_matrix, "sen_matrix"));
+    GCGCN_TRY(check_device_ptr(pos_matrix_h, "pos_matrix_h"));
+    GCGCN_TRY(check_device_ptr(pos_matrix_t, "pos_matrix_t"));
+    if (num_slots > 0) GCGCN_TRY(check_device_ptr(slots, "slots"));
+    return launch_expand_pair_context(slots, num_slots, n, max_num, length, dis_plus, sen_matrix,
+                                      reinterpret_cast<long long*>(pos_matrix_h),
+                                      reinterpret_cast<long long*>(pos_matrix_t), static_cast<cudaStream_t>(stream));
+}
+
 int gcgcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                     float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                     int32_t step, void* stream) {

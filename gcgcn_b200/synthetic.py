@@ -112,3 +112,50 @@ def make_keep_masks(doc_id: int, n: int, layers: int, heads: int, hidden: int = 
 def shard_doc_sizes(num_docs: int) -> np.ndarray:
     """Entity counts of a config-5 style shard: n cycles through DOC_N (mean 20.25)."""
     return np.asarray([DOC_N[i % len(DOC_N)] for i in range(num_docs)], dtype=np.int64)
+
+
+# ------------------------------------------------------------------------------- pickle-record stand-ins
+def make_record(seed: int, n: Optional[int] = None, L: Optional[int] = None, S: Optional[int] = None) -> dict:
+    """A synthetic record with the schema of the reference's pickled documents (gen_data_extend_graph.py:115-290):
+    `document` token ids, and `graph`, an nx.DiGraph whose nodes carry `exist_pos` [(start, end), ...] and `type`,
+    whose edges carry `sentences` [(s0, s1), ...] and `position` [(h0, h1, t0, t1), ...] (one slot per sentence the
+    two entities share), and whose graph attribute `max_sentence_num` bounds the slots.  Sentences partition the
+    document; an edge exists iff two entities have mentions in a common sentence (gen_data_extend_graph.py:209-261).
+    Documents may be longer than max_length and edges may have more slots than max_num (both get truncated)."""
+    import networkx as nx
+    rng = np.random.RandomState(4242 + seed)
+    n = int(rng.randint(2, 12)) if n is None else n
+    L = int(rng.randint(40, 700)) if L is None else L
+    bounds = [0]
+    while bounds[-1] < L:
+        bounds.append(min(L, bounds[-1] + int(rng.randint(6, 40))))
+    sents = list(zip(bounds[:-1], bounds[1:]))
+    g = nx.DiGraph()
+    for e in range(n):
+        poses, where = [], []
+        for _ in range(int(rng.randint(1, 4))):
+            si = int(rng.randint(len(sents)))
+            s0, s1 = sents[si]
+            a = int(rng.randint(s0, s1))
+            b = min(s1, a + int(rng.randint(1, 5)))
+            poses.append((a, b))
+            where.append(sents[si])
+        g.add_node(e, exist_pos=poses, exist_sentence=where, type=[int(rng.randint(1, 7))])
+    most = 0
+    for a in range(n):
+        for b in range(n):
+            if a == b:
+                continue
+            common, cpos = [], []
+            for pa, sa in zip(g.nodes[a]["exist_pos"], g.nodes[a]["exist_sentence"]):
+                for pb, sb in zip(g.nodes[b]["exist_pos"], g.nodes[b]["exist_sentence"]):
+                    if sa == sb:
+                        common.append(sa)
+                        cpos.append(pa + pb)
+            if common:
+                g.add_edge(a, b, sentences=common, position=cpos)
+                most = max(most, len(common))
+    g.graph["max_sentence_num"] = max(most, 1) if S is None else max(S, most, 1)
+    return {"document": rng.randint(1, 1000, size=L).tolist(), "document_pos": rng.randint(0, n + 1, size=L).tolist(),
+            "document_ner": rng.randint(0, 7, size=L).tolist(), "graph": g, "title": f"synthetic-{seed}",
+            "label_matrix": np.zeros((n, n, 97), dtype=np.float32), "label_mask": []}

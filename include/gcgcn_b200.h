@@ -270,6 +270,17 @@ int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
                     float* dWout, float* dbout, const gcgcn_dropout* dropout,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* ---- wire format -> dense pair-context tensors (replaces the host loops of
+ * config/Config.py:180-205 and the H2D copies of C:345-347) --------------------------------------------
+ * `slots` is int32 [num_slots, 9], one row per (edge, sentence slot) of ONE document:
+ * (u, v, slot, s0, s1, h0, h1, t0, t1) = entity pair, slot index, sentence tokens [s0, s1), head and tail
+ * mention spans.  Writes sen_matrix (bool as uint8), pos_matrix_h and pos_matrix_t (int64), each
+ * [n, n, max_num, length] row-major, exactly as C:219-222 leaves them (rows with slot >= max_num and tokens
+ * >= length are truncated away; everything outside the listed spans is 0).  The call zero-fills the outputs. */
+int gcgcn_expand_pair_context(const int32_t* slots, int32_t num_slots, int32_t n, int32_t max_num, int32_t length,
+                              int32_t dis_plus, uint8_t* sen_matrix, int64_t* pos_matrix_h, int64_t* pos_matrix_t,
+                              void* stream);
+
 /* ---- training step of config 5 (new work: the reference has no multi-GPU path) ----
  * Fused Adam over ONE flat float32 buffer holding every hot-path parameter, with the semantics of
  * torch.optim.Adam as the reference's trainer constructs it (config/Config.py:300: lr only, betas
