@@ -317,7 +317,7 @@ def aux_rates(dev, hbm_peak, tiles=128, iters=10):
     import torch
     from gcgcn_b200 import synthetic
     from gcgcn_b200.batch import PairTables, PoolTable, RaggedBatch, node_relative_pos
-    from gcgcn_b200.modules import pair_gather, pool_nodes
+    from gcgcn_b200.modules import pair_dense, pair_gather, pool_nodes
 
     docs = synthetic.make_batch() * tiles
     bt = RaggedBatch([d.n for d in docs], dev)
@@ -358,6 +358,16 @@ def aux_rates(dev, hbm_peak, tiles=128, iters=10):
     def pair_b():
         torch.autograd.grad(keep["p"], [feat, dis], [dh, dt], retain_graph=True)
 
+    # the same classifier input without the gathered intermediate: tanh(dense_layer(.)) folded in
+    dense = torch.nn.Linear(424, 128).to(dev)
+    dh128, dt128 = dh[:, :128].contiguous(), dt[:, :128].contiguous()
+
+    def dense_f():
+        keep["d"] = pair_dense(feat, dense, dis, tabs, bt)
+
+    def dense_b():
+        torch.autograd.grad(keep["d"], [feat, dis], [dh128, dt128], retain_graph=True)
+
     nnz = int(tab.tok_idx_host.size)
     n1, n2 = bt.total_nodes, bt.total_pairs
     touched = int((tab.tok_ptr_host[1:] > tab.tok_ptr_host[:-1]).sum())
@@ -366,6 +376,10 @@ def aux_rates(dev, hbm_peak, tiles=128, iters=10):
         "pool_bwd": (pool_b, 512 * (nnz + tab.total_tokens) + 8 * nnz),
         "pair_gather_fwd": (pair_f, 2 * n2 * 424 * 4 + n1 * 404 * 4 + 4 * n2 * 4),
         "pair_gather_bwd": (pair_b, 2 * n2 * 424 * 4 + n1 * 404 * 4 + 2 * n2 * 4),
+        # writes 2 n^2 128 s (+ node-level projection n 404 s in, n 128 s out); backward reads dout and out, writes dpre
+        # and reads it back twice (segmented sums over node rows and over distance rows)
+        "pair_dense_fwd": (dense_f, 2 * n2 * 128 * 4 + n1 * (404 + 128) * 4 + 4 * n2 * 4),
+        "pair_dense_bwd": (dense_b, 2 * n2 * 128 * 4 * 5 + n1 * (404 + 128) * 4 + 2 * n2 * 4),
     }
     out = {"documents": len(docs), "entities": n1, "pairs": n2, "mention_tokens": nnz, "tokens": tab.total_tokens,
            "tokens_in_a_mention": touched}

@@ -105,6 +105,9 @@ SIGNATURES = {
     "gcgcn_pair_gather_fwd": (c_int32, [_BT, _P, c_int32, _P, c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "gcgcn_pair_gather_bwd": (c_int32, [_BT, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P,
                                         _P, c_size_t, _P]),
+    "gcgcn_pair_dense_fwd": (c_int32, [_BT, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gcgcn_pair_dense_ws_bytes": (c_size_t, [c_int32]),
+    "gcgcn_pair_dense_bwd": (c_int32, [_BT, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gcgcn_block_saved_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "gcgcn_caggc_fwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 8 + [_P, _P, _DP, _P, c_size_t, _P]),
     "gcgcn_caggc_bwd": (c_int32, [_BT, c_int32, _P, _P, c_int32] + [_P] * 6 + [_P, _P]

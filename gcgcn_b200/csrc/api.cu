@@ -61,6 +61,11 @@ int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const flo
                            int dis_w, int dis_rows, const int* dis_h, const int* dis_t, float* dfeat,
                            float* ddis, void* ws, size_t ws_bytes, cudaStream_t st);
 int pair_dis_warps();
+int launch_pair_dense_fwd(const gcgcn_batch* bt, const float* U, const float* Vd, const int* h_idx, const int* t_idx,
+                          const int* dis_h, const int* dis_t, float* out_h, float* out_t, cudaStream_t st);
+int launch_pair_dense_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, const float* out_h,
+                          const float* out_t, int dis_rows, const int* dis_h, const int* dis_t, float* dU, float* dVd,
+                          float* dpre, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_pack_stack(const float* const* wn_ptrs, const float* const* we_ptrs, int heads, int layers, int slab,
                       float* WnX, float* We, float* Winner, cudaStream_t st);
 int launch_expand_pair_context(const int* slots, int num_slots, int n, int S, int L, int dis_plus, unsigned char* sen,
@@ -761,6 +766,45 @@ int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const floa
     GCGCN_TRY(check_device_ptr(dfeat, "dfeat"));
     return launch_pair_gather_bwd(bt, dout_h, dout_t, feat_w, dis_w, dis_rows, dis_h, dis_t, dfeat, ddis, ws,
                                   ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_pair_dense_fwd(const gcgcn_batch* bt, const float* U, const float* Vd, const int32_t* h_idx,
+                         const int32_t* t_idx, const int32_t* dis_h, const int32_t* dis_t, float* out_h, float* out_t,
+                         void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    if (bt->total_pairs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(U, "U"));
+    GCGCN_TRY(check_device_ptr(Vd, "Vd"));
+    GCGCN_TRY(check_device_ptr(h_idx, "h_idx"));
+    GCGCN_TRY(check_device_ptr(t_idx, "t_idx"));
+    GCGCN_TRY(check_device_ptr(dis_h, "dis_h"));
+    GCGCN_TRY(check_device_ptr(dis_t, "dis_t"));
+    GCGCN_TRY(check_device_ptr(out_h, "out_h"));
+    GCGCN_TRY(check_device_ptr(out_t, "out_t"));
+    return launch_pair_dense_fwd(bt, U, Vd, h_idx, t_idx, dis_h, dis_t, out_h, out_t, static_cast<cudaStream_t>(stream));
+}
+
+size_t gcgcn_pair_dense_ws_bytes(int32_t dis_rows) {
+    return (static_cast<size_t>(pair_dis_warps()) + 4) * dis_rows * D * sizeof(float);
+}
+
+int gcgcn_pair_dense_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, const float* out_h,
+                         const float* out_t, int32_t dis_rows, const int32_t* dis_h, const int32_t* dis_t, float* dU,
+                         float* dVd, float* dpre, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(dis_rows >= 1, "pair_dense_bwd: dis_rows must be positive");
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(dout_h, "dout_h"));
+    GCGCN_TRY(check_device_ptr(dout_t, "dout_t"));
+    GCGCN_TRY(check_device_ptr(out_h, "out_h"));
+    GCGCN_TRY(check_device_ptr(out_t, "out_t"));
+    GCGCN_TRY(check_device_ptr(dU, "dU"));
+    GCGCN_TRY(check_device_ptr(dVd, "dVd"));
+    GCGCN_TRY(check_device_ptr(dpre, "dpre"));
+    return launch_pair_dense_bwd(bt, dout_h, dout_t, out_h, out_t, dis_rows, dis_h, dis_t, dU, dVd, dpre, ws, ws_bytes,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 // ---- dense projection ------------------------------------------------------------------------

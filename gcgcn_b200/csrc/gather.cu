@@ -211,4 +211,95 @@ int launch_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const flo
     return GCGCN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Classifier-side pair features without the gathered intermediate (first half):
+//   entity_feature_h[i,j] = tanh(dense_layer(cat(F[j], dis[10 + rp_ij])))  (G:351-355)
+//                         = tanh(U[j] + Vd[10 + rp_ij]),   U = F W_F^T  [rows, 128],  Vd = dis W_d^T + b  [21, 128]
+// (dense_layer's weight split by input columns), and likewise entity_feature_t[i,j] = tanh(U[i] + Vd[10 - rp_ij]).
+// The two n^2 x 424 gathered tensors and the n^2 x 424 x 128 product over them are never formed: one warp per pair
+// reads two 512-byte rows per side (L2-resident tables) and writes 2 x 128 floats.
+// tanh(x) = 1 - 2 / (exp(2x) + 1): ~6 instructions instead of tanhf's ~25, absolute error ~1e-7 (the parity bar is an
+// absolute 1e-4); saturates correctly (exp -> inf gives 1, exp -> 0 gives -1)
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+__global__ void __launch_bounds__(256)
+pair_dense_fwd_kernel(const float4* __restrict__ U, const float4* __restrict__ Vd, const int* __restrict__ h_idx,
+                      const int* __restrict__ t_idx, const int* __restrict__ dis_h, const int* __restrict__ dis_t,
+                      float* __restrict__ out_h, float* __restrict__ out_t, long long total_pairs) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long p = warp; p < total_pairs; p += nwarps) {
+        const float4 uh = __ldg(U + static_cast<size_t>(h_idx[p]) * (D / 4) + lane);
+        const float4 ut = __ldg(U + static_cast<size_t>(t_idx[p]) * (D / 4) + lane);
+        const float4 vh = __ldg(Vd + static_cast<size_t>(dis_h[p]) * (D / 4) + lane);
+        const float4 vt = __ldg(Vd + static_cast<size_t>(dis_t[p]) * (D / 4) + lane);
+        Vec4<float>::store(out_h + static_cast<size_t>(p) * D + lane * 4,
+                           make_float4(fast_tanh(uh.x + vh.x), fast_tanh(uh.y + vh.y), fast_tanh(uh.z + vh.z), fast_tanh(uh.w + vh.w)));
+        Vec4<float>::store(out_t + static_cast<size_t>(p) * D + lane * 4,
+                           make_float4(fast_tanh(ut.x + vt.x), fast_tanh(ut.y + vt.y), fast_tanh(ut.z + vt.z), fast_tanh(ut.w + vt.w)));
+    }
+}
+
+// dpre = dout (1 - out^2) for both sides, float4 grid-stride
+__global__ void __launch_bounds__(256)
+tanh_bwd2_kernel(const float* __restrict__ dh, const float* __restrict__ dt, const float* __restrict__ oh,
+                 const float* __restrict__ ot, float* __restrict__ ph, float* __restrict__ pt, long long count4) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count4; i += stride) {
+        const float4 a = Vec4<float>::load(dh + i * 4), b = Vec4<float>::load(oh + i * 4);
+        Vec4<float>::store(ph + i * 4, make_float4(a.x * (1.f - b.x * b.x), a.y * (1.f - b.y * b.y),
+                                                   a.z * (1.f - b.z * b.z), a.w * (1.f - b.w * b.w)));
+        const float4 c = Vec4<float>::load(dt + i * 4), e = Vec4<float>::load(ot + i * 4);
+        Vec4<float>::store(pt + i * 4, make_float4(c.x * (1.f - e.x * e.x), c.y * (1.f - e.y * e.y),
+                                                   c.z * (1.f - e.z * e.z), c.w * (1.f - e.w * e.w)));
+    }
+}
+
+int launch_pair_dense_fwd(const gcgcn_batch* bt, const float* U, const float* Vd, const int* h_idx, const int* t_idx,
+                          const int* dis_h, const int* dis_t, float* out_h, float* out_t, cudaStream_t st) {
+    if (bt->total_pairs == 0) return GCGCN_OK;
+    const int blocks = static_cast<int>(std::min<long long>((bt->total_pairs + 7) / 8, static_cast<long long>(sm_count()) * 8));
+    pair_dense_fwd_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(U), reinterpret_cast<const float4*>(Vd),
+                                                  h_idx, t_idx, dis_h, dis_t, out_h, out_t, bt->total_pairs);
+    GCGCN_CHECK_LAUNCH("pair_dense_fwd");
+    return GCGCN_OK;
+}
+
+// dU[r] = sum of dpre over the pairs that read node row r, dVd[k] likewise for distance row k: the segmented sums of
+// the gather backward (same kernels, 128 columns each) applied to dpre = dout (1 - out^2), which lives in `dpre`
+// (caller-owned, 2 * total_pairs * 128 floats).
+int launch_pair_dense_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, const float* out_h,
+                          const float* out_t, int dis_rows, const int* dis_h, const int* dis_t, float* dU, float* dVd,
+                          float* dpre, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (bt->total_nodes == 0) return GCGCN_OK;
+    float* ph = dpre;
+    float* pt = dpre + static_cast<size_t>(bt->total_pairs) * D;
+    const long long count4 = bt->total_pairs * (D / 4);
+    if (count4 > 0) {
+        const int blocks = static_cast<int>(std::min<long long>((count4 + 255) / 256, static_cast<long long>(sm_count()) * 16));
+        tanh_bwd2_kernel<<<blocks, 256, 0, st>>>(dout_h, dout_t, out_h, out_t, ph, pt, count4);
+        GCGCN_CHECK_LAUNCH("pair_dense_tanh_bwd");
+    }
+    pair_gather_bwd_feat_kernel<<<bt->total_nodes, 128, 0, st>>>(
+        bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), bt->row_doc, ph, pt, D / 4, D / 4, dU);
+    GCGCN_CHECK_LAUNCH("pair_dense_bwd_rows");
+    const int cells = dis_rows * D;
+    long long warps = std::min<long long>(pair_dis_warps(), std::max<long long>(1, bt->total_pairs / 64));
+    const int wpb = DIS_BWD_THREADS / WARP;
+    const int blocks = ceil_div(warps, wpb);
+    warps = static_cast<long long>(blocks) * wpb;
+    const long long ppw = (bt->total_pairs + warps - 1) / warps;
+    const size_t need = static_cast<size_t>(warps) * cells * sizeof(float);
+    if (ws == nullptr || ws_bytes < need)
+        return fail(GCGCN_ERR_WORKSPACE, "pair_dense_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    const size_t smem = static_cast<size_t>(wpb) * cells * sizeof(float);
+    if (smem > 48 * 1024)
+        return fail(GCGCN_ERR_UNSUPPORTED, "pair_dense_bwd: distance table of %d rows too large", dis_rows);
+    pair_gather_bwd_dis_kernel<<<blocks, DIS_BWD_THREADS, smem, st>>>(ph, pt, 0, D, dis_rows, dis_h, dis_t,
+                                                                       bt->total_pairs, ppw, static_cast<float*>(ws));
+    GCGCN_CHECK_LAUNCH("pair_dense_bwd_dis");
+    return launch_reduce_partials(static_cast<const float*>(ws), static_cast<int>(warps), cells, dVd, cells, nullptr, st);
+}
+
 }  // namespace gcgcn

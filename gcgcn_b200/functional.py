@@ -438,6 +438,43 @@ class PairGatherFn(Function):
         return dfeat, ddis, None, None
 
 
+class PairDenseFn(Function):
+    """entity_feature_h/t = tanh(U[h_idx] + Vd[dis_h]), tanh(U[t_idx] + Vd[dis_t])  (G:351-355 with dense_layer split by
+    input columns; U = F W_F^T, Vd = dis_embed W_d^T + b are node-level and come from the caller)."""
+
+    @staticmethod
+    def forward(ctx, U, Vd, tables: PairTables, batch: RaggedBatch):
+        U, Vd = _cuda(U, "U"), _cuda(Vd, "Vd")
+        if U.shape != (batch.total_nodes, D) or Vd.shape[1] != D:
+            raise _lib.GcgcnError(f"pair_dense: U must be [{batch.total_nodes}, {D}] and Vd [rows, {D}]")
+        if not tables.has_dis:
+            raise _lib.GcgcnError("PairTables were built without node_relative_pos")
+        dev = U.device
+        out_h = torch.empty(batch.total_pairs, D, device=dev)
+        out_t = torch.empty(batch.total_pairs, D, device=dev)
+        _lib.call("gcgcn_pair_dense_fwd", batch.ref, _p(U), _p(Vd), _p(tables.h_idx), _p(tables.t_idx),
+                  _p(tables.dis_h), _p(tables.dis_t), _p(out_h), _p(out_t), _stream(dev))
+        ctx.save_for_backward(out_h, out_t)
+        ctx.cfg = (tables, batch, Vd.shape[0])
+        return out_h, out_t
+
+    @staticmethod
+    def backward(ctx, dh, dt):
+        out_h, out_t = ctx.saved_tensors
+        tables, batch, rows = ctx.cfg
+        dev = out_h.device
+        dh = torch.zeros_like(out_h) if dh is None else _cuda(dh, "dout_h")
+        dt = torch.zeros_like(out_t) if dt is None else _cuda(dt, "dout_t")
+        dU = torch.empty(batch.total_nodes, D, device=dev)
+        dVd = torch.empty(rows, D, device=dev)
+        dpre = torch.empty(2 * batch.total_pairs, D, device=dev)
+        wsb = int(_lib.load().gcgcn_pair_dense_ws_bytes(rows))
+        ws = workspace(dev, wsb)
+        _lib.call("gcgcn_pair_dense_bwd", batch.ref, _p(dh), _p(dt), _p(out_h), _p(out_t), rows, _p(tables.dis_h),
+                  _p(tables.dis_t), _p(dU), _p(dVd), _p(dpre), ws.data_ptr(), ws.numel(), _stream(dev))
+        return dU, dVd, None, None
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, trans_a=False, trans_b=False, bias=None,
          out: Optional[torch.Tensor] = None, alpha=1.0, beta=0.0) -> torch.Tensor:
     """Thin test hook over gcgcn_gemm (row-major fp32)."""

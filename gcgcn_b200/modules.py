@@ -25,7 +25,7 @@ from torch import nn
 
 from . import _lib
 from .batch import PairTables, PoolTable, RaggedBatch, single_doc_batch
-from .functional import (CaggcFn, EdgeMeanFn, GatFn, MhaFn, MhaStackFn, PackStackFn, PairGatherFn, PoolFn, StackFn,
+from .functional import (CaggcFn, EdgeMeanFn, GatFn, MhaFn, MhaStackFn, PackStackFn, PairDenseFn, PairGatherFn, PoolFn, StackFn,
                          block_supported)
 
 HIDDEN = 128
@@ -404,3 +404,17 @@ def pair_gather(node_feats_with_type: torch.Tensor, dis_embed: Optional[torch.Te
                 batch: RaggedBatch):
     """Classifier-side h/t pair tensors (G:351-352); ``dis_embed=None`` gives the in-loop form (G:321-322)."""
     return PairGatherFn.apply(node_feats_with_type, dis_embed, tables, batch)
+
+
+def pair_dense(node_feats_with_type: torch.Tensor, dense_layer: nn.Linear, dis_embed: torch.Tensor,
+               tables: PairTables, batch: RaggedBatch):
+    """entity_feature_h, entity_feature_t of G:351-355 -- ``tanh(dense_layer(cat(F[j], dis[10 + rp])))`` and
+    ``tanh(dense_layer(cat(F[i], dis[10 - rp])))`` -- without forming the two gathered ``[n, n, 424]`` tensors:
+    ``dense_layer`` is split by input columns into a node part and a distance part, both applied at node / table
+    level (``[rows, 404] x [404, 128]`` and ``[21, 20] x [20, 128]``, plain library products), and one kernel adds
+    the two 128-vectors per pair and applies tanh.  Same values as ``tanh(dense_layer(pair_gather(...)))``."""
+    fw = node_feats_with_type.shape[1]
+    w = dense_layer.weight
+    U = torch.nn.functional.linear(node_feats_with_type, w[:, :fw])
+    Vd = torch.nn.functional.linear(dis_embed, w[:, fw:], dense_layer.bias)
+    return PairDenseFn.apply(U, Vd, tables, batch)

@@ -238,6 +238,21 @@ int gcgcn_pair_gather_bwd(const gcgcn_batch* bt, const float* dout_h, const floa
                           const int32_t* dis_h, const int32_t* dis_t,
                           float* dfeat, float* ddis, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- classifier-side pair features without the gathered intermediate (first half) ----
+ * Replaces G:351-355: entity_feature_h[i,j] = tanh(dense_layer(cat(F[j], dis[10 + rp_ij]))) = tanh(U[j] + Vd[10 + rp_ij])
+ * and entity_feature_t[i,j] = tanh(U[i] + Vd[10 - rp_ij]), with U = F W_F^T [total_nodes, 128] and
+ * Vd = dis_embed W_d^T + bias [dis_rows, 128] (dense_layer.weight split by input columns; both computed by the caller,
+ * node-level work).  Index tables as for gcgcn_pair_gather_fwd.  out_h / out_t: [total_pairs, 128].
+ * bwd: dU, dVd = segmented sums of dout (1 - out^2) (deterministic); dpre is caller-owned scratch of
+ * 2 * total_pairs * 128 floats, ws of gcgcn_pair_dense_ws_bytes(dis_rows) bytes.                                  */
+int gcgcn_pair_dense_fwd(const gcgcn_batch* bt, const float* U, const float* Vd, const int32_t* h_idx,
+                         const int32_t* t_idx, const int32_t* dis_h, const int32_t* dis_t, float* out_h, float* out_t,
+                         void* stream);
+size_t gcgcn_pair_dense_ws_bytes(int32_t dis_rows);
+int gcgcn_pair_dense_bwd(const gcgcn_batch* bt, const float* dout_h, const float* dout_t, const float* out_h,
+                         const float* out_t, int32_t dis_rows, const int32_t* dis_h, const int32_t* dis_t, float* dU,
+                         float* dVd, float* dpre, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- block-level composites (SURVEY.md section 8b minimum set) ---------------------------
  * CAGGC = a2 + a4 sharing one pass over e0 (G:330-333); MAGGC = a5 + a6 (G:336-337).
  * They call the entry points above in order with buffers carved from `ws`; `saved` is a
