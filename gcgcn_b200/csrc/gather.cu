@@ -229,15 +229,31 @@ pair_dense_fwd_kernel(const float4* __restrict__ U, const float4* __restrict__ V
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    for (long long p = warp; p < total_pairs; p += nwarps) {
-        const float4 uh = __ldg(U + static_cast<size_t>(h_idx[p]) * (D / 4) + lane);
-        const float4 ut = __ldg(U + static_cast<size_t>(t_idx[p]) * (D / 4) + lane);
-        const float4 vh = __ldg(Vd + static_cast<size_t>(dis_h[p]) * (D / 4) + lane);
-        const float4 vt = __ldg(Vd + static_cast<size_t>(dis_t[p]) * (D / 4) + lane);
+    // two pairs per trip: eight index loads, then eight 512-byte row reads in flight, then four row stores
+    for (long long p = warp; p < total_pairs; p += 2 * nwarps) {
+        const long long p2 = p + nwarps;
+        const bool two = p2 < total_pairs;
+        const long long q = two ? p2 : p;
+        const int ih = h_idx[p], it = t_idx[p], kh = dis_h[p], kt = dis_t[p];
+        const int jh = h_idx[q], jt = t_idx[q], lh = dis_h[q], lt = dis_t[q];
+        const float4 uh = __ldg(U + static_cast<size_t>(ih) * (D / 4) + lane);
+        const float4 ut = __ldg(U + static_cast<size_t>(it) * (D / 4) + lane);
+        const float4 vh = __ldg(Vd + static_cast<size_t>(kh) * (D / 4) + lane);
+        const float4 vt = __ldg(Vd + static_cast<size_t>(kt) * (D / 4) + lane);
+        const float4 wh = __ldg(U + static_cast<size_t>(jh) * (D / 4) + lane);
+        const float4 wt = __ldg(U + static_cast<size_t>(jt) * (D / 4) + lane);
+        const float4 xh = __ldg(Vd + static_cast<size_t>(lh) * (D / 4) + lane);
+        const float4 xt = __ldg(Vd + static_cast<size_t>(lt) * (D / 4) + lane);
         Vec4<float>::store(out_h + static_cast<size_t>(p) * D + lane * 4,
                            make_float4(fast_tanh(uh.x + vh.x), fast_tanh(uh.y + vh.y), fast_tanh(uh.z + vh.z), fast_tanh(uh.w + vh.w)));
         Vec4<float>::store(out_t + static_cast<size_t>(p) * D + lane * 4,
                            make_float4(fast_tanh(ut.x + vt.x), fast_tanh(ut.y + vt.y), fast_tanh(ut.z + vt.z), fast_tanh(ut.w + vt.w)));
+        if (two) {
+            Vec4<float>::store(out_h + static_cast<size_t>(p2) * D + lane * 4,
+                               make_float4(fast_tanh(wh.x + xh.x), fast_tanh(wh.y + xh.y), fast_tanh(wh.z + xh.z), fast_tanh(wh.w + xh.w)));
+            Vec4<float>::store(out_t + static_cast<size_t>(p2) * D + lane * 4,
+                               make_float4(fast_tanh(wt.x + xt.x), fast_tanh(wt.y + xt.y), fast_tanh(wt.z + xt.z), fast_tanh(wt.w + xt.w)));
+        }
     }
 }
 
