@@ -217,6 +217,18 @@ static int launch_add(float* dst, const float* src, size_t n, cudaStream_t st) {
     return GCGCN_OK;
 }
 
+// Wsum[d][c] = sum_h Wout[d][h * 128 + c]: with dF = dy Wout, the residual's share sum_h dF_h of dx is dy Wsum -- a
+// [rows, 128] x [128, 128] product instead of a pass over the [rows, heads * 128] slab
+__global__ void __launch_bounds__(256)
+wout_head_sum_kernel(const float* __restrict__ Wout, int heads, float* __restrict__ Wsum) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // over D * D
+    if (idx >= D * D) return;
+    const int d = idx / D, c = idx - d * D;
+    float acc = 0.f;
+    for (int h = 0; h < heads; ++h) acc += Wout[static_cast<size_t>(d) * heads * D + h * D + c];
+    Wsum[idx] = acc;
+}
+
 static int launch_head_sum(const float* dF, int heads, int rows, float* dx, cudaStream_t st) {
     if (rows == 0) return GCGCN_OK;
     const size_t total = static_cast<size_t>(rows) * (D / 4);
@@ -258,6 +270,7 @@ size_t gcgcn_workspace_bytes(int32_t total_nodes, int64_t total_pairs, int32_t h
     b += 2 * align256(nodes * D * sizeof(float));                      // dq / ux / misc
     b += GEMM_WS_BYTES + (size_t(8) << 20);                            // split-K and reduction partials
     b += size_t(4) << 20;                                              // fragment-ordered dense-connect weights
+    b += size_t(256) << 10;                                            // head-summed output weights
     b += align256(gemm_presplit_bytes(total_nodes < 0 ? 0 : total_nodes));   // pre-split [rows,128] operand of the weight-gradient GEMMs
     return b;
 }
@@ -560,7 +573,14 @@ static int stack_bwd_impl(const gcgcn_batch* bt, int32_t heads, int32_t layers, 
     // dx = [residual: sum_h dF_h] + dZ WnX^T ; debar = dE We^T
     float beta = 0.f;
     if (flags & GCGCN_STACK_RESIDUAL) {
-        GCGCN_TRY(launch_head_sum(dF, heads, M, dx, st));
+        float* Wsum = (linear && heads > 1 && slab == D && in_dim == D) ? ar.take<float>(static_cast<size_t>(D) * D) : nullptr;
+        if (Wsum != nullptr) {
+            wout_head_sum_kernel<<<ceil_div(D * D, 256), 256, 0, st>>>(Wout, heads, Wsum);
+            GCGCN_CHECK_LAUNCH("wout_head_sum");
+            GCGCN_TRY(launch_gemm(0, 0, M, D, D, 1.f, dy, D, Wsum, D, 0.f, dx, D, nullptr, gws, GEMM_WS_BYTES, st));
+        } else {
+            GCGCN_TRY(launch_head_sum(dF, heads, M, dx, st));
+        }
         beta = 1.f;
     }
     GCGCN_TRY(launch_gemm(0, 1, M, in_dim, HD, 1.f, dZ, HD, WnX, HD, beta, dx, in_dim, nullptr, gws, GEMM_WS_BYTES, st));
