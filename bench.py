@@ -180,9 +180,12 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "variant": args.variant, "layer_num": layers,
-                   "head_num": heads, "step": "reference arm: one step = one pass over the 12-document "
-                                             "batch on the host cores (bounded sample of the workload)"},
+        "config": {"workload": f"configs[1]: GCGCN_{args.variant} graph blocks fwd+bwd, the 12-document DocRED-shaped "
+                               "batch (n=42..5, SURVEY 8d), 12 documents per step on the host cores -- a bounded "
+                               "sample of the GPU arm's workload (the same batch x 512 per GPU per step)",
+                   "variant": args.variant, "layer_num": layers, "head_num": heads, "docs_per_step": len(docs),
+                   "step": "reference arm: one step = one pass over the 12-document batch, one document at a "
+                           "time as the reference trainer does (C:339)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "12-document batch per step, fwd+bwd, one document at a time; "
                                    "oracle/gcgcn_oracle.py (same ATen ops as the reference, pinned bit-exact)"},
@@ -409,8 +412,7 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG=VERSION
-        os.environ["NCCL_DEBUG"] = os.environ.get("GCGCN_NCCL_DEBUG", "WARN")
+        # NCCL_DEBUG is left as the environment sets it: claim_stdout() already keeps NCCL's banner off stdout
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -540,8 +542,6 @@ def run_gpu_arm(args):
         copy_stream = torch.cuda.Stream(dev)
         ready = [torch.cuda.Event(), torch.cuda.Event()]      # the inputs of set s are on the device
         freed = [torch.cuda.Event(), torch.cuda.Event()]      # the compute that read set s is done
-        counter = {"i": 0}
-
         def stage(sidx):
             with torch.cuda.stream(copy_stream), torch.no_grad():
                 copy_stream.wait_event(freed[sidx])
@@ -549,13 +549,20 @@ def run_gpu_arm(args):
                     dv.copy_(h, non_blocking=True)
                 ready[sidx].record(copy_stream)
 
+        # One window = `count` steps and exactly `count` host->device input copies, ALL inside the window: step 0
+        # stages its own inputs after the window opened, step i stages step i+1's (overlapping step i's kernels) and
+        # the last step stages nothing, so when the closing event is recorded on the main stream -- after the last
+        # step's device->host reads, which are issued on it -- the copy stream is idle as well.
+        window = {"i": 0, "count": 0}
+
         def e2e_step():
-            i = counter["i"]
+            i = window["i"]
             sidx = i % 2
             main = torch.cuda.current_stream(dev)
             if i == 0:
                 stage(sidx)
-            stage(1 - sidx)                                   # next step's inputs: overlaps this step's kernels
+            if i + 1 < window["count"]:
+                stage(1 - sidx)                               # next step's inputs: overlaps this step's kernels
             main.wait_event(ready[sidx])
             out = run_step(sets[sidx])
             if world == 1:
@@ -565,17 +572,26 @@ def run_gpu_arm(args):
             host_out["dx0"].copy_(sets[sidx][0].grad, non_blocking=True)
             host_grads.copy_(bucket.flat, non_blocking=True)
             freed[sidx].record(main)
-            counter["i"] = i + 1
+            window["i"] = i + 1
 
-        e2e_step()
-        e2e_steps = max(2, min(args.steps, 5))
-        ms_e, _, _ = timed(e2e_step, e2e_steps)
+        def e2e_window(count):
+            window.update(i=0, count=count)
+            copy_stream.synchronize()
+            ms_w, _, _ = timed(e2e_step, count)
+            copy_stream.synchronize()
+            return ms_w
+
+        e2e_window(2)                                         # warm-up window (pinned pages touched, pools grown)
+        e2e_steps = max(20, args.steps)
+        ms_e = e2e_window(e2e_steps)
         e2e = {"value": world * ndocs * e2e_steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / e2e_steps,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
+               "h2d_gbs": h2d * e2e_steps / (ms_e * 1e-3) / 1e9,
                "note": "inputs x0,e0,e1,dy1,dy2 from pinned host memory (double-buffered on the device: the copy of "
-                       "step i+1 overlaps the kernels of step i; one full input copy per timed step); y1,y2,dx0 and "
-                       "the parameter-gradient bucket read back; de0/de1 stay on the device (their consumer, the "
-                       "edge-feature producer's backward, lives there)"}
+                       "step i+1 overlaps the kernels of step i); the timed window holds exactly one full input copy "
+                       "per step, none staged before it opens, and closes after the last device->host read; "
+                       "y1,y2,dx0 and the parameter-gradient bucket read back; de0/de1 stay on the device (their "
+                       "consumer, the edge-feature producer's backward, lives there)"}
 
     if rank != 0:
         if world > 1:
@@ -612,16 +628,26 @@ def run_gpu_arm(args):
         traffic = None
         if tr and "dram_bytes_per_step" in tr:      # ncu dram__bytes_read+write of this kernel, same workload
             traffic = tr["dram_bytes_per_step"] * args.steps / max(cnt, 1)
-        top = dict(rl)
-        top.update({"kernel": name, "traffic": traffic, "traffic_source": tr.get("source") if tr else None,
+        dom = dict(rl)
+        dom.update({"kernel": name, "traffic": traffic, "traffic_source": tr.get("source") if tr else None,
                     "launches_per_step": cnt / args.steps, "us_per_launch": tot_ms * 1e3 / cnt,
-                    "share_of_step": tot_ms / total_k, "peak_source": peak_src,
-                    "timing": "per-launch CUDA events recorded by the library on the launching stream during "
-                              "an eager pass of the same K steps",
-                    "path_bytes_per_step": alg, "path_achieved": path_gbs, "path_frac": path_gbs / hbm_peak,
-                    "path_note": "whole step: SURVEY 8d algorithmic bytes s*d*(5n^2+8n) per document / step time "
-                                 "vs the measured HBM peak",
-                    "kernels": breakdown})
+                    "share_of_step": tot_ms / total_k,
+                    "bytes_model": "every operand of the kernel once, incl. the [rows, H*128] intermediates it reads "
+                                   "and writes (NOT SURVEY 8d algorithmic bytes: those are the edge streams' only)"})
+        tot = traffic_tab.get("(whole step)")
+        traffic_total = tot.get("dram_bytes_per_step") if tot else None
+        # headline roofline = the whole hot path: SURVEY 8d algorithmic bytes of one step / step time against the
+        # measured HBM peak; the dominant kernel's own (operand-byte) roofline and the per-kernel table explain it
+        top = {"bound": "hbm", "achieved": path_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": path_gbs / hbm_peak,
+               "traffic": traffic_total, "traffic_total": traffic_total,
+               "traffic_source": tot.get("source") if tot else None,
+               "scope": "whole step (one pass of the hot path over the shard = one 'launch'): SURVEY 8d algorithmic "
+                        "bytes s*d*(5n^2+8n) per document / step time vs the measured HBM peak",
+               "path_bytes_per_step": alg, "path_achieved": path_gbs, "path_frac": path_gbs / hbm_peak,
+               "peak_source": peak_src,
+               "timing": "step: CUDA events around the K timed steps; per-kernel: per-launch CUDA events recorded by "
+                         "the library on the launching stream during an eager pass of the same K steps",
+               "dominant_kernel": dom, "kernels": breakdown}
 
     aux = None
     if not args.no_aux and not args.nodes:
@@ -637,9 +663,9 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "variant": args.variant, "layer_num": layers, "head_num": heads,
-                   "edge_storage": args.dtype, "docs_per_gpu": ndocs, "total_nodes": bt.total_nodes,
+                   "edge_storage": args.dtype, "accumulate": "fp32", "docs_per_gpu": ndocs, "total_nodes": bt.total_nodes,
                    "total_pairs": bt.total_pairs, "parallelism": f"doc-sharded dp{world}",
                    "l2": f"inputs larger than L2: {2 * bt.total_pairs * 128 * esz / 1e9:.2f} GB of edge features "
                          "streamed per step",
@@ -685,7 +711,6 @@ def run_training_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("GCGCN_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     layers, heads = VARIANTS[args.variant]

@@ -51,21 +51,40 @@ def sources():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into the in-tree shared library (nvcc
-    cross-compiles without a GPU).  Skipped when the library is newer than its sources."""
+    """Compile every CUDA source for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU).
+    One object per source under build/obj (compiled in parallel, each only when older than its source or any
+    header), then one link; skipped entirely when the library is newer than everything."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
-    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    newest_hdr = max(os.path.getmtime(p) for p in hdrs)
     if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(p) for p in deps)
-        if os.path.getmtime(LIB_PATH) >= newest:
+        if os.path.getmtime(LIB_PATH) >= max([newest_hdr] + [os.path.getmtime(p) for p in srcs]):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + srcs
-    if verbose:
-        print(" ".join(cmd))
+    objdir = os.path.join(os.path.dirname(_HERE), "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(newest_hdr, os.path.getmtime(src)):
+            return obj, None
+        cmd = [nvcc] + compile_flags + ["-I", INCLUDE, "-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, (None if res.returncode == 0 else res.stdout + res.stderr)
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    errors = [e for _, e in results if e]
+    if errors:
+        raise GcgcnError("nvcc failed:\n" + "\n".join(errors))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + [o for o, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise GcgcnError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise GcgcnError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

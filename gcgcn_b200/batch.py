@@ -235,9 +235,18 @@ class PairTables:
         self.has_dis = rel_pos is not None
         self.dis_h_host = cat(dh) if self.has_dis else None
         self.dis_t_host = cat(dt) if self.has_dis else None
+        # range of the distance rows the tables address; checked against the embedding's row count by the callers
+        # (an out-of-range row would read, and in the backward write, out of bounds on the device)
+        self.dis_min = int(min(self.dis_h_host.min(), self.dis_t_host.min())) if self.has_dis and self.dis_h_host.size else 0
+        self.dis_max = int(max(self.dis_h_host.max(), self.dis_t_host.max())) if self.has_dis and self.dis_h_host.size else 0
         self.device = None
         if device is not None:
             self.to(device)
+
+    def check_dis_rows(self, rows: int):
+        if self.has_dis and (self.dis_min < 0 or self.dis_max >= rows):
+            raise _lib.GcgcnError(f"PairTables address distance rows {self.dis_min}..{self.dis_max} but the table has "
+                                  f"{rows} rows (dis_plus +/- node_relative_pos must stay inside the embedding, G:306-307)")
 
     def to(self, device):
         self.device = torch.device(device)

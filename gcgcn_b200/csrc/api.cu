@@ -919,6 +919,7 @@ int gcgcn_caggc_fwd(const gcgcn_batch* bt, int32_t layers, const float* x, const
                     const float* u, const float* v, const float* c, const float* WnX, const float* We,
                     const float* Winner, const float* Wout, const float* bout, float* y, void* saved,
                     const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
+    ::gcgcn::StreamDeviceGuard outer_guard__(static_cast<cudaStream_t>(stream));   // composite: covers its own launches too
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     BlockDrop drop;
@@ -942,6 +943,7 @@ int gcgcn_caggc_bwd(const gcgcn_batch* bt, int32_t layers, const float* x, const
                     const float* Wout, const float* dy, const void* saved, float* dx, void* de, float* du,
                     float* dv, float* dc, float* dWnX, float* dWe, float* dWinner, float* dWout, float* dbout,
                     const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
+    ::gcgcn::StreamDeviceGuard outer_guard__(static_cast<cudaStream_t>(stream));   // composite: covers its own launches too
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     BlockDrop drop;
@@ -981,6 +983,7 @@ int gcgcn_maggc_fwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
                     int32_t edge_dtype, const float* Wq, const float* bq, const float* WnX, const float* We,
                     const float* Winner, const float* Wout, const float* bout, float* y, void* saved,
                     const gcgcn_dropout* dropout, void* ws, size_t ws_bytes, void* stream) {
+    ::gcgcn::StreamDeviceGuard outer_guard__(static_cast<cudaStream_t>(stream));   // composite: covers its own launches too
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     MagSaved s = carve_mag(saved, bt->total_nodes, bt->total_pairs, heads);
@@ -1000,6 +1003,7 @@ int gcgcn_maggc_bwd(const gcgcn_batch* bt, int32_t layers, int32_t heads, const 
                     const float* dy, const void* saved, float* dx, void* de, float* dWq, float* dbq, float* dWnX,
                     float* dWe, float* dWinner, float* dWout, float* dbout, const gcgcn_dropout* dropout, void* ws,
                     size_t ws_bytes, void* stream) {
+    ::gcgcn::StreamDeviceGuard outer_guard__(static_cast<cudaStream_t>(stream));   // composite: covers its own launches too
     GCGCN_TRY(check_batch(bt));
     GCGCN_TRY(check_device_ptr(saved, "saved"));
     MagSaved s = carve_mag(const_cast<void*>(saved), bt->total_nodes, bt->total_pairs, heads);

@@ -41,7 +41,39 @@ inline int cuda_ok(cudaError_t e, const char* what) {
         if (rc__ != GCGCN_OK) return rc__;                              \
     } while (0)
 
+// Every entry point launches on the device that owns `stream`, whatever the calling thread's current device is
+// (a stream of cuda:1 handed in while cuda:0 is current used to launch into the wrong context); the previous
+// device is restored when the entry point returns.  The legacy default stream (NULL) keeps the current device.
+struct StreamDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit StreamDeviceGuard(cudaStream_t st) {
+        int dev = -1;
+        if (st == nullptr) return;
+        if (cudaStreamGetDevice(st, &dev) != cudaSuccess) { cudaGetLastError(); return; }
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+        if (prev != dev && cudaSetDevice(dev) == cudaSuccess) switched = true;
+    }
+    ~StreamDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    StreamDeviceGuard(const StreamDeviceGuard&) = delete;
+    StreamDeviceGuard& operator=(const StreamDeviceGuard&) = delete;
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: one bit per device ordinal records
+// where a kernel has been prepared (a process that touches a second GPU prepares it there on first use).
+inline bool device_prepared(const std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    return (mask.load(std::memory_order_acquire) >> dev) & 1ULL;
+}
+inline void device_mark_prepared(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    mask.fetch_or(1ULL << dev, std::memory_order_release);
+}
+
 #define GCGCN_API_ENTER(stream)                                                          \
+    ::gcgcn::StreamDeviceGuard device_guard__(static_cast<cudaStream_t>(stream));        \
     do {                                                                                 \
         if (::gcgcn::g_timing.load(std::memory_order_relaxed))                           \
             ::gcgcn::timing_mark("(between calls)", static_cast<cudaStream_t>(stream));  \

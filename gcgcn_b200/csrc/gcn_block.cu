@@ -807,8 +807,8 @@ static int launch_fwd_class(const gcgcn_batch* bt, int heads, int count, int fir
                             float* G, float* F, float scale, const BlockDrop& drop, cudaStream_t st) {
     constexpr int layers = D / GD;
     const size_t smem = block_fwd_smem(16 * MTC, layers, GD);
-    static bool ready = false;
-    if (!ready) { GCGCN_TRY(prepare_kernel(block_fwd_kernel<GD, DH, MTC>, smem, "block_fwd")); ready = true; }
+    static std::atomic<unsigned long long> ready{0};        // per device: the attribute is a per-device setting
+    if (!device_prepared(ready)) { GCGCN_TRY(prepare_kernel(block_fwd_kernel<GD, DH, MTC>, smem, "block_fwd")); device_mark_prepared(ready); }
     block_fwd_kernel<GD, DH, MTC><<<dim3(count, heads), BK_THREADS, smem, st>>>(
         bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), A, q, P, Z, E, Winner, x, G, F, heads,
         bt->total_pairs, order, first, scale, drop);
@@ -868,8 +868,8 @@ static int launch_bwd_class(const gcgcn_batch* bt, int heads, int count, int fir
                             float* dZ, float* dE, float* dOut, float scale, const BlockDrop& drop, cudaStream_t st) {
     constexpr int layers = D / GD;
     const size_t smem = block_bwd_smem(16 * MTC, layers, GD);
-    static bool ready = false;
-    if (!ready) { GCGCN_TRY(prepare_kernel(block_bwd_kernel<GD, DH, OUT, MTC>, smem, "block_bwd")); ready = true; }
+    static std::atomic<unsigned long long> ready{0};
+    if (!device_prepared(ready)) { GCGCN_TRY(prepare_kernel(block_bwd_kernel<GD, DH, OUT, MTC>, smem, "block_bwd")); device_mark_prepared(ready); }
     block_bwd_kernel<GD, DH, OUT, MTC><<<dim3(count, heads), BK_THREADS, smem, st>>>(
         bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), A, q, Z, G, Winner, dF, dZ, dE, dOut, heads,
         bt->total_pairs, order, first, scale, drop);

@@ -954,12 +954,12 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     const bool a_kc = !ta, b_kc = (tb != 0);
 #define GCGCN_TC_LAUNCH(AK, BK, G, ...)                                                                  \
     do {                                                                                                 \
-        static bool attr_done = false;                                                                   \
-        if (!attr_done) {                                                                                \
+        static std::atomic<unsigned long long> attr_done{0};                                             \
+        if (!device_prepared(attr_done)) {                                                               \
             GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, G, __VA_ARGS__>,               \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                                    static_cast<int>(TC_SMEM_BYTES)), "gemm_tc smem"));   \
-            attr_done = true;                                                                            \
+            device_mark_prepared(attr_done);                                                             \
         }                                                                                                \
         gemm_tc_kernel<AK, BK, G, __VA_ARGS__><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);           \
     } while (0)
@@ -967,19 +967,19 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     const bool resa = bpre && resa_on && a.kblocks <= RA_KB && a.tiles_n >= 2 && a.partial == nullptr;
     static const bool tmema_on = getenv("GCGCN_GEMM_TMEMA") == nullptr || getenv("GCGCN_GEMM_TMEMA")[0] != '0';   // =0: shared-memory resident-A kernel
     if (resa && tmema_on && !ta) {
-        static bool attr_done2 = false;
-        if (!attr_done2) {
+        static std::atomic<unsigned long long> attr_done2{0};
+        if (!device_prepared(attr_done2)) {
             GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_tmema smem"));
-            attr_done2 = true;
+            device_mark_prepared(attr_done2);
         }
         gemm_tc_tmema_kernel<<<std::min(sms, a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
     } else if (resa) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (!device_prepared(attr_done)) {
             GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_resa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(RA_SMEM_BYTES)), "gemm_tc_resa smem"));
-            attr_done = true;
+            device_mark_prepared(attr_done);
         }
         gemm_tc_resa_kernel<<<std::min(sms, a.tiles_m), RA_THREADS, RA_SMEM_BYTES, st>>>(a);
     } else if (apre) GCGCN_TC_LAUNCH(false, false, 2, false, true);

@@ -413,6 +413,7 @@ class PairGatherFn(Function):
             dw = dis.shape[1]
             if not tables.has_dis:
                 raise _lib.GcgcnError("PairTables were built without node_relative_pos")
+            tables.check_dis_rows(dis.shape[0])
         dev = feat.device
         out_h = torch.empty(batch.total_pairs, fw + dw, device=dev)
         out_t = torch.empty(batch.total_pairs, fw + dw, device=dev)
@@ -449,6 +450,7 @@ class PairDenseFn(Function):
             raise _lib.GcgcnError(f"pair_dense: U must be [{batch.total_nodes}, {D}] and Vd [rows, {D}]")
         if not tables.has_dis:
             raise _lib.GcgcnError("PairTables were built without node_relative_pos")
+        tables.check_dis_rows(Vd.shape[0])
         dev = U.device
         out_h = torch.empty(batch.total_pairs, D, device=dev)
         out_t = torch.empty(batch.total_pairs, D, device=dev)

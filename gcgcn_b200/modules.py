@@ -17,6 +17,7 @@ Reference quirks that are reproduced on purpose:
 """
 from __future__ import annotations
 
+import threading
 import weakref
 from typing import List, Optional, Sequence
 
@@ -53,20 +54,27 @@ class _KeepMixin:
 
 # edge-mean hand-off between GATAttention.forward and the GraphConvolution.forward that follows it
 # on the same edge tensor (G:332-333): one pass over e serves both.
-_EBAR_SLOT = {"ref": None, "version": None, "ebar": None}
+# The slot is per thread and remembers the autograd mode it was filled under: an ebar stashed under no_grad (or
+# by another thread's model) has no history, and handing it to a grad-mode GraphConvolution would silently drop
+# the edge-mean term of de0 -- such a stash is ignored (and dropped), the mean is simply recomputed.
+_EBAR_TLS = threading.local()
 
 
 def _stash_ebar(edge: torch.Tensor, ebar: torch.Tensor):
-    _EBAR_SLOT.update(ref=weakref.ref(edge), version=edge._version, ebar=ebar)
+    _EBAR_TLS.slot = (weakref.ref(edge), edge._version, ebar, torch.is_grad_enabled(), ebar.requires_grad)
 
 
 def _take_ebar(edge: torch.Tensor) -> Optional[torch.Tensor]:
-    r = _EBAR_SLOT["ref"]
-    if r is not None and r() is edge and _EBAR_SLOT["version"] == edge._version:
-        ebar = _EBAR_SLOT["ebar"]
-        _EBAR_SLOT.update(ref=None, version=None, ebar=None)
-        return ebar
-    return None
+    slot = getattr(_EBAR_TLS, "slot", None)
+    _EBAR_TLS.slot = None                     # one consumer; never keeps a tensor (and its graph) alive longer
+    if slot is None:
+        return None
+    ref, version, ebar, grad_mode, had_grad = slot
+    if ref() is not edge or version != edge._version:
+        return None
+    if grad_mode != torch.is_grad_enabled() or (grad_mode and edge.requires_grad and not had_grad):
+        return None
+    return ebar
 
 
 def _pairs2d(edge: torch.Tensor) -> torch.Tensor:

@@ -54,8 +54,11 @@ class GradBucket:
     def all_reduce(self, group=None, average: bool = False, async_op: bool = False):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
+        if average and async_op:
+            raise ValueError("GradBucket.all_reduce: average=True needs the result; wait on an async_op=True "
+                             "all-reduce yourself and divide, or fold 1/world_size into the optimiser's grad_scale")
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-        if average and not async_op:
+        if average:
             self.flat.div_(dist.get_world_size(group))
         return work
 
@@ -129,13 +132,29 @@ class FlatTrainer:
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
                 p.grad = self.flat[o:o + s].view_as(p)
 
+    def _collect_detached(self):
+        """``module.zero_grad()`` / ``optimizer.zero_grad(set_to_none=True)`` drop the views, after which autograd
+        allocates fresh ``.grad`` tensors the bucket never sees.  Fold any such gradient into the bucket (and
+        re-attach the view) so that all_reduce() / step() never run on a stale, zeroed bucket."""
+        base = self.flat.data_ptr()
+        for p, o, s in zip(self.params, self.offsets, self.sizes):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + 4 * o:
+                continue
+            view = self.flat[o:o + s].view_as(p)
+            if g is not None:
+                view.add_(g)
+            p.grad = view
+
     def all_reduce(self, group=None, async_op: bool = False):
+        self._collect_detached()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     def step(self, grad_scale: float = 1.0):
         from . import _lib
+        self._collect_detached()
         if not self.flat.is_cuda:
             raise _lib.GcgcnError("FlatTrainer.step: gcgcn_b200 has no CPU path (parameters must live on a B200)")
         self.steps += 1

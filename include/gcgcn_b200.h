@@ -226,6 +226,10 @@ int gcgcn_unpack_stack_grads(const float* dWnX, const float* dWe, const float* d
  * for every pair p of the batch.  Index tables are int32 [total_pairs] holding *global* node
  * rows (h_idx[i,j] = node_ptr[b]+j, t_idx[i,j] = node_ptr[b]+i, quirk 6) and distance rows
  * (dis_plus +/- node_relative_pos), built by gcgcn_b200.batch.PairTables.
+ * h_idx / t_idx MUST be these canonical tables: the backward derives the same layout from the batch descriptor
+ * instead of reading them (segmented sums over the rows / columns of each pair grid), so any other table would get a
+ * forward/backward mismatch.  Every dis_h / dis_t entry must lie in [0, dis_rows): the host builder checks it
+ * (PairTables.check_dis_rows); the kernels do not.
  * feat_w and dis_w must be multiples of 4; dis_w may be 0 (in-loop gathers, G:321-322).
  * bwd: dfeat[r,:] = sum over pairs that gathered row r (segmented, deterministic);
  *      ddis[k,:]  = sum over pairs that gathered distance row k.                           */
