@@ -46,6 +46,18 @@ class Batch(ctypes.Structure):
     ]
 
 
+class EdgeTablesC(ctypes.Structure):
+    """struct gcgcn_edge_tables"""
+    _fields_ = [
+        ("num_tokens", c_int32), ("num_slots", c_int32), ("num_pairs", c_int32), ("att_total", c_int32),
+        ("dis_plus", c_int32), ("reserved", c_int32),
+        ("tok_first", c_void_p), ("tok_slot_lo", c_void_p), ("tok_slot_hi", c_void_p),
+        ("slot_tok0", c_void_p), ("slot_len", c_void_p), ("slot_span", c_void_p), ("slot_att", c_void_p),
+        ("slot_rowi", c_void_p), ("slot_rowj", c_void_p), ("pair_idx", c_void_p), ("pair_slot_ptr", c_void_p),
+        ("pair_denom", c_void_p), ("node_ctr_ptr", c_void_p), ("node_ctr", c_void_p),
+    ]
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -91,6 +103,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _P = c_void_p
 _BT = POINTER(Batch)
 _DP = POINTER(Dropout)
+_ET = POINTER(EdgeTablesC)
 
 # name -> (restype, argtypes); mirrors include/gcgcn_b200.h one to one
 SIGNATURES = {
@@ -136,6 +149,16 @@ SIGNATURES = {
     "gcgcn_maggc_bwd": (c_int32, [_BT, c_int32, c_int32, _P, c_int32] + [_P] * 5 + [_P, _P]
                         + [_P] * 9 + [_DP, _P, c_size_t, _P]),
     "gcgcn_expand_pair_context": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "gcgcn_edgefeat_ws_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int64]),
+    "gcgcn_word_table_fwd": (c_int32, [_P, _P, _P, _P, c_int32, _P, _P]),
+    "gcgcn_word_table_bwd": (c_int32, [_P, _P, _P, _P, c_int32, _P, _P, _P, c_size_t, _P]),
+    "gcgcn_word_pool_fwd": (c_int32, [_ET, _P, _P, _P, _P, _P]),
+    "gcgcn_word_pool_bwd": (c_int32, [_ET, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gcgcn_sent_pool_fwd": (c_int32, [_ET, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gcgcn_sent_pool_bwd": (c_int32, [_ET, c_int32] + [_P] * 10 + [_P, c_size_t, _P]),
+    "gcgcn_edge_fill_fwd": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, _P, _P]),
+    "gcgcn_edge_fill_bwd": (c_int32, [_P, _P, c_int32, c_int64, c_int32, _P, _P, _P, c_size_t, _P]),
+    "gcgcn_colsum": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P, c_size_t, _P]),
     "gcgcn_adam_step": (c_int32, [_P, _P, _P, _P, c_int64] + [c_float] * 6 + [c_int32, _P]),
     "gcgcn_gemm": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, c_int32, _P,
                              c_int32, c_float, _P, c_int32, _P, _P, c_size_t, _P]),

@@ -75,6 +75,27 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long count, f
 int launch_unpack_stack(const float* dWnX, const float* dWe, const float* dWinner, int heads, int layers, int slab,
                         float* dwn_flat, float* dwe_flat, cudaStream_t st);
 
+int launch_word_table_fwd(const float* SF, const float* DF, const float* wa, const float* ba, int tokens, float* T,
+                          cudaStream_t st);
+int word_table_parts(int tokens);
+int launch_word_table_bwd(const float* SF, const float* DF, const float* wa, const float* dT, int tokens, float* dSF,
+                          float* out, float* partial, cudaStream_t st);
+int launch_word_pool_fwd(const gcgcn_edge_tables* t, const float* T, const float* ctx, float* att, float* cwa,
+                         cudaStream_t st);
+int launch_word_pool_bwd(const gcgcn_edge_tables* t, const float* ctx, const float* att, const float* dcwa, float* dlog,
+                         float* dctx, float* dT, cudaStream_t st);
+int launch_sent_pool_fwd(const gcgcn_edge_tables* t, const float* cw, const float* sfeat, const float* nfeat,
+                         const float* va, const float* ca, float* score, float* csa, cudaStream_t st);
+int sent_pool_parts(int pairs);
+int launch_sent_pool_bwd(const gcgcn_edge_tables* t, int total_nodes, const float* cw, const float* sfeat,
+                         const float* nfeat, const float* va, const float* score, const float* dcsa, float* dcw,
+                         float* dsfeat, float* dnfeat, float* out, float* dpre, float* partial, cudaStream_t st);
+int launch_edge_fill_fwd(const float* bias, const float* rows, const void* pair_idx, int pairs, long long total_pairs,
+                         int dtype, void* e, cudaStream_t st);
+int edge_colsum_parts(long long total_pairs);
+int launch_edge_fill_bwd(const void* de, const void* pair_idx, int pairs, long long total_pairs, int dtype, float* drows,
+                         float* dbias, float* partial, cudaStream_t st);
+
 // ---- error text, launch counter, device cache --------------------------------------------------
 std::atomic<uint64_t> g_launches{0};
 std::atomic<bool> g_timing{false};
@@ -825,6 +846,181 @@ int gcgcn_pair_dense_bwd(const gcgcn_batch* bt, const float* dout_h, const float
     GCGCN_TRY(check_device_ptr(dpre, "dpre"));
     return launch_pair_dense_bwd(bt, dout_h, dout_t, out_h, out_t, dis_rows, dis_h, dis_t, dU, dVd, dpre, ws, ws_bytes,
                                  static_cast<cudaStream_t>(stream));
+}
+
+// ---- edge-feature producer ------------------------------------------------------------
+namespace {
+constexpr size_t WT_PARTIAL_FLOATS = 21 * D + D + 4, SP_PARTIAL_FLOATS = D + 4;
+int check_edge_tables(const gcgcn_edge_tables* t) {
+    if (t == nullptr) return fail(GCGCN_ERR_INVALID_ARG, "edge tables are NULL");
+    if (t->num_tokens < 0 || t->num_slots < 0 || t->num_pairs < 0 || t->att_total < 0)
+        return fail(GCGCN_ERR_INVALID_ARG, "negative size in edge tables");
+    if (t->num_slots > 0) {
+        GCGCN_TRY(check_device_ptr(t->slot_tok0, "tabs.slot_tok0"));
+        GCGCN_TRY(check_device_ptr(t->slot_len, "tabs.slot_len"));
+        GCGCN_TRY(check_device_ptr(t->slot_span, "tabs.slot_span"));
+        GCGCN_TRY(check_device_ptr(t->slot_att, "tabs.slot_att"));
+    }
+    return GCGCN_OK;
+}
+}  // namespace
+
+size_t gcgcn_edgefeat_ws_bytes(int32_t num_tokens, int32_t att_total, int32_t num_slots, int32_t num_pairs,
+                               int64_t total_pairs) {
+    size_t a = align256(static_cast<size_t>(word_table_parts(num_tokens)) * WT_PARTIAL_FLOATS * sizeof(float));
+    size_t b = align256(static_cast<size_t>(att_total < 0 ? 0 : att_total) * sizeof(float));
+    size_t c = align256(static_cast<size_t>(num_slots < 0 ? 0 : num_slots) * 2 * D * sizeof(float)) +
+               align256(static_cast<size_t>(sent_pool_parts(num_pairs)) * SP_PARTIAL_FLOATS * sizeof(float));
+    size_t d = align256(static_cast<size_t>(edge_colsum_parts(total_pairs < 0 ? 0 : total_pairs)) * D * sizeof(float));
+    size_t m = a > b ? a : b;
+    if (c > m) m = c;
+    if (d > m) m = d;
+    return m + (size_t(4) << 20);
+}
+
+int gcgcn_word_table_fwd(const float* SF, const float* DF, const float* wa, const float* ba, int32_t tokens, float* T,
+                         void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(tokens >= 0, "word_table_fwd: tokens < 0");
+    if (tokens == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(SF, "SF"));
+    GCGCN_TRY(check_device_ptr(DF, "DF"));
+    GCGCN_TRY(check_device_ptr(wa, "wa"));
+    GCGCN_TRY(check_device_ptr(ba, "ba"));
+    GCGCN_TRY(check_device_ptr(T, "T"));
+    return launch_word_table_fwd(SF, DF, wa, ba, tokens, T, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_word_table_bwd(const float* SF, const float* DF, const float* wa, const float* dT, int32_t tokens, float* dSF,
+                         float* dparams, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(tokens >= 0, "word_table_bwd: tokens < 0");
+    GCGCN_TRY(check_device_ptr(DF, "DF"));
+    GCGCN_TRY(check_device_ptr(wa, "wa"));
+    GCGCN_TRY(check_device_ptr(dparams, "dparams"));
+    if (tokens > 0) {
+        GCGCN_TRY(check_device_ptr(SF, "SF"));
+        GCGCN_TRY(check_device_ptr(dT, "dT"));
+        GCGCN_TRY(check_device_ptr(dSF, "dSF"));
+    }
+    Arena ar(ws, ws_bytes);
+    float* partial = ar.take<float>(static_cast<size_t>(word_table_parts(tokens)) * WT_PARTIAL_FLOATS);
+    if (partial == nullptr) return fail(GCGCN_ERR_WORKSPACE, "word_table_bwd: workspace too small");
+    return launch_word_table_bwd(SF, DF, wa, dT, tokens, dSF, dparams, partial, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_word_pool_fwd(const gcgcn_edge_tables* tabs, const float* T, const float* ctx, float* att, float* cwa,
+                        void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_edge_tables(tabs));
+    if (tabs->num_slots == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(T, "T"));
+    GCGCN_TRY(check_device_ptr(ctx, "ctx"));
+    GCGCN_TRY(check_device_ptr(att, "att"));
+    GCGCN_TRY(check_device_ptr(cwa, "cwa"));
+    return launch_word_pool_fwd(tabs, T, ctx, att, cwa, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_word_pool_bwd(const gcgcn_edge_tables* tabs, const float* ctx, const float* att, const float* dcwa,
+                        float* dctx, float* dT, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_edge_tables(tabs));
+    if (tabs->num_slots == 0 || tabs->num_tokens == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(ctx, "ctx"));
+    GCGCN_TRY(check_device_ptr(att, "att"));
+    GCGCN_TRY(check_device_ptr(dcwa, "dcwa"));
+    GCGCN_TRY(check_device_ptr(dctx, "dctx"));
+    GCGCN_TRY(check_device_ptr(dT, "dT"));
+    GCGCN_TRY(check_device_ptr(tabs->tok_first, "tabs.tok_first"));
+    Arena ar(ws, ws_bytes);
+    float* dlog = ar.take<float>(static_cast<size_t>(tabs->att_total));
+    if (dlog == nullptr) return fail(GCGCN_ERR_WORKSPACE, "word_pool_bwd: workspace too small");
+    return launch_word_pool_bwd(tabs, ctx, att, dcwa, dlog, dctx, dT, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_sent_pool_fwd(const gcgcn_edge_tables* tabs, const float* cw, const float* sfeat, const float* nfeat,
+                        const float* va, const float* ca, float* score, float* csa, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_edge_tables(tabs));
+    if (tabs->num_pairs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(cw, "cw"));
+    GCGCN_TRY(check_device_ptr(sfeat, "sfeat"));
+    GCGCN_TRY(check_device_ptr(nfeat, "nfeat"));
+    GCGCN_TRY(check_device_ptr(va, "va"));
+    GCGCN_TRY(check_device_ptr(ca, "ca"));
+    GCGCN_TRY(check_device_ptr(score, "score"));
+    GCGCN_TRY(check_device_ptr(csa, "csa"));
+    GCGCN_TRY(check_device_ptr(tabs->pair_slot_ptr, "tabs.pair_slot_ptr"));
+    return launch_sent_pool_fwd(tabs, cw, sfeat, nfeat, va, ca, score, csa, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_sent_pool_bwd(const gcgcn_edge_tables* tabs, int32_t total_nodes, const float* cw, const float* sfeat,
+                        const float* nfeat, const float* va, const float* score, const float* dcsa, float* dcw,
+                        float* dsfeat, float* dnfeat, float* dparams, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_edge_tables(tabs));
+    GCGCN_REQUIRE(total_nodes >= 0, "sent_pool_bwd: total_nodes < 0");
+    GCGCN_TRY(check_device_ptr(va, "va"));
+    GCGCN_TRY(check_device_ptr(dparams, "dparams"));
+    if (total_nodes > 0) {
+        GCGCN_TRY(check_device_ptr(dnfeat, "dnfeat"));
+        GCGCN_TRY(check_device_ptr(tabs->node_ctr_ptr, "tabs.node_ctr_ptr"));
+    }
+    if (tabs->num_pairs > 0) {
+        GCGCN_TRY(check_device_ptr(cw, "cw"));
+        GCGCN_TRY(check_device_ptr(score, "score"));
+        GCGCN_TRY(check_device_ptr(dcsa, "dcsa"));
+        GCGCN_TRY(check_device_ptr(dcw, "dcw"));
+        GCGCN_TRY(check_device_ptr(dsfeat, "dsfeat"));
+    }
+    Arena ar(ws, ws_bytes);
+    float* dpre = ar.take<float>(static_cast<size_t>(tabs->num_slots) * 2 * D + 4);
+    float* partial = ar.take<float>(static_cast<size_t>(sent_pool_parts(tabs->num_pairs)) * SP_PARTIAL_FLOATS);
+    if (dpre == nullptr || partial == nullptr) return fail(GCGCN_ERR_WORKSPACE, "sent_pool_bwd: workspace too small");
+    return launch_sent_pool_bwd(tabs, total_nodes, cw, sfeat, nfeat, va, score, dcsa, dcw, dsfeat, dnfeat, dparams, dpre,
+                                partial, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_edge_fill_fwd(const float* bias, const float* rows, const int64_t* pair_idx, int32_t num_pairs,
+                        int64_t total_pairs, int32_t edge_dtype, void* e, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(num_pairs >= 0 && total_pairs >= 0, "edge_fill_fwd: negative size");
+    if (total_pairs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(bias, "bias"));
+    GCGCN_TRY(check_device_ptr(e, "e"));
+    if (num_pairs > 0) {
+        GCGCN_TRY(check_device_ptr(rows, "rows"));
+        GCGCN_TRY(check_device_ptr(pair_idx, "pair_idx"));
+    }
+    return launch_edge_fill_fwd(bias, rows, pair_idx, num_pairs, total_pairs, edge_dtype, e, static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_edge_fill_bwd(const void* de, const int64_t* pair_idx, int32_t num_pairs, int64_t total_pairs,
+                        int32_t edge_dtype, float* drows, float* dbias, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(num_pairs >= 0 && total_pairs >= 0, "edge_fill_bwd: negative size");
+    GCGCN_TRY(check_device_ptr(dbias, "dbias"));
+    if (total_pairs > 0) GCGCN_TRY(check_device_ptr(de, "de"));
+    if (num_pairs > 0) {
+        GCGCN_TRY(check_device_ptr(drows, "drows"));
+        GCGCN_TRY(check_device_ptr(pair_idx, "pair_idx"));
+    }
+    Arena ar(ws, ws_bytes);
+    float* partial = ar.take<float>(static_cast<size_t>(edge_colsum_parts(total_pairs)) * D);
+    if (partial == nullptr) return fail(GCGCN_ERR_WORKSPACE, "edge_fill_bwd: workspace too small");
+    return launch_edge_fill_bwd(de, pair_idx, num_pairs, total_pairs, edge_dtype, drows, dbias, partial,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int gcgcn_colsum(const float* X, int32_t M, int32_t N, int32_t ldx, float* out, void* ws, size_t ws_bytes, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(M >= 0 && N >= 0 && ldx >= N, "colsum: bad shape");
+    if (N == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(out, "out"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (M == 0) return cuda_ok(cudaMemsetAsync(out, 0, static_cast<size_t>(N) * sizeof(float), st), "colsum: memset");
+    GCGCN_TRY(check_device_ptr(X, "X"));
+    return launch_colsum(X, M, N, ldx, out, ws, ws_bytes, st);
 }
 
 // ---- dense projection ------------------------------------------------------------------------

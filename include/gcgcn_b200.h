@@ -300,6 +300,74 @@ int gcgcn_expand_pair_context(const int32_t* slots, int32_t num_slots, int32_t n
                               int32_t dis_plus, uint8_t* sen_matrix, int64_t* pos_matrix_h, int64_t* pos_matrix_t,
                               void* stream);
 
+/* ---- edge-feature producer: WordAttention + SentenceAttention as G:299-327 uses them ----
+ * Replaces, per hop i, word_attention[i] (G:313-314), linear_word_att[i] (G:317), sentence_attention[i] (G:323-324) and
+ * linear_sentence_att[i] (G:326) for a ragged batch of documents.  Only "active" slots are evaluated: a sentence slot
+ * whose sentence contains token 0 (sent_att_padding_matrix = ~sen_matrix[:, :, :, 0:1], G:302); every other slot is
+ * masked to -1e5 before the relu of G:212, contributes exactly 0 to context_sent_att and receives exactly zero
+ * gradient, and a pair without active slots gets linear_sentence_att.bias.  The word scores come from the table
+ * T[l][k] = attention_all(tanh(attention_sent(ctx[l]) + attention_pos(dis_embed[k]))) (G:179-183 has 21 L distinct
+ * values, not n^2 S L).  The five linears are gcgcn_gemm calls made by the caller (gcgcn_b200/edgefeat.py); the entry
+ * points below are the rest.  Tables are built on the host from the wire format (edgefeat.EdgeTables):
+ *   active tokens a: tokens [0, Lact) of every document that has an active slot, documents back to back;
+ *   active slots s (sorted by document, then pair): sentence tokens [0, slot_len), mention spans, node rows;
+ *   active pairs p: global pair index, CSR over their slots, denominator float32(sent_num) + 1e-10 (G:206, 213).   */
+typedef struct gcgcn_edge_tables {
+    int32_t num_tokens;           /* active tokens                                                         */
+    int32_t num_slots;            /* active slots                                                          */
+    int32_t num_pairs;            /* active pairs                                                          */
+    int32_t att_total;            /* attention entries: sum over slots of 2 * slot_len                     */
+    int32_t dis_plus;             /* config/Config.py:119                                                  */
+    int32_t reserved;
+    const int32_t* tok_first;     /* [num_tokens] active-token index of token 0 of the same document       */
+    const int32_t* tok_slot_lo;   /* [num_tokens] first active slot of the token's document                */
+    const int32_t* tok_slot_hi;   /* [num_tokens] one past the last                                        */
+    const int32_t* slot_tok0;     /* [num_slots] active-token index of the document's token 0              */
+    const int32_t* slot_len;      /* [num_slots] min(sentence end, document length)                        */
+    const int32_t* slot_span;     /* [num_slots][4] head mention [h0, h1], tail mention [t0, t1] (C:187-201) */
+    const int32_t* slot_att;      /* [num_slots] offset of the slot's 2 * slot_len attention entries       */
+    const int32_t* slot_rowi;     /* [num_slots] node row of the pair's row entity i                       */
+    const int32_t* slot_rowj;     /* [num_slots] node row of its column entity j                           */
+    const int64_t* pair_idx;      /* [num_pairs] global pair index (pair_ptr[b] + i * n + j)               */
+    const int32_t* pair_slot_ptr; /* [num_pairs + 1]                                                       */
+    const float* pair_denom;      /* [num_pairs]                                                           */
+    const int32_t* node_ctr_ptr;  /* [total_nodes + 1] CSR: (slot * 2 + side) entries embedding this node row */
+    const int32_t* node_ctr;
+} gcgcn_edge_tables;
+/* scratch any entry point below needs */
+size_t gcgcn_edgefeat_ws_bytes(int32_t num_tokens, int32_t att_total, int32_t num_slots, int32_t num_pairs,
+                               int64_t total_pairs);
+/* T[a][k] = wa . tanh(SF[a] + DF[k]) + ba;  SF [tokens,128], DF [21,128], T [tokens,21]                    */
+int gcgcn_word_table_fwd(const float* SF, const float* DF, const float* wa, const float* ba, int32_t tokens, float* T,
+                         void* stream);
+/* dparams [21*128 + 128 + 4] = dDF, dwa, dba, 3 floats of padding                                          */
+int gcgcn_word_table_bwd(const float* SF, const float* DF, const float* wa, const float* dT, int32_t tokens, float* dSF,
+                         float* dparams, void* ws, size_t ws_bytes, void* stream);
+/* per (slot, side): att = softmax over the sentence tokens of T[l][pos(l)] (G:186-187; the -1e5 fill of the tokens
+ * outside the sentence underflows to exactly 0), cwa[slot][side*128 ..] = sum_l att[l] ctx[l] (G:188).
+ * ctx [tokens,128] = the active rows of context_output; att [att_total] is an output saved for backward.     */
+int gcgcn_word_pool_fwd(const gcgcn_edge_tables* tabs, const float* T, const float* ctx, float* att, float* cwa,
+                        void* stream);
+int gcgcn_word_pool_bwd(const gcgcn_edge_tables* tabs, const float* ctx, const float* att, const float* dcwa,
+                        float* dctx, float* dT, void* ws, size_t ws_bytes, void* stream);
+/* per active pair: score_side[s] = va . tanh(sfeat[s] + nfeat[j | i]) + ca (G:202-204; side h embeds the column
+ * entity, side t the row entity, G:320-321), csa_side = sum_s relu(score_side[s]) cw[s] / denom (G:212-213).
+ * score [slots,2] is saved for backward; csa [pairs,256] = (h | t).                                          */
+int gcgcn_sent_pool_fwd(const gcgcn_edge_tables* tabs, const float* cw, const float* sfeat, const float* nfeat,
+                        const float* va, const float* ca, float* score, float* csa, void* stream);
+/* dparams [128 + 4] = dva, dca, 3 floats of padding                                                        */
+int gcgcn_sent_pool_bwd(const gcgcn_edge_tables* tabs, int32_t total_nodes, const float* cw, const float* sfeat,
+                        const float* nfeat, const float* va, const float* score, const float* dcsa, float* dcw,
+                        float* dsfeat, float* dnfeat, float* dparams, void* ws, size_t ws_bytes, void* stream);
+/* e[p] = bias for every pair, bias + rows[k] for the active pair pair_idx[k] (rows = csa W_ls^T, no bias).
+ * bwd: drows[k] = de[pair_idx[k]], dbias = column sums of de over ALL pairs.                                */
+int gcgcn_edge_fill_fwd(const float* bias, const float* rows, const int64_t* pair_idx, int32_t num_pairs,
+                        int64_t total_pairs, int32_t edge_dtype, void* e, void* stream);
+int gcgcn_edge_fill_bwd(const void* de, const int64_t* pair_idx, int32_t num_pairs, int64_t total_pairs,
+                        int32_t edge_dtype, float* drows, float* dbias, void* ws, size_t ws_bytes, void* stream);
+/* out[c] = sum_r X[r][c] (bias gradients of the linears); ws >= gcgcn_edgefeat_ws_bytes(...) or 4 MB         */
+int gcgcn_colsum(const float* X, int32_t M, int32_t N, int32_t ldx, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- training step of config 5 (new work: the reference has no multi-GPU path) ----
  * Fused Adam over ONE flat float32 buffer holding every hot-path parameter, with the semantics of
  * torch.optim.Adam as the reference's trainer constructs it (config/Config.py:300: lr only, betas

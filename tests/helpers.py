@@ -88,3 +88,84 @@ def maxdiff(a, b) -> float:
 def assert_close(a, b, tol, what=""):
     d = maxdiff(a, b)
     assert d <= tol, f"{what}: max|diff| = {d:.3e} > {tol:.1e}"
+
+
+# ------------------------------------------------------------------------------- graph head
+def head_shapes(layers=2, heads=8, hidden=128, dis_size=20, type_size=20, relations=97, hops=2):
+    """state_dict keys -> shapes of everything the reference model owns after ``context_output`` (G:254-279)."""
+    g = hidden // layers
+    s = {}
+    for nm in ("linear_node_h", "linear_node_t", "linear_edge_r"):
+        s[f"get_weighted_adj_matrix.{nm}.weight"] = (hidden, hidden)
+        s[f"get_weighted_adj_matrix.{nm}.bias"] = (hidden,)
+    s["get_weighted_adj_matrix.wt.weight"] = (1, 3 * hidden)
+    s["get_weighted_adj_matrix.wt.bias"] = (1,)
+    for kind in ("linears_q", "linears_k"):
+        for h in range(heads):
+            s[f"get_adj_matrix.0.{kind}.{h}.weight"] = (hidden // heads, hidden)
+            s[f"get_adj_matrix.0.{kind}.{h}.bias"] = (hidden // heads,)
+    for l in range(layers):
+        s[f"graphcnn.0.graphconv.{l}.weights_edge"] = (hidden, g)
+        s[f"graphcnn.0.graphconv.{l}.weights_node"] = (hidden + g * l, g)
+    s["graphcnn.0.linear_layer.weight"] = (hidden, hidden)
+    s["graphcnn.0.linear_layer.bias"] = (hidden,)
+    for h in range(heads):
+        for l in range(layers):
+            s[f"graphcnn.1.graphconv.{h * layers + l}.weights_edge"] = (hidden, g)
+            s[f"graphcnn.1.graphconv.{h * layers + l}.weights_node"] = (hidden + g * l, g)
+    s["graphcnn.1.linear_layer.weight"] = (hidden, hidden * heads)
+    s["graphcnn.1.linear_layer.bias"] = (hidden,)
+    for i in range(hops):
+        s[f"word_attention.{i}.attention_sent.weight"] = (hidden, hidden)
+        s[f"word_attention.{i}.attention_sent.bias"] = (hidden,)
+        s[f"word_attention.{i}.attention_pos.weight"] = (hidden, dis_size)
+        s[f"word_attention.{i}.attention_pos.bias"] = (hidden,)
+        s[f"word_attention.{i}.attention_all.weight"] = (1, hidden)
+        s[f"word_attention.{i}.attention_all.bias"] = (1,)
+        s[f"sentence_attention.{i}.attention_sent.weight"] = (hidden, hidden)
+        s[f"sentence_attention.{i}.attention_sent.bias"] = (hidden,)
+        s[f"sentence_attention.{i}.attention_pos.weight"] = (hidden, hidden)
+        s[f"sentence_attention.{i}.attention_pos.bias"] = (hidden,)
+        s[f"sentence_attention.{i}.attention_all.weight"] = (1, hidden)
+        s[f"sentence_attention.{i}.attention_all.bias"] = (1,)
+        s[f"linear_word_att.{i}.weight"] = (hidden, 2 * hidden)
+        s[f"linear_word_att.{i}.bias"] = (hidden,)
+        s[f"linear_sentence_att.{i}.weight"] = (hidden, 2 * hidden)
+        s[f"linear_sentence_att.{i}.bias"] = (hidden,)
+    s["dense_layer.weight"] = (hidden, hidden * (hops + 1) + dis_size + type_size)
+    s["dense_layer.bias"] = (hidden,)
+    s["bili_layer_01.weight"] = (relations, hidden, hidden)
+    s["bili_layer_01.bias"] = (relations,)
+    s["classification_layer_01.weight"] = (relations, 2 * hidden)
+    s["classification_layer_01.bias"] = (relations,)
+    s["dis_embed.weight"] = (21, dis_size)
+    s["ner_emb.weight"] = (7, type_size)
+    return s
+
+
+def head_state(seed=0, layers=2, heads=8):
+    """Deterministic weights for every head parameter (uniform, fan-in scaled), independent of any module's init
+    order: tests/golden/make_golden_edge.py loads the same values into the UNMODIFIED reference model, the GPU tests
+    load them into the drop-in modules.  Embedding row 0 of ner_emb is the padding row (G:242)."""
+    gen = torch.Generator().manual_seed(4321 + seed)
+    out = {}
+    for name, shape in head_shapes(layers, heads).items():
+        if len(shape) == 1:
+            bound = 0.1
+        elif name.endswith("weights_node") or name.endswith("weights_edge"):
+            bound = (6.0 / (shape[0] + shape[1])) ** 0.5
+        elif name in ("dis_embed.weight", "ner_emb.weight"):
+            bound = 0.5
+        else:
+            bound = 1.0 / shape[-1] ** 0.5
+        out[name] = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+    out["ner_emb.weight"][0] = 0.0
+    return out
+
+
+def head_labels(seed, n, relations=97):
+    """Sparse synthetic multi-hot labels [n, n, R] float32 (about 2 % positives), zero diagonal."""
+    gen = torch.Generator().manual_seed(555 + seed)
+    lab = (torch.rand(n, n, relations, generator=gen) < 0.02).float()
+    lab[torch.arange(n), torch.arange(n)] = 0.0
+    return lab

@@ -171,9 +171,9 @@ def test_reference_call_sequence_shares_the_edge_pass():
     e0, e1 = d.e0.to(DEV).requires_grad_(True), d.e1.to(DEV).requires_grad_(True)
     mask = torch.eq(d.adj.to(DEV), 0)
     weight_adj_matrix = gat(node_feat, e0, mask)
-    assert M._EBAR_SLOT["ebar"] is not None
+    assert getattr(M._EBAR_TLS, "slot", None) is not None
     y1 = cag(node_feat, e0, weight_adj_matrix)
-    assert M._EBAR_SLOT["ebar"] is None                    # consumed: e0 was streamed once
+    assert getattr(M._EBAR_TLS, "slot", None) is None     # consumed: e0 was streamed once
     adj_matrix_list = mha(y1, e1)
     y2 = mag(y1, e1, adj_matrix_list)
     dy1, dy2 = upstream(d.doc_id, y1.shape, y2.shape)
@@ -187,3 +187,22 @@ def test_reference_call_sequence_shares_the_edge_pass():
     # a plain python list of H separate tensors works too (the reference's type)
     y2b = mag(y1.detach(), e1.detach(), [a.detach().clone() for a in adj_matrix_list])
     assert_close(y2b, y2, 1e-6, "list input")
+
+
+def test_ebar_stashed_under_no_grad_is_not_reused_in_grad_mode():
+    """a GATAttention.forward under no_grad must not hand its history-free edge mean to a grad-mode
+    GraphConvolution.forward on the same tensor (de0 would silently lose the GraphConv edge-mean term)."""
+    gb, state = device_blocks(2, 8)
+    gat, cag = gb.get_weighted_adj_matrix, gb.graphcnn[0]
+    d = S.make_doc(7)
+    x = d.x0.to(DEV).requires_grad_(True)
+    e0 = d.e0.to(DEV).requires_grad_(True)
+    with torch.no_grad():
+        att = gat(x, e0, None)
+    y = cag(x, e0, att)                      # recomputes the mean with history
+    y.sum().backward()
+    assert e0.grad is not None and float(e0.grad.abs().max()) > 0.0
+    xo, eo = d.x0.clone().requires_grad_(True), d.e0.clone().requires_grad_(True)
+    yo = O.caggc_conv(xo, eo, att.cpu(), sub(state, "graphcnn.0"), 2)
+    yo.sum().backward()
+    assert_close(e0.grad, eo.grad, FP32_TOL, "de0")
