@@ -159,6 +159,11 @@ SIGNATURES = {
     "gcgcn_edge_fill_fwd": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, _P, _P]),
     "gcgcn_edge_fill_bwd": (c_int32, [_P, _P, c_int32, c_int64, c_int32, _P, _P, _P, c_size_t, _P]),
     "gcgcn_colsum": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P, c_size_t, _P]),
+    "gcgcn_bilinear_reduce_fwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P]),
+    "gcgcn_bilinear_outer_bwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, _P]),
+    "gcgcn_bilinear_dt_bwd": (c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, _P]),
+    "gcgcn_pair_bce_fwd": (c_int32, [_BT, _P, _P, c_int32, _P, _P]),
+    "gcgcn_pair_bce_bwd": (c_int32, [_BT, _P, _P, c_int32, _P, _P, _P]),
     "gcgcn_adam_step": (c_int32, [_P, _P, _P, _P, c_int64] + [c_float] * 6 + [c_int32, _P]),
     "gcgcn_gemm": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, c_int32, _P,
                              c_int32, c_float, _P, c_int32, _P, _P, c_size_t, _P]),

@@ -1,0 +1,109 @@
+"""Relation classifier and loss of GCGCN on the GPU (second half).
+
+``logits = bili_layer_01(h, t) + classification_layer_01(cat[h, t])`` (/root/reference/models/GCGCN_glove.py:275-276,
+356-358) over every pair of a ragged batch, and the trainer's loss (config/Config.py:355-364).  ``h``, ``t`` are
+``entity_feature_h`` / ``entity_feature_t`` ``[total_pairs, 128]`` (``modules.pair_dense``).  The bilinear form is the
+one dense n^2-scale contraction of the model (2 * 128 * 128 * 97 flop per pair): it runs on this package's tcgen05 GEMM
+(3xTF32) as ``Y = h W'`` with ``W'`` the ``[R, 128, 128]`` weight viewed as ``[128, R*128]``, then a row-wise reduction
+against ``t``; the pairs are walked in chunks so that ``Y`` (R*128 floats per pair) stays inside a fixed workspace.
+No CPU path.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _lib
+from .batch import RaggedBatch
+from .functional import D, LinearFn, _cuda, _p, _stream, gemm, workspace
+
+CHUNK_PAIRS = 8192          # 8192 pairs x 97 x 128 floats = 407 MB of Y per chunk
+
+
+def _wmat(W: torch.Tensor) -> torch.Tensor:
+    """[R, 128(a), 128(b)] -> [128(a), R*128 (r, b)]."""
+    R = W.shape[0]
+    return W.permute(1, 0, 2).reshape(D, R * D).contiguous()
+
+
+class BilinearFn(Function):
+    """out[p, r] = sum_{a,b} h[p,a] W[r,a,b] t[p,b] + bias[r]   (torch.nn.Bilinear, G:275, 358)."""
+
+    @staticmethod
+    def forward(ctx, h, t, W, bias):
+        h, t, W, bias = _cuda(h, "h"), _cuda(t, "t"), _cuda(W, "weight"), _cuda(bias, "bias")
+        P, R, dev = h.shape[0], W.shape[0], h.device
+        if W.shape[1:] != (D, D) or h.shape[1] != D or t.shape != h.shape:
+            raise _lib.GcgcnError(f"bilinear: expected h, t [P, {D}] and weight [R, {D}, {D}]")
+        Wm = _wmat(W)
+        out = torch.empty(P, R, device=dev)
+        for p0 in range(0, P, CHUNK_PAIRS):
+            p1 = min(P, p0 + CHUNK_PAIRS)
+            Y = gemm(h[p0:p1], Wm)
+            _lib.call("gcgcn_bilinear_reduce_fwd", _p(Y), _p(t[p0:p1]), _p(bias), p1 - p0, R, 0, _p(out[p0:p1]), R,
+                      _stream(dev))
+            del Y
+        ctx.save_for_backward(h, t, Wm)
+        ctx.R = R
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, t, Wm = ctx.saved_tensors
+        R, dev, P = ctx.R, h.device, h.shape[0]
+        dout = _cuda(dout, "dout")
+        dh, dt = torch.empty_like(h), torch.empty_like(t)
+        dWm = torch.zeros_like(Wm)
+        for p0 in range(0, P, CHUNK_PAIRS):
+            p1 = min(P, p0 + CHUNK_PAIRS)
+            rows = p1 - p0
+            Y = gemm(h[p0:p1], Wm)                                               # recomputed, not saved
+            _lib.call("gcgcn_bilinear_dt_bwd", _p(dout[p0:p1]), R, _p(Y), rows, R, _p(dt[p0:p1]), _stream(dev))
+            dY = Y                                                               # same storage
+            _lib.call("gcgcn_bilinear_outer_bwd", _p(dout[p0:p1]), R, _p(t[p0:p1]), rows, R, _p(dY), _stream(dev))
+            gemm(dY, Wm, trans_b=True, out=dh[p0:p1])                            # dh = dY W'^T
+            gemm(h[p0:p1], dY, trans_a=True, out=dWm, beta=1.0)                  # dW' += h^T dY
+            del Y, dY
+        dbias = torch.empty(R, device=dev)
+        ws = workspace(dev, 8 << 20)
+        _lib.call("gcgcn_colsum", _p(dout), P, R, R, _p(dbias), ws.data_ptr(), ws.numel(), _stream(dev))
+        dW = dWm.view(D, R, D).permute(1, 0, 2).contiguous()
+        return dh, dt, dW, dbias
+
+
+class PairBceFn(Function):
+    """Per-document loss of config/Config.py:355-364 from logits and multi-hot labels [total_pairs, R]."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, batch: RaggedBatch):
+        logits, labels = _cuda(logits, "logits"), _cuda(labels, "labels")
+        if logits.shape != labels.shape or logits.shape[0] != batch.total_pairs:
+            raise _lib.GcgcnError("pair_bce: logits and labels must both be [total_pairs, R]")
+        loss = torch.empty(batch.num_docs, device=logits.device)
+        _lib.call("gcgcn_pair_bce_fwd", batch.ref, _p(logits), _p(labels), logits.shape[1], _p(loss), _stream(logits.device))
+        ctx.save_for_backward(logits, labels)
+        ctx.batch = batch
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels = ctx.saved_tensors
+        dloss = _cuda(dloss, "dloss")
+        dz = torch.empty_like(logits)
+        _lib.call("gcgcn_pair_bce_bwd", ctx.batch.ref, _p(logits), _p(labels), logits.shape[1], _p(dloss), _p(dz),
+                  _stream(logits.device))
+        return dz, None, None
+
+
+def relation_logits(h: torch.Tensor, t: torch.Tensor, bili: nn.Bilinear, cls: nn.Linear) -> torch.Tensor:
+    """G:356-358: ``bili(h, t) + cls(cat[h, t])`` without forming the concatenation (the linear layer is split by
+    input columns into its h and t halves)."""
+    w = cls.weight
+    lin = LinearFn.apply(h, w[:, :D], cls.bias) + LinearFn.apply(t, w[:, D:], None)
+    return BilinearFn.apply(h, t, bili.weight, bili.bias) + lin
+
+
+def pair_bce_loss(logits: torch.Tensor, labels: torch.Tensor, batch: RaggedBatch) -> torch.Tensor:
+    """[num_docs] losses exactly as the reference trainer forms them per document (C:355-364)."""
+    return PairBceFn.apply(logits, labels, batch)

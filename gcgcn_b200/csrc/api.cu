@@ -96,6 +96,14 @@ int edge_colsum_parts(long long total_pairs);
 int launch_edge_fill_bwd(const void* de, const void* pair_idx, int pairs, long long total_pairs, int dtype, float* drows,
                          float* dbias, float* partial, cudaStream_t st);
 
+int launch_bilinear_reduce(const float* Y, const float* t, const float* bias, int rows, int R, int accumulate, float* out,
+                           int ldo, cudaStream_t st);
+int launch_bilinear_outer(const float* dout, int ldd, const float* t, int rows, int R, float* dY, cudaStream_t st);
+int launch_bilinear_dt(const float* dout, int ldd, const float* Y, int rows, int R, float* dt, cudaStream_t st);
+int launch_pair_bce_fwd(const gcgcn_batch* bt, const float* z, const float* y, int R, float* loss, cudaStream_t st);
+int launch_pair_bce_bwd(const gcgcn_batch* bt, const float* z, const float* y, int R, const float* dloss, float* dz,
+                        cudaStream_t st);
+
 // ---- error text, launch counter, device cache --------------------------------------------------
 std::atomic<uint64_t> g_launches{0};
 std::atomic<bool> g_timing{false};
@@ -1021,6 +1029,63 @@ int gcgcn_colsum(const float* X, int32_t M, int32_t N, int32_t ldx, float* out, 
     if (M == 0) return cuda_ok(cudaMemsetAsync(out, 0, static_cast<size_t>(N) * sizeof(float), st), "colsum: memset");
     GCGCN_TRY(check_device_ptr(X, "X"));
     return launch_colsum(X, M, N, ldx, out, ws, ws_bytes, st);
+}
+
+// ---- relation classifier and loss -----------------------------------------------------
+int gcgcn_bilinear_reduce_fwd(const float* Y, const float* t, const float* bias, int32_t rows, int32_t relations,
+                              int32_t accumulate, float* out, int32_t ldo, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(rows >= 0 && relations >= 0 && ldo >= relations, "bilinear_reduce: bad shape");
+    if (rows == 0 || relations == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(Y, "Y"));
+    GCGCN_TRY(check_device_ptr(t, "t"));
+    GCGCN_TRY(check_device_ptr(out, "out"));
+    return launch_bilinear_reduce(Y, t, bias, rows, relations, accumulate, out, ldo, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int32_t rows, int32_t relations, float* dY,
+                             void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(rows >= 0 && relations >= 0 && ldd >= relations, "bilinear_outer: bad shape");
+    if (rows == 0 || relations == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(dout, "dout"));
+    GCGCN_TRY(check_device_ptr(t, "t"));
+    GCGCN_TRY(check_device_ptr(dY, "dY"));
+    return launch_bilinear_outer(dout, ldd, t, rows, relations, dY, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_bilinear_dt_bwd(const float* dout, int32_t ldd, const float* Y, int32_t rows, int32_t relations, float* dt,
+                          void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(rows >= 0 && relations >= 0 && ldd >= relations, "bilinear_dt: bad shape");
+    if (rows == 0 || relations == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(dout, "dout"));
+    GCGCN_TRY(check_device_ptr(Y, "Y"));
+    GCGCN_TRY(check_device_ptr(dt, "dt"));
+    return launch_bilinear_dt(dout, ldd, Y, rows, relations, dt, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_pair_bce_fwd(const gcgcn_batch* bt, const float* logits, const float* labels, int32_t relations, float* loss,
+                       void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(relations >= 1, "pair_bce_fwd: relations < 1");
+    if (bt->num_docs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(loss, "loss"));
+    if (bt->total_pairs > 0) {
+        GCGCN_TRY(check_device_ptr(logits, "logits"));
+        GCGCN_TRY(check_device_ptr(labels, "labels"));
+    }
+    return launch_pair_bce_fwd(bt, logits, labels, relations, loss, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_pair_bce_bwd(const gcgcn_batch* bt, const float* logits, const float* labels, int32_t relations,
+                       const float* dloss, float* dlogits, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(relations >= 1, "pair_bce_bwd: relations < 1");
+    if (bt->total_pairs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(logits, "logits"));
+    GCGCN_TRY(check_device_ptr(labels, "labels"));
+    GCGCN_TRY(check_device_ptr(dloss, "dloss"));
+    GCGCN_TRY(check_device_ptr(dlogits, "dlogits"));
+    return launch_pair_bce_bwd(bt, logits, labels, relations, dloss, dlogits, static_cast<cudaStream_t>(stream));
 }
 
 // ---- dense projection ------------------------------------------------------------------------

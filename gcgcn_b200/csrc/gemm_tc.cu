@@ -928,7 +928,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     // weight-like B operand (small, reused by every 128-row tile of a tall A): pre-split it once per call
     const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
     const bool bpre = gemm_tc_bpre_enabled() && batch == 1 && splits == 1 && !ta && M >= 4096 &&
-                      static_cast<size_t>(N) * K * sizeof(float) <= (size_t(2) << 20) && ws != nullptr &&
+                      static_cast<size_t>(N) * K * sizeof(float) <= (size_t(8) << 20) && ws != nullptr &&
                       blob_total <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
     if (bpre) {
         tc_presplit_b_kernel<<<a.tiles_n * a.kblocks, 256, 0, st>>>(B, ldb, tb != 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));

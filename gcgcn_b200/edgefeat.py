@@ -21,7 +21,7 @@ from torch.autograd import Function
 
 from . import _lib
 from .batch import DIS_PLUS, PoolTable, RaggedBatch
-from .functional import D, PoolFn, _cuda, _edge, _p, _stream, gemm, workspace
+from .functional import D, LinearFn, PoolFn, _cuda, _edge, _p, _stream, linear, workspace
 
 BUCKETS = 21           # config/Config.py:118 dis_num
 
@@ -133,42 +133,6 @@ class EdgeTables:
 
 
 # ------------------------------------------------------------------------------- autograd bindings
-class LinearFn(Function):
-    """y = x W^T + b on gcgcn_gemm (3xTF32 tcgen05 tiles, or the CUDA-core kernel for tiny / unaligned shapes);
-    backward = two more products and a column sum.  ``b`` may be None."""
-
-    @staticmethod
-    def forward(ctx, x, W, b):
-        x, W = _cuda(x, "x"), _cuda(W, "weight")
-        b = None if b is None else _cuda(b, "bias")
-        ctx.save_for_backward(x, W)
-        ctx.has_bias = b is not None
-        if x.shape[0] == 0:
-            return x.new_zeros(0, W.shape[0])
-        return gemm(x, W, trans_b=True, bias=b)
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, W = ctx.saved_tensors
-        dy = _cuda(dy, "dy")
-        M = x.shape[0]
-        dev = x.device
-        if M == 0:
-            return x.new_zeros(x.shape), torch.zeros_like(W), (torch.zeros(W.shape[0], device=dev) if ctx.has_bias else None)
-        dx = gemm(dy, W) if ctx.needs_input_grad[0] else None
-        dW = gemm(dy, x, trans_a=True) if ctx.needs_input_grad[1] else None
-        db = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(W.shape[0], device=dev)
-            ws = workspace(dev, 8 << 20)
-            _lib.call("gcgcn_colsum", _p(dy), M, W.shape[0], dy.shape[1], _p(db), ws.data_ptr(), ws.numel(), _stream(dev))
-        return dx, dW, db
-
-
-def linear(x, layer: nn.Linear):
-    return LinearFn.apply(x, layer.weight, layer.bias)
-
-
 class WordTableFn(Function):
     """T[a][k] = wa . tanh(SF[a] + DF[k]) + ba  (G:183 over the 21 x L distinct arguments)."""
 

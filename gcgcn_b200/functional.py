@@ -486,8 +486,49 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_a=False, trans_b=False, bias=No
     N = b.shape[0] if trans_b else b.shape[1]
     if out is None:
         out = torch.zeros(M, N, device=a.device)
-    ws = workspace(a.device, (24 << 20) + ((K + 31) // 32) * 33024 * ((M + 127) // 128) + 4096)
+    # 24 MB of split-K partials / pre-split weight blobs, plus (weight-gradient shapes only) the pre-split short operand
+    pre = ((K + 31) // 32) * 33024 * ((M + 127) // 128) if (trans_a and not trans_b and M <= 256) else 0
+    ws = workspace(a.device, (24 << 20) + pre + 4096)
     _lib.call("gcgcn_gemm", int(trans_a), int(trans_b), M, N, K, float(alpha), _p(a), a.shape[1], _p(b),
               b.shape[1], float(beta), _p(out), out.shape[1], _p(bias), ws.data_ptr(), ws.numel(),
               _stream(a.device))
     return out
+
+
+# ------------------------------------------------------------------------------- linear layers on gcgcn_gemm
+class LinearFn(Function):
+    """y = x W^T + b on gcgcn_gemm (3xTF32 tcgen05 tiles, or the CUDA-core kernel for tiny / unaligned shapes);
+    backward = two more products and a column sum.  ``b`` may be None."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x, W = _cuda(x, "x"), _cuda(W, "weight")
+        b = None if b is None else _cuda(b, "bias")
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        if x.shape[0] == 0:
+            return x.new_zeros(0, W.shape[0])
+        return gemm(x, W, trans_b=True, bias=b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = _cuda(dy, "dy")
+        M = x.shape[0]
+        dev = x.device
+        if M == 0:
+            return x.new_zeros(x.shape), torch.zeros_like(W), (torch.zeros(W.shape[0], device=dev) if ctx.has_bias else None)
+        dx = gemm(dy, W) if ctx.needs_input_grad[0] else None
+        dW = gemm(dy, x, trans_a=True) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(W.shape[0], device=dev)
+            ws = workspace(dev, 8 << 20)
+            _lib.call("gcgcn_colsum", _p(dy), M, W.shape[0], dy.shape[1], _p(db), ws.data_ptr(), ws.numel(), _stream(dev))
+        return dx, dW, db
+
+
+def linear(x, layer):
+    return LinearFn.apply(x, layer.weight, layer.bias)
+
+

@@ -26,7 +26,7 @@ from torch import nn
 
 from . import _lib
 from .batch import PairTables, PoolTable, RaggedBatch, single_doc_batch
-from .functional import (CaggcFn, EdgeMeanFn, GatFn, MhaFn, MhaStackFn, PackStackFn, PairDenseFn, PairGatherFn, PoolFn, StackFn,
+from .functional import (CaggcFn, EdgeMeanFn, GatFn, LinearFn, MhaFn, MhaStackFn, PackStackFn, PairDenseFn, PairGatherFn, PoolFn, StackFn,
                          block_supported)
 
 HIDDEN = 128
@@ -344,10 +344,59 @@ class GraphBlocks(nn.Module, _KeepMixin):
         keep = self._keep(out.shape, self.dropout.p, out.device) if self._dropping() else None
         return out if keep is None else out * keep                                     # G:341
 
+    def _draw(self, att_p, gcn_p):
+        if not self.training or (att_p <= 0.0 and gcn_p <= 0.0):
+            return None
+        return (int(torch.randint(0, 2 ** 62, (1,)).item()), att_p, gcn_p)
+
+    def _fusable(self, x):
+        # Block-level entry points: no mask tensors.  In train mode their kernels regenerate the dropout keep
+        # factors from a per-call seed (drawn from torch's CPU generator, so torch.manual_seed reproduces a run);
+        # masks injected by a test (inject_keep) take the one-entry-point-per-module route instead.
+        gat, mha = self.get_weighted_adj_matrix, self.get_adj_matrix[0]
+        cag, mag = self.graphcnn
+        injected = any(getattr(m, "_injected", None) for m in (self, gat, mha, cag, mag))
+        return self.fused and not injected and not gat.apply_mask and x.is_cuda
+
+    def hop0(self, x0, e0, batch: RaggedBatch, adj=None):
+        """CAGGC hop (G:330-341 at i = 0): returns (y1, a0)."""
+        mask = None if adj is None else torch.eq(adj, 0)                                # G:330
+        gat, cag = self.get_weighted_adj_matrix, self.graphcnn[0]
+        cag_ok = self._fusable(x0) and (not self.training or block_supported(batch, 1, cag.layer_num, False))
+        if cag_ok:
+            u, v, c = gat.collapse()
+            wn_x, w_e, winner = _pack_stack(cag.graphconv, 1, cag.layer_num, cag._g)
+            drop = self._draw(gat.dropout.p if gat.training else 0.0, cag.gcn_dropout.p if cag.training else 0.0)
+            self.last_drop["caggc"] = drop
+            new, a0 = CaggcFn.apply(x0, e0, u, v, c, wn_x, w_e, winner, cag.linear_layer.weight,
+                                    cag.linear_layer.bias, batch, cag.layer_num, drop)          # G:332-333
+        else:
+            a0, ebar0 = gat.forward_batched(x0, e0, batch, mask)                                # G:332
+            new = cag.forward_batched(x0, ebar0, a0.view(1, -1), batch)                         # G:333
+        return self._blend(new, x0), a0
+
+    def hop1(self, y1, e1, batch: RaggedBatch, ebar1=None):
+        """MAGGC hop (G:334-341 at i = 1): returns (y2, a1).  ``ebar1`` = an edge mean of e1 computed ahead."""
+        mha, mag = self.get_adj_matrix[0], self.graphcnn[1]
+        mag_ok = self._fusable(y1) and block_supported(batch, mag.head_num, mag.layer_num, True)
+        a1 = None if mag_ok else mha.forward_batched(y1, batch)                                 # G:336
+        if ebar1 is None:
+            ebar1 = EdgeMeanFn.apply(e1, batch)
+        if mag_ok:
+            wq = torch.cat([l.weight for l in mha.linears_q], 0)
+            bq = torch.cat([l.bias for l in mha.linears_q], 0)
+            wn_x, w_e, winner = _pack_stack(mag.graphconv, mag.head_num, mag.layer_num, mag._g)
+            drop = self._draw(mha.dropout.p if mha.training else 0.0, mag.gcn_dropout.p if mag.training else 0.0)
+            self.last_drop["maggc"] = drop
+            new, a1 = MhaStackFn.apply(y1, ebar1, wq, bq, wn_x, w_e, winner, mag.linear_layer.weight,
+                                       mag.linear_layer.bias, batch, mag.head_num, mag.layer_num, drop)  # G:336-337
+        else:
+            new = mag.forward_batched(y1, ebar1, a1, batch)                                     # G:337
+        return self._blend(new, y1), a1
+
     def forward(self, x0, e0, e1, batch: RaggedBatch, adj=None):
         """x0 [total_nodes,128]; e0, e1 [total_pairs,128] (fp32 or bf16); adj [total_pairs] or None.
         Returns y1, y2 and node_feats = cat[x0, x0, y1] (append-before-update, G:338)."""
-        mask = None if adj is None else torch.eq(adj, 0)                                # G:330
         ebar1 = None
         if self.overlap and e1.is_cuda:
             main = torch.cuda.current_stream(e1.device)
@@ -358,48 +407,10 @@ class GraphBlocks(nn.Module, _KeepMixin):
             with torch.cuda.stream(side):
                 ebar1 = EdgeMeanFn.apply(e1, batch)
             ebar1.record_stream(main)
-        gat, mha = self.get_weighted_adj_matrix, self.get_adj_matrix[0]
-        cag, mag = self.graphcnn
-        # Block-level entry points: no mask tensors.  In train mode their kernels regenerate the dropout keep
-        # factors from a per-call seed (drawn from torch's CPU generator, so torch.manual_seed reproduces a run);
-        # masks injected by a test (inject_keep) take the one-entry-point-per-module route instead.
-        injected = any(getattr(m, "_injected", None) for m in (self, gat, mha, cag, mag))
-        fusable = self.fused and not injected and not gat.apply_mask and x0.is_cuda
-        cag_ok = fusable and (not self.training or block_supported(batch, 1, cag.layer_num, False))
-        mag_ok = fusable and block_supported(batch, mag.head_num, mag.layer_num, True)
-
-        def draw(att_p, gcn_p):
-            if not self.training or (att_p <= 0.0 and gcn_p <= 0.0):
-                return None
-            return (int(torch.randint(0, 2 ** 62, (1,)).item()), att_p, gcn_p)
-
-        if cag_ok:
-            u, v, c = gat.collapse()
-            wn_x, w_e, winner = _pack_stack(cag.graphconv, 1, cag.layer_num, cag._g)
-            drop = draw(gat.dropout.p if gat.training else 0.0, cag.gcn_dropout.p if cag.training else 0.0)
-            self.last_drop["caggc"] = drop
-            new, a0 = CaggcFn.apply(x0, e0, u, v, c, wn_x, w_e, winner, cag.linear_layer.weight,
-                                    cag.linear_layer.bias, batch, cag.layer_num, drop)          # G:332-333
-        else:
-            a0, ebar0 = gat.forward_batched(x0, e0, batch, mask)                                # G:332
-            new = cag.forward_batched(x0, ebar0, a0.view(1, -1), batch)                         # G:333
-        y1 = self._blend(new, x0)
-        a1 = None if mag_ok else mha.forward_batched(y1, batch)                                 # G:336
-        if ebar1 is None:
-            ebar1 = EdgeMeanFn.apply(e1, batch)
-        else:
+        y1, a0 = self.hop0(x0, e0, batch, adj)
+        if ebar1 is not None:
             torch.cuda.current_stream(e1.device).wait_stream(self._side[e1.device])
-        if mag_ok:
-            wq = torch.cat([l.weight for l in mha.linears_q], 0)
-            bq = torch.cat([l.bias for l in mha.linears_q], 0)
-            wn_x, w_e, winner = _pack_stack(mag.graphconv, mag.head_num, mag.layer_num, mag._g)
-            drop = draw(mha.dropout.p if mha.training else 0.0, mag.gcn_dropout.p if mag.training else 0.0)
-            self.last_drop["maggc"] = drop
-            new, a1 = MhaStackFn.apply(y1, ebar1, wq, bq, wn_x, w_e, winner, mag.linear_layer.weight,
-                                       mag.linear_layer.bias, batch, mag.head_num, mag.layer_num, drop)  # G:336-337
-        else:
-            new = mag.forward_batched(y1, ebar1, a1, batch)                                     # G:337
-        y2 = self._blend(new, y1)
+        y2, a1 = self.hop1(y1, e1, batch, ebar1)
         return {"y1": y1, "y2": y2, "a0": a0, "a1": a1, "node_feats": torch.cat([x0, x0, y1], 1)}
 
 
@@ -419,10 +430,10 @@ def pair_dense(node_feats_with_type: torch.Tensor, dense_layer: nn.Linear, dis_e
     """entity_feature_h, entity_feature_t of G:351-355 -- ``tanh(dense_layer(cat(F[j], dis[10 + rp])))`` and
     ``tanh(dense_layer(cat(F[i], dis[10 - rp])))`` -- without forming the two gathered ``[n, n, 424]`` tensors:
     ``dense_layer`` is split by input columns into a node part and a distance part, both applied at node / table
-    level (``[rows, 404] x [404, 128]`` and ``[21, 20] x [20, 128]``, plain library products), and one kernel adds
-    the two 128-vectors per pair and applies tanh.  Same values as ``tanh(dense_layer(pair_gather(...)))``."""
+    level (``[rows, 404] x [404, 128]`` and ``[21, 20] x [20, 128]`` on gcgcn_gemm), and one kernel adds the two
+    128-vectors per pair and applies tanh.  Same values as ``tanh(dense_layer(pair_gather(...)))``."""
     fw = node_feats_with_type.shape[1]
     w = dense_layer.weight
-    U = torch.nn.functional.linear(node_feats_with_type, w[:, :fw])
-    Vd = torch.nn.functional.linear(dis_embed, w[:, fw:], dense_layer.bias)
+    U = LinearFn.apply(node_feats_with_type, w[:, :fw], None)
+    Vd = LinearFn.apply(dis_embed, w[:, fw:], dense_layer.bias)
     return PairDenseFn.apply(U, Vd, tables, batch)

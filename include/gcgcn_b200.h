@@ -368,6 +368,29 @@ int gcgcn_edge_fill_bwd(const void* de, const int64_t* pair_idx, int32_t num_pai
 /* out[c] = sum_r X[r][c] (bias gradients of the linears); ws >= gcgcn_edgefeat_ws_bytes(...) or 4 MB         */
 int gcgcn_colsum(const float* X, int32_t M, int32_t N, int32_t ldx, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- relation classifier and loss (second half) -------------------------------------------
+ * logits = bili_layer_01(h, t) + classification_layer_01(cat[h, t])  (G:356-358) with h, t = entity_feature_h / _t
+ * [total_pairs, 128] from gcgcn_pair_dense_fwd.  The bilinear form runs on gcgcn_gemm as Y = h W' (W' = the
+ * [R, 128, 128] weight viewed as [128, R*128], 3xTF32 tcgen05 tiles) followed by the reductions below; the caller
+ * (gcgcn_b200/classifier.py) walks the pairs in chunks so that Y stays within a fixed workspace.
+ *   reduce: out[p][r] (+)= sum_b Y[p][r*128 + b] t[p][b] (+ bias[r])        Y [rows, R*128], out row stride ldo
+ *   outer:  dY[p][r*128 + b] = dout[p][r] t[p][b]                            (then dh = dY W'^T, dW' = h^T dY)
+ *   dt:     dt[p][b] = sum_r dout[p][r] Y[p][r*128 + b]                                                        */
+int gcgcn_bilinear_reduce_fwd(const float* Y, const float* t, const float* bias, int32_t rows, int32_t relations,
+                              int32_t accumulate, float* out, int32_t ldo, void* stream);
+int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int32_t rows, int32_t relations, float* dY,
+                             void* stream);
+int gcgcn_bilinear_dt_bwd(const float* dout, int32_t ldd, const float* Y, int32_t rows, int32_t relations, float* dt,
+                          void* stream);
+/* The trainer's loss, config/Config.py:355-364, per document of the batch: predict = sigmoid(logits) (C:355), then the
+ * mean over the ordered pairs i != j of BCELoss(predict[i][j], label[i][j]) (mean over the R relation slots, C:361-364;
+ * torch's clamping of the logs at -100 included).  logits, labels [total_pairs, R]; loss [num_docs].
+ * bwd: dlogits = d(sum_b dloss[b] loss[b]) / dlogits (zero on the diagonal pairs).                              */
+int gcgcn_pair_bce_fwd(const gcgcn_batch* bt, const float* logits, const float* labels, int32_t relations, float* loss,
+                       void* stream);
+int gcgcn_pair_bce_bwd(const gcgcn_batch* bt, const float* logits, const float* labels, int32_t relations,
+                       const float* dloss, float* dlogits, void* stream);
+
 /* ---- training step of config 5 (new work: the reference has no multi-GPU path) ----
  * Fused Adam over ONE flat float32 buffer holding every hot-path parameter, with the semantics of
  * torch.optim.Adam as the reference's trainer constructs it (config/Config.py:300: lr only, betas

@@ -33,7 +33,7 @@ def producer(state):
 def rel_close(a, b, tol, what):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     assert a.shape == b.shape, (what, a.shape, b.shape)
-    scale = max(float(b.abs().max()), 1e-3)
+    scale = max(float(b.abs().max()), 1e-2)      # (softmax-shift biases have a true gradient of 0: rounding noise only)
     d = float((a - b).abs().max()) / scale
     assert d <= tol, f"{what}: max|diff| / max|ref| = {d:.3e} > {tol:.1e}"
 
@@ -170,7 +170,7 @@ def test_document_without_active_slots_gets_the_bias_and_bf16_storage():
     assert torch.allclose(ef.linear_sentence_att[0].bias.grad.cpu(), torch.full((128,), float(w.n * w.n)))
     eb = ef(0, ctx, x, state["dis_embed.weight"].to(DEV), tabs, edge_dtype=torch.bfloat16)
     assert eb.dtype == torch.bfloat16
-    assert float((eb.float().cpu() - e.detach().cpu()).abs().max()) <= 2e-2
+    assert float((eb.detach().float().cpu() - e.detach().cpu()).abs().max()) <= 2e-2
 
 
 def test_pair_with_every_slot_active_divides_by_1e_minus_10():
