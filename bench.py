@@ -312,7 +312,7 @@ def kernel_roofline(name, launches, ms, flop, bt, H, L, esz, steps, hbm_peak, te
 
 
 # ------------------------------------------------------------------------------- pooling / pair gathers
-def aux_rates(dev, hbm_peak, tiles=128, iters=10):
+def aux_rates(dev, hbm_peak, tensor_peak, tiles=128, iters=10):
     """the mention->entity pooling (a1) and the classifier-side pair gathers (a8) are timed apart from
     the graph blocks, each against its own algorithmic bytes.  12-document batch x `tiles`, device-resident,
     CUDA events around `iters` back-to-back calls after 3 warm-up calls (outputs of the gathers are 2.7 GB per
@@ -390,7 +390,233 @@ def aux_rates(dev, hbm_peak, tiles=128, iters=10):
         sec = clock(fn)
         out[name] = {"us": sec * 1e6, "bytes": nbytes, "achieved": nbytes / sec / 1e9, "unit": "GB/s",
                      "frac": nbytes / sec / 1e9 / hbm_peak, "graphs_per_s": len(docs) / sec}
+    del keep["p"], keep["d"], dh, dt, dh128, dt128
+    torch.cuda.empty_cache()
+
+    # ---- the edge-feature producer (word + sentence attention) on the same 1536 documents ----
+    from gcgcn_b200.edgefeat import EdgeFeatures, EdgeTables
+    wires = [synthetic.make_wire(d) for d in docs[:12]] * tiles
+    etabs = EdgeTables(wires, bt, dev)
+    torch.manual_seed(2)
+    producer = EdgeFeatures().to(dev)
+    x_nodes = torch.tanh(torch.randn(n1, 128, device=dev, generator=gen)).requires_grad_(True)
+    de = torch.randn(n2, 128, device=dev, generator=gen)
+
+    def edge_f():
+        keep["e"] = producer(0, ctx, x_nodes, dis, etabs)
+
+    def edge_b():
+        torch.autograd.grad(keep["e"], [ctx, x_nodes, dis] + list(producer.word_attention[0].parameters()), de,
+                            retain_graph=True, allow_unused=True)
+
+    for name, fn, nbytes in (("edge_features_fwd", edge_f, n2 * 512 + etabs.num_tokens * 1024),
+                             ("edge_features_bwd", edge_b, n2 * 512 + etabs.num_tokens * 1024)):
+        sec = clock(fn)
+        out[name] = {"us": sec * 1e6, "bytes": nbytes, "achieved": nbytes / sec / 1e9, "unit": "GB/s",
+                     "frac": nbytes / sec / 1e9 / hbm_peak, "graphs_per_s": len(docs) / sec,
+                     "active_slots": etabs.num_slots, "active_tokens": etabs.num_tokens,
+                     "note": "algorithmic bytes: the [pairs, 128] edge tensor written (fwd) / its gradient read (bwd) once "
+                             "+ the active context rows; the reference forms [n, n, S, L, 128] tensors here"}
+    del keep["e"], de
+    torch.cuda.empty_cache()
+
+    # ---- Bilinear(128,128,97) + Linear(256,97) + the trainer's loss on 256 documents ----
+    from gcgcn_b200.classifier import pair_bce_loss, relation_logits
+    cdocs = 12 * 16
+    cbt = RaggedBatch([d.n for d in docs[:cdocs]], dev)
+    P = cbt.total_pairs
+    torch.manual_seed(3)
+    bili = torch.nn.Bilinear(128, 128, 97).to(dev)
+    cls = torch.nn.Linear(256, 97).to(dev)
+    fh = torch.tanh(torch.randn(P, 128, device=dev, generator=gen)).requires_grad_(True)
+    ft = torch.tanh(torch.randn(P, 128, device=dev, generator=gen)).requires_grad_(True)
+    labels = (torch.rand(P, 97, device=dev, generator=gen) < 0.02).float()
+
+    def cls_f():
+        keep["z"] = relation_logits(fh, ft, bili, cls)
+        keep["loss"] = pair_bce_loss(keep["z"], labels, cbt)
+
+    def cls_b():
+        torch.autograd.grad(keep["loss"].sum(), [fh, ft] + list(bili.parameters()) + list(cls.parameters()), retain_graph=True)
+
+    flop = 2.0 * P * (128 * 128 * 97 + 256 * 97)
+    for name, fn, mult in (("classifier_fwd", cls_f, 1.0), ("classifier_bwd", cls_b, 3.0)):
+        sec = clock(fn)
+        out[name] = {"us": sec * 1e6, "pairs": P, "documents": cdocs, "fp32_equivalent_tflops": mult * flop / sec / 1e12,
+                     "executed_tf32_tflops": 3.0 * mult * flop / sec / 1e12, "unit": "TFLOP/s",
+                     "frac": 3.0 * mult * flop / sec / 1e12 / tensor_peak, "graphs_per_s": cdocs / sec,
+                     "note": "bilinear as Y = h W' on the tcgen05 GEMM (3xTF32) + row reductions, pairs in chunks of 8192; "
+                             "backward = forward product recomputed + two more products (3x the forward flops)"}
+    del keep["z"], keep["loss"]
+    torch.cuda.empty_cache()
+
+    # ---- drop-in use (B = 1): the reference's own call sequence (G:330-341) with the drop-in modules, one document at
+    # a time like the reference trainer (C:339), fwd+bwd, over the 12-document batch ----
+    from gcgcn_b200.modules import GraphBlocks
+    torch.manual_seed(0)
+    gbm = GraphBlocks(2, 8).to(dev).eval()
+    gat, mha, cag, mag = gbm.get_weighted_adj_matrix, gbm.get_adj_matrix[0], gbm.graphcnn[0], gbm.graphcnn[1]
+    b1 = []
+    for d in docs[:12]:
+        b1.append((d.x0.to(dev).requires_grad_(True), d.e0.to(dev).requires_grad_(True), d.e1.to(dev).requires_grad_(True),
+                   torch.eq(d.adj.to(dev), 0), torch.randn(d.n, 128, device=dev), torch.randn(d.n, 128, device=dev)))
+
+    def dropin_pass():
+        for x, e0_, e1_, mask, g1, g2 in b1:
+            a0 = gat(x, e0_, mask)                                   # G:332
+            y1 = cag(x, e0_, a0)                                     # G:333
+            a1 = mha(y1, e1_)                                        # G:336
+            y2 = mag(y1, e1_, a1)                                    # G:337
+            torch.autograd.backward([y1, y2], [g1, g2])
+
+    sec = clock(dropin_pass)
+    out["dropin_b1"] = {"us_per_document": sec * 1e6 / 12, "graphs_per_s": 12 / sec,
+                        "note": "per-document drop-in modules (GATAttention -> GraphConvolution -> MultiHeadAttention -> "
+                                "MultiGraphConvolution forward + backward), B = 1 per call, 12 documents one at a time; "
+                                "compare cpu_baseline.reference_eager_cuda (the reference's ATen ops on the same GPU)"}
     return out
+
+
+
+# ------------------------------------------------------------------------------- end-to-end arm
+def run_e2e(args, dev, gb, bt, gb_params, timed, world, ndocs):
+    """The e2e leg of run_gpu_arm (see the comment at its call site).  Two complete device-side input sets (context,
+    upstream gradients and every index table) are alternated: while step i computes on one, step i+1's inputs are
+    copied into the other on a copy stream.  One window = `count` steps and exactly `count` full host->device input
+    copies, all inside the window; it closes after the last device->host read."""
+    import numpy as np
+    import torch
+    from gcgcn_b200 import synthetic
+    from gcgcn_b200.batch import PoolTable, RaggedBatch
+    from gcgcn_b200.edgefeat import EdgeFeatures, EdgeTables
+    from gcgcn_b200.modules import pool_nodes
+    from gcgcn_b200.sharding import GradBucket
+
+    docs12 = synthetic.make_batch()
+    wires12 = [synthetic.make_wire(d) for d in docs12]
+    reps = ndocs // 12
+    wires = wires12 * reps
+    torch.manual_seed(1)
+    producer = EdgeFeatures().to(dev)
+    producer.train(gb.training)
+    dis_embed = torch.randn(21, 20, device=dev).requires_grad_(True)
+    params = list(gb_params) + list(producer.parameters()) + [dis_embed]
+    bucket = GradBucket(params)
+
+    class Set:
+        """one device-side input set + the pinned host buffers it is refilled from"""
+        def __init__(self):
+            self.bt = RaggedBatch(bt.sizes, dev)
+            self.pool = PoolTable.from_spans([d.spans for d in docs12] * reps, [d.L for d in docs12] * reps, device=dev)
+            self.edge = EdgeTables(wires, self.bt, dev)
+            tok = self.pool.total_tokens
+            self.ctx = torch.empty(tok, 128, device=dev)
+            self.dy1 = torch.empty(bt.total_nodes, 128, device=dev)
+            self.dy2 = torch.empty(bt.total_nodes, 128, device=dev)
+            # entities pooled + the producer's active context rows fetched in one pass (one gather, one transpose)
+            self.rows = PoolTable.concat(self.pool, self.edge.gather, dev)
+            self.tables = [self.bt.node_ptr, self.bt.pair_ptr, self.bt.row_doc, self.bt.doc_order]
+            self.tables += [getattr(self.rows, k) for k in ("ent_ptr", "tok_idx", "w", "tok_ptr", "ent_idx", "w_t")]
+            self.tables += list(self.edge.dev.values()) + [self.edge.pair_idx, self.edge.pair_denom]
+
+    sets = [Set(), Set()]
+    gen = torch.Generator().manual_seed(4242 + int(os.environ.get("RANK", "0")))
+    tok = sets[0].pool.total_tokens
+    host = {"ctx": torch.tanh(torch.randn(tok, 128, generator=gen)).pin_memory(),
+            "dy1": torch.randn(bt.total_nodes, 128, generator=gen).pin_memory(),
+            "dy2": torch.randn(bt.total_nodes, 128, generator=gen).pin_memory()}
+    host_tables = [t.detach().cpu().pin_memory() for t in sets[0].tables]
+    host_out = {k: torch.empty(bt.total_nodes, 128).pin_memory() for k in ("y1", "y2")}
+    host_grads = torch.empty(bucket.flat.numel()).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host.values()) + sum(t.numel() * t.element_size() for t in host_tables)
+    d2h = 2 * bt.total_nodes * 128 * 4 + host_grads.numel() * 4
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    window = {"i": 0, "count": 0}
+
+    def stage(sidx):
+        st = sets[sidx]
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            copy_stream.wait_event(freed[sidx])
+            st.ctx.copy_(host["ctx"], non_blocking=True)
+            st.dy1.copy_(host["dy1"], non_blocking=True)
+            st.dy2.copy_(host["dy2"], non_blocking=True)
+            for h, dv in zip(host_tables, st.tables):
+                dv.copy_(h, non_blocking=True)
+            ready[sidx].record(copy_stream)
+
+    def e2e_step():
+        i = window["i"]
+        sidx = i % 2
+        main = torch.cuda.current_stream(dev)
+        if i == 0:
+            stage(sidx)
+        if i + 1 < window["count"]:
+            stage(1 - sidx)                               # next step's inputs: overlaps this step's kernels
+        main.wait_event(ready[sidx])
+        st = sets[sidx]
+        for p in params:
+            p.grad = None
+        ctx = st.ctx.detach().requires_grad_(True)
+        rows = pool_nodes(ctx, st.rows)                                       # G:297-298 + the rows G:300 reads
+        x0, act = rows[:bt.total_nodes], rows[bt.total_nodes:]
+        e0 = producer(0, None, x0, dis_embed, st.edge, ctx_act=act)           # G:313-326, hop 0
+        y1, _ = gb.hop0(x0, e0, st.bt)                                        # G:330-341
+        e1 = producer(1, None, y1, dis_embed, st.edge, ctx_act=act)           # hop 1 consumes y1
+        y2, _ = gb.hop1(y1, e1, st.bt)
+        torch.autograd.backward([y1, y2], [st.dy1, st.dy2])
+        bucket.pack()
+        if world > 1:
+            bucket.all_reduce()
+        host_out["y1"].copy_(y1.detach(), non_blocking=True)
+        host_out["y2"].copy_(y2.detach(), non_blocking=True)
+        host_grads.copy_(bucket.flat, non_blocking=True)
+        freed[sidx].record(main)
+        window["i"] = i + 1
+
+    def e2e_window(count):
+        window.update(i=0, count=count)
+        copy_stream.synchronize()
+        ms_w, launches, _ = timed(e2e_step, count)
+        copy_stream.synchronize()
+        return ms_w, launches
+
+    e2e_window(3)                                         # warm-up window (pinned pages touched, pools grown)
+    steps = max(20, args.steps)
+    ms_e, launches = e2e_window(steps)
+    # the same pipeline with the inputs already resident (no copies): what the copies cost on top of the kernels
+    def dev_step():
+        st = sets[0]
+        for p in params:
+            p.grad = None
+        ctx = st.ctx.detach().requires_grad_(True)
+        rows = pool_nodes(ctx, st.rows)
+        x0, act = rows[:bt.total_nodes], rows[bt.total_nodes:]
+        e0 = producer(0, None, x0, dis_embed, st.edge, ctx_act=act)
+        y1, _ = gb.hop0(x0, e0, st.bt)
+        e1 = producer(1, None, y1, dis_embed, st.edge, ctx_act=act)
+        y2, _ = gb.hop1(y1, e1, st.bt)
+        torch.autograd.backward([y1, y2], [st.dy1, st.dy2])
+    for _ in range(3):
+        dev_step()
+    ms_d, _, _ = timed(dev_step, max(10, args.steps))
+    for p in gb_params:
+        p.grad = None
+    return {"value": world * ndocs * steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / steps, "steps": steps,
+            "h2d_gbs": h2d * steps / (ms_e * 1e-3) / 1e9, "gpu_launches_per_step": launches / steps,
+            "device_resident_ms_per_step": ms_d / max(10, args.steps),
+            "active_slots": sets[0].edge.num_slots, "active_tokens": sets[0].edge.num_tokens, "tokens": tok,
+            "wire_bytes_per_doc": sum(w.nbytes for w in wires12) / 12.0,
+            "note": "inputs from pinned host memory every step: context_output of all documents (fp32), the upstream "
+                    "gradients dy1/dy2 and every index table (batch offsets, pooling CSR, active-slot tables of the "
+                    "edge-feature producer); the edge tensors e0/e1 are produced on the device by the producer "
+                    "(G:299-327) from context + node features and consumed by CAGGC/MAGGC there; y1, y2 and the "
+                    "parameter-gradient bucket (graph blocks + producer) are read back; d loss/d context stays on the "
+                    "device (its consumer, the encoder's backward, lives there).  Double-buffered: the copy of step "
+                    "i+1 overlaps the kernels of step i; exactly one full input copy per timed step, none staged "
+                    "before the window opens; the window closes after the last device->host read."}
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -526,72 +752,14 @@ def run_gpu_arm(args):
         clocks["window"] = "warm-up steps + timed region (same kernels, back to back)"
     value = world * ndocs * args.steps / (ms * 1e-3)
 
-    # ---- end to end from pinned host buffers (same step; H2D of inputs and D2H of results inside)
+    # ---- end to end from pinned host buffers: what the caller of the plugin holds on the host is the encoder output
+    # (context_output) and the wire format of the documents; the edge tensors e0/e1 are produced ON the device by the
+    # edge-feature producer (G:299-327; they never exist on the host in the model), so one e2e step is
+    #   H2D(ctx, upstream gradients, index tables) -> pooling -> producer(hop 0) -> CAGGC -> producer(hop 1) -> MAGGC
+    #   -> backward of all of it -> D2H(y1, y2, parameter gradients)
     e2e = None
-    if not args.no_e2e:
-        host_in = [t.detach().cpu().pin_memory() for t in (x0, e0, e1, dy1, dy2)]
-        dev_in = [x0, e0, e1, dy1, dy2]
-        host_out = {k: torch.empty(bt.total_nodes, 128).pin_memory() for k in ("y1", "y2", "dx0")}
-        host_grads = torch.empty(bucket.flat.numel()).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in host_in)
-        d2h = 3 * bt.total_nodes * 128 * 4 + host_grads.numel() * 4
-
-        # two device-side input sets: while one step computes on set s, the next step's inputs are copied into the
-        # other set on a copy stream (every timed step still pays one full H2D of a step's inputs and its D2H)
-        sets = [dev_in, [t.detach().clone().requires_grad_(t.requires_grad) for t in dev_in]]
-        copy_stream = torch.cuda.Stream(dev)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]      # the inputs of set s are on the device
-        freed = [torch.cuda.Event(), torch.cuda.Event()]      # the compute that read set s is done
-        def stage(sidx):
-            with torch.cuda.stream(copy_stream), torch.no_grad():
-                copy_stream.wait_event(freed[sidx])
-                for h, dv in zip(host_in, sets[sidx]):
-                    dv.copy_(h, non_blocking=True)
-                ready[sidx].record(copy_stream)
-
-        # One window = `count` steps and exactly `count` host->device input copies, ALL inside the window: step 0
-        # stages its own inputs after the window opened, step i stages step i+1's (overlapping step i's kernels) and
-        # the last step stages nothing, so when the closing event is recorded on the main stream -- after the last
-        # step's device->host reads, which are issued on it -- the copy stream is idle as well.
-        window = {"i": 0, "count": 0}
-
-        def e2e_step():
-            i = window["i"]
-            sidx = i % 2
-            main = torch.cuda.current_stream(dev)
-            if i == 0:
-                stage(sidx)
-            if i + 1 < window["count"]:
-                stage(1 - sidx)                               # next step's inputs: overlaps this step's kernels
-            main.wait_event(ready[sidx])
-            out = run_step(sets[sidx])
-            if world == 1:
-                bucket.pack()
-            host_out["y1"].copy_(out["y1"].detach(), non_blocking=True)
-            host_out["y2"].copy_(out["y2"].detach(), non_blocking=True)
-            host_out["dx0"].copy_(sets[sidx][0].grad, non_blocking=True)
-            host_grads.copy_(bucket.flat, non_blocking=True)
-            freed[sidx].record(main)
-            window["i"] = i + 1
-
-        def e2e_window(count):
-            window.update(i=0, count=count)
-            copy_stream.synchronize()
-            ms_w, _, _ = timed(e2e_step, count)
-            copy_stream.synchronize()
-            return ms_w
-
-        e2e_window(2)                                         # warm-up window (pinned pages touched, pools grown)
-        e2e_steps = max(20, args.steps)
-        ms_e = e2e_window(e2e_steps)
-        e2e = {"value": world * ndocs * e2e_steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
-               "h2d_gbs": h2d * e2e_steps / (ms_e * 1e-3) / 1e9,
-               "note": "inputs x0,e0,e1,dy1,dy2 from pinned host memory (double-buffered on the device: the copy of "
-                       "step i+1 overlaps the kernels of step i); the timed window holds exactly one full input copy "
-                       "per step, none staged before it opens, and closes after the last device->host read; "
-                       "y1,y2,dx0 and the parameter-gradient bucket read back; de0/de1 stay on the device (their "
-                       "consumer, the edge-feature producer's backward, lives there)"}
+    if not args.no_e2e and not args.nodes:
+        e2e = run_e2e(args, dev, gb, bt, params, timed, world, ndocs)
 
     if rank != 0:
         if world > 1:
@@ -653,7 +821,7 @@ def run_gpu_arm(args):
     if not args.no_aux and not args.nodes:
         for t in (x0, e0, e1):
             t.grad = None
-        aux = aux_rates(dev, hbm_peak)
+        aux = aux_rates(dev, hbm_peak, tensor_peak)
     cpu = None
     if not args.no_cpu_baseline:
         rate, info = cpu_oracle_rate(args.variant, args.cpu_seconds)

@@ -146,6 +146,17 @@ class PoolTable:
         return self
 
     @classmethod
+    def concat(cls, a: "PoolTable", b: "PoolTable", device=None):
+        """Rows of ``a`` followed by rows of ``b`` over the same token space: one gather launch (and one transposed
+        gather in the backward) serves both -- the graph head pools the entities and fetches the producer's active
+        context rows in a single pass over ``context_output``."""
+        if a.total_tokens != b.total_tokens:
+            raise ValueError("both tables must index the same token rows")
+        ent_ptr = np.concatenate([a.ent_ptr_host, a.ent_ptr_host[-1] + b.ent_ptr_host[1:]])
+        return cls(ent_ptr, np.concatenate([a.tok_idx_host, b.tok_idx_host]), np.concatenate([a.w_host, b.w_host]),
+                   a.total_tokens, device)
+
+    @classmethod
     def from_spans(cls, docs_spans: Sequence[Sequence[Sequence[Sequence[int]]]],
                    doc_lens: Sequence[int], max_length: int = MAX_LENGTH, device=None):
         """docs_spans[b][e] = [[start, end), ...] in document-local token positions."""

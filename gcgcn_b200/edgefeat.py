@@ -278,18 +278,23 @@ class EdgeFeatures(nn.Module):
         self.linear_word_att = nn.ModuleList([nn.Linear(hidden_size * 2, hidden_size) for _ in range(graph_hop)])
         self.linear_sentence_att = nn.ModuleList([nn.Linear(hidden_size * 2, hidden_size) for _ in range(graph_hop)])
 
-    def forward(self, hop: int, context: torch.Tensor, node_feat: torch.Tensor, dis_embed: torch.Tensor,
-                tabs: EdgeTables, edge_dtype=torch.float32) -> torch.Tensor:
+    def forward(self, hop: int, context: Optional[torch.Tensor], node_feat: torch.Tensor, dis_embed: torch.Tensor,
+                tabs: EdgeTables, edge_dtype=torch.float32, ctx_act: Optional[torch.Tensor] = None) -> torch.Tensor:
         """context [total_tokens, 128] (``context_output`` of every document back to back), node_feat
         [total_nodes, 128] (the hop's node features), dis_embed [21, 20] (``dis_embed.weight``) ->
-        context_sent_att of every pair of the batch, [total_pairs, 128]  (G:313-326 for hop ``hop``)."""
+        context_sent_att of every pair of the batch, [total_pairs, 128]  (G:313-326 for hop ``hop``).
+        ``ctx_act`` = the active context rows ``context[tabs.act_tok]`` when the caller has gathered them already
+        (both hops read the same rows; ``context`` may then be None)."""
+        if context is None:
+            context = ctx_act
         if not context.is_cuda:
             raise _lib.GcgcnError("EdgeFeatures: gcgcn_b200 runs on CUDA only (no CPU fallback)")
         wa, sa = self.word_attention[hop], self.sentence_attention[hop]
         lw, ls = self.linear_word_att[hop], self.linear_sentence_att[hop]
         if tabs.num_slots == 0:           # no sentence contains token 0: every pair gets the bias (G:326 on zeros)
             return EdgeFillFn.apply(context.new_zeros(0, D), ls.bias, tabs, edge_dtype)
-        ctx_act = PoolFn.apply(context, tabs.gather)                                  # rows of the first sentences
+        if ctx_act is None:
+            ctx_act = PoolFn.apply(context, tabs.gather)                              # rows of the first sentences
         SF = linear(ctx_act, wa.attention_sent)                                       # G:179
         DF = linear(dis_embed, wa.attention_pos)                                      # G:180 on the 21 table rows
         T = WordTableFn.apply(SF, DF, wa.attention_all.weight, wa.attention_all.bias)  # G:183

@@ -36,6 +36,8 @@ class HeadBatch:
         self.node_type = torch.from_numpy(np.concatenate([np.asarray(d.node_type, dtype=np.int64) for d in docs])
                                           if docs else np.zeros(0, np.int64)).to(self.device)
         self.total_tokens = self.pool.total_tokens
+        # entities pooled and the producer's active context rows fetched in ONE pass over context_output
+        self.pool_and_active = PoolTable.concat(self.pool, self.edge.gather, self.device)
 
     @property
     def wire_nbytes(self) -> int:
@@ -76,10 +78,11 @@ class GraphHead(nn.Module):
             raise _lib.GcgcnError("GraphHead: gcgcn_b200 runs on CUDA only (no CPU fallback)")
         bt, blocks, edge = hb.batch, self._blocks, self._edge
         dis = self.dis_embed.weight
-        x0 = pool_nodes(context, hb.pool)                                              # G:297-298
-        e0 = edge(0, context, x0, dis, hb.edge, edge_dtype)                            # G:313-326, i = 0
+        rows = pool_nodes(context, hb.pool_and_active)                                 # G:297-298 + the rows G:300 reads
+        x0, ctx_act = rows[:bt.total_nodes], rows[bt.total_nodes:]
+        e0 = edge(0, None, x0, dis, hb.edge, edge_dtype, ctx_act)                      # G:313-326, i = 0
         y1, a0 = blocks.hop0(x0, e0, bt)                                               # G:330-341
-        e1 = edge(1, context, y1, dis, hb.edge, edge_dtype)                            # G:313-326, i = 1
+        e1 = edge(1, None, y1, dis, hb.edge, edge_dtype, ctx_act)                      # G:313-326, i = 1
         y2, a1 = blocks.hop1(y1, e1, bt)                                               # G:336-341 (dead for the logits, G:338)
         type_feats = nn.functional.embedding(hb.node_type, self.ner_emb.weight, padding_idx=0)
         feats = torch.cat([x0, x0, y1, type_feats], 1)                                 # G:343-347: cat[x0, x0, y1, type]

@@ -159,3 +159,36 @@ def make_record(seed: int, n: Optional[int] = None, L: Optional[int] = None, S: 
     return {"document": rng.randint(1, 1000, size=L).tolist(), "document_pos": rng.randint(0, n + 1, size=L).tolist(),
             "document_ner": rng.randint(0, 7, size=L).tolist(), "graph": g, "title": f"synthetic-{seed}",
             "label_matrix": np.zeros((n, n, 97), dtype=np.float32), "label_mask": []}
+
+
+# ------------------------------------------------------------------------------- wire format of the DocRED-shaped batch
+def make_wire(doc: Doc, max_num: int = 5):
+    """The wire format (featurize.WireDoc) of a synthetic ``Doc``: its mention spans, types and first positions, plus
+    sentences, edges and (edge, sentence slot) rows generated the way the reference's preprocessing defines them
+    (gen_data_extend_graph.py:209-261): sentences of 12-40 tokens partition the document, an edge (u, v) exists iff
+    the two entities have mentions in a common sentence, with one slot per such mention pair."""
+    from .featurize import WireDoc
+    rng = np.random.RandomState(977 + doc.doc_id)
+    bounds = [0]
+    while bounds[-1] < doc.L:
+        bounds.append(min(doc.L, bounds[-1] + int(rng.randint(12, 41))))
+    bounds = np.asarray(bounds)
+    sent_of = lambda a: int(np.searchsorted(bounds, a, side="right") - 1)
+    ment = [[(a, b, sent_of(a)) for a, b in ms] for ms in doc.spans]
+    edges, slots, most = [], [], 0
+    for u in range(doc.n):
+        for v in range(doc.n):
+            if u == v:
+                continue
+            j = 0
+            for a0, a1, sa in ment[u]:
+                for b0, b1, sb in ment[v]:
+                    if sa == sb:
+                        slots.append((u, v, j, int(bounds[sa]), int(bounds[sa + 1]), a0, a1, b0, b1))
+                        j += 1
+            if j:
+                edges.append((u, v))
+                most = max(most, j)
+    return WireDoc(n=doc.n, length=doc.L, max_num=min(max(most, 1), max_num), spans=doc.spans,
+                   node_type=doc.node_type.numpy().astype(np.int64), first_pos=np.asarray(doc.first_pos, dtype=np.int64),
+                   edges=np.asarray(edges, dtype=np.int32).reshape(-1, 2), slots=np.asarray(slots, dtype=np.int32).reshape(-1, 9))
