@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the separate pooling / pair-gather timings")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[2] / configs[3] points of the aux section")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -478,6 +479,78 @@ def aux_rates(dev, hbm_peak, tensor_peak, tiles=128, iters=10):
 
 
 
+
+# ------------------------------------------------------------------------------- configs[2] / configs[3] inside the default run
+def graph_block_point(dev, layers, heads, sizes, edge_dtype, hbm_peak, steps=5, warmup=3):
+    """One device-resident measurement of the graph blocks (fwd+bwd, eval mode) on a batch of `sizes` entity counts:
+    graphs/s and the whole-path fraction of the HBM roofline (SURVEY 8d algorithmic bytes / step time)."""
+    import torch
+    from gcgcn_b200.batch import RaggedBatch
+    from gcgcn_b200.modules import GraphBlocks
+    torch.manual_seed(0)
+    gbs = GraphBlocks(layers, heads).to(dev).eval()
+    btx = RaggedBatch(sizes, dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x0 = torch.tanh(torch.randn(btx.total_nodes, 128, device=dev, generator=gen)).requires_grad_(True)
+    e0 = torch.randn(btx.total_pairs, 128, device=dev, generator=gen).to(edge_dtype).requires_grad_(True)
+    e1 = torch.randn(btx.total_pairs, 128, device=dev, generator=gen).to(edge_dtype).requires_grad_(True)
+    dy1 = torch.randn(btx.total_nodes, 128, device=dev, generator=gen)
+    dy2 = torch.randn(btx.total_nodes, 128, device=dev, generator=gen)
+    ps = [p for n, p in gbs.named_parameters() if "linears_k" not in n]
+
+    def one():
+        x0.grad = e0.grad = e1.grad = None
+        for p in ps:
+            p.grad = None
+        out = gbs(x0, e0, e1, btx)
+        torch.autograd.backward([out["y1"], out["y2"]], [dy1, dy2])
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        one()
+    ev1.record()
+    torch.cuda.synchronize()
+    sec = ev0.elapsed_time(ev1) * 1e-3 / steps
+    esz = 4 if edge_dtype == torch.float32 else 2
+    alg = btx.algorithmic_bytes(esz, backward=True)
+    res = {"documents": btx.num_docs, "max_entities": btx.max_nodes, "layer_num": layers, "head_num": heads,
+           "edge_storage": "fp32" if esz == 4 else "bf16", "ms_per_step": sec * 1e3, "graphs_per_s": btx.num_docs / sec,
+           "path_bytes_per_step": alg, "path_achieved_gbs": alg / sec / 1e9, "path_frac": alg / sec / 1e9 / hbm_peak,
+           "edge_bytes_per_tensor": btx.total_pairs * 128 * esz}
+    del x0, e0, e1, dy1, dy2, gbs
+    torch.cuda.empty_cache()
+    return res
+
+
+def sweep_and_variants(dev, hbm_peak, edge_gb=4.0):
+    """BASELINE.json configs[3] (entity-count sweep 42/128/256 x 4/8 heads, fully connected, n^2 edge tensors of
+    `edge_gb` GB each so that every point streams far more than L2) and configs[2] (the BERT graph head L_s=4, H=4 with
+    bf16 edge storage on the DocRED-shaped batch), measured inside the default run so that the driver's record carries
+    them."""
+    import numpy as np
+    import torch
+    from gcgcn_b200 import synthetic
+    out = {"sweep": [], "note": "device-resident inputs, CUDA events around 5 steps after 3 warm-up steps; path_frac = "
+                                "SURVEY 8d algorithmic bytes / step time / measured HBM peak"}
+    for n in (42, 128, 256):
+        for h in (4, 8):
+            ndoc = max(1, int(edge_gb * 1e9 // (n * n * 512)))
+            r = graph_block_point(dev, 2, h, np.full(ndoc, n, dtype=np.int64), torch.float32, hbm_peak)
+            r["workload"] = f"configs[3]: {ndoc} fully connected graphs of {n} entities, {h} heads"
+            out["sweep"].append(r)
+    r = graph_block_point(dev, 4, 4, synthetic.shard_doc_sizes(12 * 512), torch.bfloat16, hbm_peak)
+    r["workload"] = "configs[2]: GCGCN_Bert graph head (L_s=4, H=4), bf16 edge storage, fp32 accumulate, 6144 documents"
+    out["config2_bert_bf16"] = r
+    r = graph_block_point(dev, 4, 4, synthetic.shard_doc_sizes(12 * 512), torch.float32, hbm_peak)
+    r["workload"] = "GCGCN_Bert graph head shapes (L_s=4, H=4), fp32 edge storage, 6144 documents"
+    out["bert_head_fp32"] = r
+    return out
+
+
 # ------------------------------------------------------------------------------- end-to-end arm
 def run_e2e(args, dev, gb, bt, gb_params, timed, world, ndocs):
     """The e2e leg of run_gpu_arm (see the comment at its call site).  Two complete device-side input sets (context,
@@ -669,18 +742,27 @@ def run_gpu_arm(args):
     dy2 = torch.randn(bt.total_nodes, 128, device=dev, generator=gen)
     params = [p for n, p in gb.named_parameters() if "linears_k" not in n]
     bucket = GradBucket(params)
+    overlapped = None
+    if world > 1:
+        # backward runs MAGGC -> CAGGC: the MAGGC / MultiHeadAttention gradients are final first, and their all-reduce
+        # (1.8 of the 2.2 MB) rides a side stream under the CAGGC backward; the CAGGC / GAT bucket follows
+        from gcgcn_b200.sharding import OverlappedBuckets
+        named = [(n, p) for n, p in gb.named_parameters() if "linears_k" not in n]
+        late = [p for n, p in named if n.startswith(("graphcnn.0", "get_weighted_adj_matrix"))]
+        early = [p for n, p in named if not n.startswith(("graphcnn.0", "get_weighted_adj_matrix"))]
+        overlapped = OverlappedBuckets([early, late])
 
     def run_step(inp):
         x0_, e0_, e1_, dy1_, dy2_ = inp
         x0_.grad = e0_.grad = e1_.grad = None
         for p in params:
             p.grad = None
+        if overlapped is not None:
+            overlapped.reset()
         out = gb(x0_, e0_, e1_, bt)
         torch.autograd.backward([out["y1"], out["y2"]], [dy1_, dy2_])
-        if world > 1:
-            bucket.pack()
-            bucket.all_reduce()
-            bucket.unpack()
+        if overlapped is not None:
+            overlapped.finish()
         return out
 
     def step():
@@ -822,6 +904,10 @@ def run_gpu_arm(args):
         for t in (x0, e0, e1):
             t.grad = None
         aux = aux_rates(dev, hbm_peak, tensor_peak)
+        if not args.no_sweep and world == 1:
+            del x0, e0, e1, dy1, dy2
+            torch.cuda.empty_cache()
+            aux.update(sweep_and_variants(dev, hbm_peak))
     cpu = None
     if not args.no_cpu_baseline:
         rate, info = cpu_oracle_rate(args.variant, args.cpu_seconds)
@@ -837,7 +923,9 @@ def run_gpu_arm(args):
                    "total_pairs": bt.total_pairs, "parallelism": f"doc-sharded dp{world}",
                    "l2": f"inputs larger than L2: {2 * bt.total_pairs * 128 * esz / 1e9:.2f} GB of edge features "
                          "streamed per step",
-                   "collective": "none" if world == 1 else f"one NCCL all-reduce of {bucket.nbytes} B per step",
+                   "collective": "none" if world == 1 else
+                                 f"NCCL all-reduce of the {bucket.nbytes} B of parameter gradients per step in two buckets "
+                                 "(MAGGC first, issued from a gradient hook on a side stream under the CAGGC backward)",
                    "launch": "eager (one C-ABI call per op)" if graphed is None else
                              "CUDA-graph replay of the captured forward+backward pass (same kernels as eager)",
                    "eager_ms_per_step": ms_eager / args.steps,

@@ -19,6 +19,7 @@ from .batch import RaggedBatch
 from .functional import D, LinearFn, _cuda, _p, _stream, gemm, workspace
 
 CHUNK_PAIRS = 8192          # 8192 pairs x 97 x 128 floats = 407 MB of Y per chunk
+FUSED_FORWARD = True        # False: the forward materialises Y = h W' chunk by chunk like the backward does (test hook)
 
 
 def _wmat(W: torch.Tensor) -> torch.Tensor:
@@ -38,12 +39,18 @@ class BilinearFn(Function):
             raise _lib.GcgcnError(f"bilinear: expected h, t [P, {D}] and weight [R, {D}, {D}]")
         Wm = _wmat(W)
         out = torch.empty(P, R, device=dev)
-        for p0 in range(0, P, CHUNK_PAIRS):
-            p1 = min(P, p0 + CHUNK_PAIRS)
-            Y = gemm(h[p0:p1], Wm)
-            _lib.call("gcgcn_bilinear_reduce_fwd", _p(Y), _p(t[p0:p1]), _p(bias), p1 - p0, R, 0, _p(out[p0:p1]), R,
+        if FUSED_FORWARD and P > 0:
+            # one tensor-core pass: the accumulator tiles of h W' are contracted with t in the GEMM's epilogue
+            ws = workspace(dev, int(_lib.load().gcgcn_bilinear_ws_bytes(P, R)))
+            _lib.call("gcgcn_bilinear_fwd", _p(h), _p(t), _p(Wm), _p(bias), P, R, 0, _p(out), R, ws.data_ptr(), ws.numel(),
                       _stream(dev))
-            del Y
+        else:
+            for p0 in range(0, P, CHUNK_PAIRS):
+                p1 = min(P, p0 + CHUNK_PAIRS)
+                Y = gemm(h[p0:p1], Wm)
+                _lib.call("gcgcn_bilinear_reduce_fwd", _p(Y), _p(t[p0:p1]), _p(bias), p1 - p0, R, 0, _p(out[p0:p1]), R,
+                          _stream(dev))
+                del Y
         ctx.save_for_backward(h, t, Wm)
         ctx.R = R
         return out

@@ -98,6 +98,10 @@ int launch_edge_fill_bwd(const void* de, const void* pair_idx, int pairs, long l
 
 int launch_bilinear_reduce(const float* Y, const float* t, const float* bias, int rows, int R, int accumulate, float* out,
                            int ldo, cudaStream_t st);
+int launch_bilinear_finish(const float* part, long long ld, const float* bias, int rows, int R, int accumulate, float* out,
+                           int ldo, cudaStream_t st);
+int launch_gemm_rowdot(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* T, float* part,
+                       long long part_ld, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_bilinear_outer(const float* dout, int ldd, const float* t, int rows, int R, float* dY, cudaStream_t st);
 int launch_bilinear_dt(const float* dout, int ldd, const float* Y, int rows, int R, float* dt, cudaStream_t st);
 int launch_pair_bce_fwd(const gcgcn_batch* bt, const float* z, const float* y, int R, float* loss, cudaStream_t st);
@@ -1042,6 +1046,33 @@ int gcgcn_bilinear_reduce_fwd(const float* Y, const float* t, const float* bias,
     GCGCN_TRY(check_device_ptr(out, "out"));
     return launch_bilinear_reduce(Y, t, bias, rows, relations, accumulate, out, ldo, static_cast<cudaStream_t>(stream));
 }
+size_t gcgcn_bilinear_ws_bytes(int32_t rows, int32_t relations) {
+    const size_t r = static_cast<size_t>(relations < 0 ? 0 : relations), m = static_cast<size_t>(rows < 0 ? 0 : rows);
+    const size_t ld = (m + 31) & ~size_t(31);
+    return align256(r * 4 * 33024) + align256(2 * r * ld * sizeof(float)) + 4096;      // pre-split W' blobs + partials
+}
+
+int gcgcn_bilinear_fwd(const float* h, const float* t, const float* Wm, const float* bias, int32_t rows,
+                       int32_t relations, int32_t accumulate, float* out, int32_t ldo, void* ws, size_t ws_bytes,
+                       void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(rows >= 0 && relations >= 0 && ldo >= relations, "bilinear_fwd: bad shape");
+    if (rows == 0 || relations == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(h, "h"));
+    GCGCN_TRY(check_device_ptr(t, "t"));
+    GCGCN_TRY(check_device_ptr(Wm, "Wm"));
+    GCGCN_TRY(check_device_ptr(out, "out"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(ws, ws_bytes);
+    const size_t ld = (static_cast<size_t>(rows) + 31) & ~size_t(31);
+    uint8_t* blobs = ar.take<uint8_t>(static_cast<size_t>(relations) * 4 * 33024);
+    float* part = ar.take<float>(2 * static_cast<size_t>(relations) * ld);
+    if (blobs == nullptr || part == nullptr) return fail(GCGCN_ERR_WORKSPACE, "bilinear_fwd: workspace too small");
+    GCGCN_TRY(launch_gemm_rowdot(rows, relations * D, D, h, D, Wm, relations * D, t, part, static_cast<long long>(ld), blobs,
+                                 static_cast<size_t>(relations) * 4 * 33024, st));
+    return launch_bilinear_finish(part, static_cast<long long>(ld), bias, rows, relations, accumulate, out, ldo, st);
+}
+
 int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int32_t rows, int32_t relations, float* dY,
                              void* stream) {
     GCGCN_API_ENTER(stream);

@@ -136,7 +136,42 @@ pair_bce_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restric
     }
 }
 
+// out[p][r] (+)= part[(2 r) ld + p] + part[(2 r + 1) ld + p] + bias[r]: the two column halves the row-dot GEMM leaves per
+// (pair, relation), transposed through shared memory so that both the reads (along p) and the writes (along r) coalesce
+__global__ void __launch_bounds__(256)
+bilinear_finish_kernel(const float* __restrict__ part, long long ld, const float* __restrict__ bias, int rows, int R,
+                       int accumulate, float* __restrict__ out, int ldo) {
+    __shared__ float tile[32][33];
+    const int p0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 8 warps
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int r = r0 + rr, p = p0 + tx;
+        float v = 0.f;
+        if (r < R && p < rows) v = part[(2LL * r) * ld + p] + part[(2LL * r + 1) * ld + p];
+        tile[rr][tx] = v;
+    }
+    __syncthreads();
+    for (int pp = ty; pp < 32; pp += 8) {
+        const int p = p0 + pp, r = r0 + tx;
+        if (p < rows && r < R) {
+            float v = tile[tx][pp] + (bias != nullptr ? bias[r] : 0.f);
+            float* o = out + static_cast<size_t>(p) * ldo + r;
+            if (accumulate) v += *o;
+            *o = v;
+        }
+    }
+}
+
 static int cl_grid(long long warps) { return static_cast<int>((warps + 7) / 8); }
+
+int launch_bilinear_finish(const float* part, long long ld, const float* bias, int rows, int R, int accumulate, float* out,
+                           int ldo, cudaStream_t st) {
+    if (rows <= 0 || R <= 0) return GCGCN_OK;
+    dim3 grid((rows + 31) / 32, (R + 31) / 32);
+    bilinear_finish_kernel<<<grid, 256, 0, st>>>(part, ld, bias, rows, R, accumulate, out, ldo);
+    GCGCN_CHECK_LAUNCH("bilinear_finish");
+    return GCGCN_OK;
+}
 
 int launch_bilinear_reduce(const float* Y, const float* t, const float* bias, int rows, int R, int accumulate, float* out,
                            int ldo, cudaStream_t st) {

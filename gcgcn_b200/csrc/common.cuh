@@ -50,6 +50,11 @@ struct StreamDeviceGuard {
     explicit StreamDeviceGuard(cudaStream_t st) {
         int dev = -1;
         if (st == nullptr) return;
+        // a capturing stream must not be queried (the query would invalidate the capture); whoever captures has
+        // made the stream's device current already
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return; }
+        if (cap != cudaStreamCaptureStatusNone) return;
         if (cudaStreamGetDevice(st, &dev) != cudaSuccess) { cudaGetLastError(); return; }
         if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
         if (prev != dev && cudaSetDevice(dev) == cudaSuccess) switched = true;

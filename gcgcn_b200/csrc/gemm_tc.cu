@@ -57,6 +57,11 @@ struct TcArgs {
     int kblocks;                    // ceil(K / TC_BK), blob index stride of Bpre
     int batch;                      // independent products per launch (same shapes, strided operands)
     long long sA, sB, sC;           // element strides between consecutive products
+    // row-dot epilogue (gemm_tc_tmema_kernel<true>): instead of storing the 128 x 128 tile, every row is contracted with
+    // the matching 128 values of rd_t: rd_out[(tile_n * 2 + half) * rd_ld + row] = sum_{c in half} acc[row][c] rd_t[row][c]
+    const float* rd_t;              // [M][128]
+    float* rd_out;                  // [tiles_n][2][rd_ld]
+    long long rd_ld;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -700,6 +705,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+template <bool ROWDOT>
 __global__ void __launch_bounds__(TA_THREADS, 1) gemm_tc_tmema_kernel(const TcArgs args) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* b_stage = smem;                                           // [TA_BSTAGES][B_hi part, B_lo part]
@@ -825,14 +831,54 @@ __global__ void __launch_bounds__(TA_THREADS, 1) gemm_tc_tmema_kernel(const TcAr
         float* stg = epi_stage + ew * TC_EPI_WARP_FLOATS;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
-            for (int n = 0; n < tiles_n; ++n) {
-                mbar_wait(tfull_bar(acc), acc_phase);
-                tc_fence_after();
-                tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, mi * TC_BM, n * TC_BN, 0, 0, true, lane,
-                                 (ew / 4) * CH, CH);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (ROWDOT) {
+            // bilinear-form epilogue: lane = row keeps the 64 values of rd_t[row] that face this warp's column half in
+            // registers for all column tiles of the row tile; one scalar per (row, column tile, half) leaves the SM
+            static_assert(CH == 2, "row-dot epilogue assumes two 32-column chunks per epilogue warp");
+            const int half = ew / 4;
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x) {
+                const int row = mi * TC_BM + quarter * 32 + lane;
+                float4 t[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    t[j] = row < args.M ? *reinterpret_cast<const float4*>(args.rd_t + static_cast<size_t>(row) * 128 + half * 64 + 4 * j)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int n = 0; n < tiles_n; ++n) {
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+                    float s = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                               static_cast<uint32_t>(acc * TC_BN + (half * 2 + c) * 32);
+                        tmem_ld32(taddr, v);
+                        if (c == 1) {           // the accumulator is in registers: hand the TMEM buffer back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 tv = t[c * 8 + j];
+                            s += __uint_as_float(v[4 * j]) * tv.x + __uint_as_float(v[4 * j + 1]) * tv.y +
+                                 __uint_as_float(v[4 * j + 2]) * tv.z + __uint_as_float(v[4 * j + 3]) * tv.w;
+                        }
+                    }
+                    if (row < args.M) args.rd_out[(static_cast<long long>(n) * 2 + half) * args.rd_ld + row] = s;
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
             }
+        } else {
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
+                for (int n = 0; n < tiles_n; ++n) {
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+                    tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, mi * TC_BM, n * TC_BN, 0, 0, true, lane,
+                                     (ew / 4) * CH, CH);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -903,6 +949,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     a.tiles_m = ceil_div(M, TC_BM);
     a.tiles_n = ceil_div(N, TC_BN);
     a.batch = batch; a.sA = sA; a.sB = sB; a.sC = sC;
+    a.rd_t = nullptr; a.rd_out = nullptr; a.rd_ld = 0;
     const int tiles = a.tiles_m * a.tiles_n * batch;
     const int sms = sm_count();
     int splits = 1;
@@ -969,11 +1016,11 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     if (resa && tmema_on && !ta) {
         static std::atomic<unsigned long long> attr_done2{0};
         if (!device_prepared(attr_done2)) {
-            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_tmema smem"));
             device_mark_prepared(attr_done2);
         }
-        gemm_tc_tmema_kernel<<<std::min(sms, a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
+        gemm_tc_tmema_kernel<false><<<std::min(sms, a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
     } else if (resa) {
         static std::atomic<unsigned long long> attr_done{0};
         if (!device_prepared(attr_done)) {
@@ -997,6 +1044,40 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     if (splits > 1)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));
     *taken = 1;
+    return GCGCN_OK;
+}
+
+// Row-dot GEMM: part[(nt * 2 + half) * ld + m] = sum_{c in half of column tile nt} (A B)[m][128 nt + c] T[m][c]
+// -- the bilinear form out[p, r] = sum_b (h W')[p, r*128 + b] t[p, b] without ever storing h W' (97 x 128 floats per
+// pair).  A [M, K <= 128] row-major stays resident in tensor memory per row tile (split hi/lo), B [K, N] (N a multiple
+// of 128) streams through shared memory as pre-split blobs, the accumulator tiles are consumed from TMEM.
+int launch_gemm_rowdot(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* T, float* part,
+                       long long part_ld, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return GCGCN_OK;
+    if (K < 1 || K > RA_KB * TC_BK || N % TC_BN != 0)
+        return fail(GCGCN_ERR_UNSUPPORTED, "gemm_rowdot: needs 1 <= K <= %d and N a multiple of %d (K %d, N %d)", RA_KB * TC_BK,
+                    TC_BN, K, N);
+    TcArgs a;
+    a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = 0;
+    a.A = A; a.B = B; a.bias = nullptr; a.C = nullptr; a.partial = nullptr; a.alpha = 1.f; a.beta = 0.f;
+    a.tiles_m = ceil_div(M, TC_BM); a.tiles_n = N / TC_BN; a.k_splits = 1; a.k_per_split = K;
+    a.kblocks = ceil_div(K, TC_BK); a.batch = 1; a.sA = a.sB = a.sC = 0; a.Apre = nullptr;
+    a.rd_t = T; a.rd_out = part; a.rd_ld = part_ld;
+    const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
+    if (ws == nullptr || blob_total > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
+        return fail(GCGCN_ERR_WORKSPACE, "gemm_rowdot: workspace of %zu bytes needed for the pre-split weights", blob_total);
+    tc_presplit_b_kernel<<<a.tiles_n * a.kblocks, 256, 0, st>>>(B, ldb, 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
+    GCGCN_CHECK_LAUNCH("gemm_presplit_b");
+    a.Bpre = static_cast<const uint8_t*>(ws);
+    static std::atomic<unsigned long long> attr_done{0};
+    if (!device_prepared(attr_done)) {
+        GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_rowdot smem"));
+        device_mark_prepared(attr_done);
+    }
+    gemm_tc_tmema_kernel<true><<<std::min(sm_count(), a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
+    timing_set_work(2.0 * M * N * K);
+    GCGCN_CHECK_LAUNCH("gemm_tc_rowdot<A in TMEM>");
     return GCGCN_OK;
 }
 

@@ -80,6 +80,86 @@ class GradBucket:
                     g.copy_(v)
 
 
+class OverlappedBuckets:
+    """Gradient all-reduce that overlaps the rest of the backward pass ("overlap with the tail
+    of backward -- weight grads for MAGGC finish first since backward runs MAGGC -> CAGGC").
+
+    The parameters are cut into buckets in the order their gradients become final (``groups``: lists of parameters,
+    e.g. [MAGGC + MultiHeadAttention, CAGGC + GATAttention]).  A post-accumulate-grad hook per parameter counts a
+    bucket down; when its last gradient lands, the bucket is packed and its all-reduce is issued ``async_op=True`` on
+    a side stream while autograd keeps launching the remaining backward kernels on the main stream.  ``finish()``
+    waits for the collectives and writes the reduced values back into ``p.grad``.  Parameters that never receive a
+    gradient (``linears_k``, G:137) must be left out of the groups.
+    """
+
+    def __init__(self, groups: Sequence[Sequence[torch.nn.Parameter]], group=None):
+        self.group = group
+        self.buckets = [GradBucket(g) for g in groups]
+        self._left = [0] * len(self.buckets)
+        self._work = [None] * len(self.buckets)
+        self._stream = None
+        self._handles = []
+        for bi, b in enumerate(self.buckets):
+            for p in b.params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+        self.reset()
+
+    @property
+    def nbytes(self) -> int:
+        return sum(b.nbytes for b in self.buckets)
+
+    def reset(self):
+        """Call before every backward pass."""
+        self._left = [len(b.params) for b in self.buckets]
+        self._work = [None] * len(self.buckets)
+
+    def _make_hook(self, bi):
+        def hook(_param):
+            self._left[bi] -= 1
+            if self._left[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        b = self.buckets[bi]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        if b.flat.is_cuda:
+            main = torch.cuda.current_stream(b.flat.device)
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(b.flat.device)
+            self._stream.wait_stream(main)                 # the bucket's gradients are complete on the main stream
+            with torch.cuda.stream(self._stream):
+                b.pack()
+                self._work[bi] = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            b.pack()
+            self._work[bi] = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """After backward(): wait for every bucket's all-reduce and copy the sums into ``p.grad``."""
+        for bi, b in enumerate(self.buckets):
+            if self._left[bi] > 0:                          # a gradient never arrived: reduce what there is
+                self._launch(bi)
+            w = self._work[bi]
+            if w is None:
+                continue
+            if b.flat.is_cuda:
+                with torch.cuda.stream(self._stream):
+                    w.wait()
+                    b.unpack()
+            else:
+                w.wait()
+                b.unpack()
+        if self._stream is not None:
+            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 class FlatTrainer:
     """Config 5's optimiser state: parameters, gradients and both Adam moments each live in ONE flat fp32
     buffer, the module's parameters and their ``.grad`` are views into them.

@@ -376,6 +376,14 @@ int gcgcn_colsum(const float* X, int32_t M, int32_t N, int32_t ldx, float* out, 
  *   reduce: out[p][r] (+)= sum_b Y[p][r*128 + b] t[p][b] (+ bias[r])        Y [rows, R*128], out row stride ldo
  *   outer:  dY[p][r*128 + b] = dout[p][r] t[p][b]                            (then dh = dY W'^T, dW' = h^T dY)
  *   dt:     dt[p][b] = sum_r dout[p][r] Y[p][r*128 + b]                                                        */
+/* Fused forward: out[p][r] (+)= sum_{a,b} h[p][a] W'[a][r*128 + b] t[p][b] + bias[r] in ONE tensor-core pass -- h stays
+ * resident in tensor memory per 128-pair tile, W' streams through shared memory as pre-split blobs, and the epilogue
+ * contracts every 128 x 128 accumulator tile (one relation) with t straight out of TMEM, so h W' never exists.
+ * Wm = W' [128, relations*128] row-major; ws >= gcgcn_bilinear_ws_bytes(rows, relations).                       */
+size_t gcgcn_bilinear_ws_bytes(int32_t rows, int32_t relations);
+int gcgcn_bilinear_fwd(const float* h, const float* t, const float* Wm, const float* bias, int32_t rows,
+                       int32_t relations, int32_t accumulate, float* out, int32_t ldo, void* ws, size_t ws_bytes,
+                       void* stream);
 int gcgcn_bilinear_reduce_fwd(const float* Y, const float* t, const float* bias, int32_t rows, int32_t relations,
                               int32_t accumulate, float* out, int32_t ldo, void* stream);
 int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int32_t rows, int32_t relations, float* dY,

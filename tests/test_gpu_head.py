@@ -117,3 +117,39 @@ def test_loss_kernel_alone_matches_torch_bce():
     (want * w).sum().backward()
     assert float((loss.detach().cpu() - want.detach()).abs().max()) <= 1e-5
     assert float((zg.grad.cpu() - z.grad).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("P", [1, 127, 1000, 8192 + 77])
+def test_bilinear_classifier_against_torch(P):
+    """G:356-358 on its own: Bilinear(128, 128, 97) + Linear(256, 97) over P pairs (P not a multiple of the 128-row tile,
+    and more than one chunk of the backward) against torch's own modules on the CPU; the fused forward (row-dot
+    epilogue on the tcgen05 GEMM) against the chunked forward that materialises h W'."""
+    from gcgcn_b200 import classifier as C
+    torch.manual_seed(P)
+    bili, cls = torch.nn.Bilinear(128, 128, 97), torch.nn.Linear(256, 97)
+    gen = torch.Generator().manual_seed(P + 1)
+    h = torch.tanh(torch.randn(P, 128, generator=gen)).requires_grad_(True)
+    t = torch.tanh(torch.randn(P, 128, generator=gen)).requires_grad_(True)
+    up = torch.randn(P, 97, generator=gen)
+    want = bili(h, t) + cls(torch.cat([h, t], -1))
+    (want * up).sum().backward()
+    ref = {"h": h.grad, "t": t.grad, "W": bili.weight.grad, "b": bili.bias.grad, "Wc": cls.weight.grad, "bc": cls.bias.grad}
+    import copy
+    bg, cg = copy.deepcopy(bili).to(DEV), copy.deepcopy(cls).to(DEV)
+    for m in (bg, cg):
+        m.zero_grad()
+    hg, tg = h.detach().to(DEV).requires_grad_(True), t.detach().to(DEV).requires_grad_(True)
+    got = C.relation_logits(hg, tg, bg, cg)
+    (got * up.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert float((got.detach().cpu() - want.detach()).abs().max()) <= FP32_TOL
+    for k, g in (("h", hg.grad), ("t", tg.grad), ("W", bg.weight.grad), ("b", bg.bias.grad), ("Wc", cg.weight.grad),
+                 ("bc", cg.bias.grad)):
+        assert rel(g, ref[k]) <= 1e-4, k
+    C.FUSED_FORWARD = False
+    try:
+        with torch.no_grad():
+            chunked = C.relation_logits(hg, tg, bg, cg)
+    finally:
+        C.FUSED_FORWARD = True
+    assert float((chunked - got.detach()).abs().max()) <= 2e-5

@@ -14,7 +14,7 @@ from helpers import PREFIXES, blocks_state, oracle_blocks, sub
 from gcgcn_b200 import synthetic as S
 from gcgcn_b200.batch import shard_documents
 from gcgcn_b200.modules import GraphBlocks
-from gcgcn_b200.sharding import FlatTrainer, GradBucket, all_reduce_gradients, local_documents
+from gcgcn_b200.sharding import FlatTrainer, GradBucket, OverlappedBuckets, all_reduce_gradients, local_documents
 
 DOC_IDS = [2, 5, 8, 9, 10, 11]        # n = 28, 19, 14, 11, 8, 5
 LAYERS, HEADS = 2, 8
@@ -124,3 +124,45 @@ def test_flat_trainer_bucket_all_reduce_two_ranks(tmp_path):
     want = dict(gb.named_parameters())
     for n, o, sz in zip(got[0]["names"], got[0]["offsets"], got[0]["sizes"]):
         assert torch.allclose(got[0]["flat"][o:o + sz].view_as(want[n]), want[n].grad, rtol=1e-5, atol=1e-5), n
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    # a tiny autograd graph whose backward finishes the second group's gradients first, like MAGGC -> CAGGC
+    a = torch.nn.Linear(8, 8)
+    b = torch.nn.Linear(8, 4)
+    dead = torch.nn.Parameter(torch.zeros(3))                   # never used: left out of the buckets (linears_k)
+    ob = OverlappedBuckets([list(b.parameters()), list(a.parameters())])
+    order = []
+    for name, p in (("b", b.weight), ("a", a.weight)):
+        p.register_post_accumulate_grad_hook(lambda _p, name=name: order.append(name))
+    for step in range(2):                                       # hooks must survive a second pass
+        for p in list(a.parameters()) + list(b.parameters()):
+            p.grad = None
+        ob.reset()
+        x = torch.full((5, 8), float(rank + 1 + step))
+        b(torch.tanh(a(x))).sum().backward()
+        ob.finish()
+    assert order[:2] == ["b", "a"] and dead.grad is None
+    torch.save({n: p.grad.clone() for n, p in list(a.named_parameters()) + [("b." + k, v) for k, v in b.named_parameters()]},
+               os.path.join(out_dir, f"overlap{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_buckets_reduce_in_backward_order(tmp_path):
+    port = _free_port()
+    mp.spawn(_overlap_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [torch.load(tmp_path / f"overlap{r}.pt") for r in range(2)]
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(8, 8), torch.nn.Linear(8, 4)
+    for rank in range(2):                                       # the sum of both ranks' step-1 gradients
+        x = torch.full((5, 8), float(rank + 2))
+        b(torch.tanh(a(x))).sum().backward()
+    for r in range(2):
+        assert torch.allclose(got[r]["weight"], a.weight.grad, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(got[r]["b.weight"], b.weight.grad, rtol=1e-5, atol=1e-6)
+    assert torch.equal(got[0]["weight"], got[1]["weight"])
