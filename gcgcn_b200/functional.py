@@ -484,8 +484,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_a=False, trans_b=False, bias=No
     M = a.shape[1] if trans_a else a.shape[0]
     K = a.shape[0] if trans_a else a.shape[1]
     N = b.shape[0] if trans_b else b.shape[1]
-    if out is None:
-        out = torch.zeros(M, N, device=a.device)
+    if out is None:      # beta == 0 overwrites every element: no fill needed
+        out = torch.empty(M, N, device=a.device) if (beta == 0.0 and K > 0) else torch.zeros(M, N, device=a.device)
     # 24 MB of split-K partials / pre-split weight blobs, plus (weight-gradient shapes only) the pre-split short operand
     pre = ((K + 31) // 32) * 33024 * ((M + 127) // 128) if (trans_a and not trans_b and M <= 256) else 0
     ws = workspace(a.device, (24 << 20) + pre + 4096)
