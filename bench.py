@@ -502,7 +502,7 @@ def graph_block_point(dev, layers, heads, sizes, edge_dtype, hbm_peak, steps=5, 
         x0.grad = e0.grad = e1.grad = None
         for p in ps:
             p.grad = None
-        out = gbs(x0, e0, e1, btx)
+        out = gbs(x0, e0, e1, btx, with_node_feats=False)
         torch.autograd.backward([out["y1"], out["y2"]], [dy1, dy2])
 
     for _ in range(warmup):
@@ -759,7 +759,7 @@ def run_gpu_arm(args):
             p.grad = None
         if overlapped is not None:
             overlapped.reset()
-        out = gb(x0_, e0_, e1_, bt)
+        out = gb(x0_, e0_, e1_, bt, with_node_feats=False)      # (the classifier's input; SURVEY 8d times the blocks)
         torch.autograd.backward([out["y1"], out["y2"]], [dy1_, dy2_])
         if overlapped is not None:
             overlapped.finish()

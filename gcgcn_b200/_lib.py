@@ -134,6 +134,9 @@ SIGNATURES = {
     "gcgcn_mha_stack_bwd": (c_int32, [_BT, c_int32, c_int32] + [_P] * 22 + [_DP, _P, c_size_t, _P]),
     "gcgcn_pack_stack_weights": (c_int32, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "gcgcn_unpack_stack_grads": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "gcgcn_gat_collapse_fwd": (c_int32, [_P] * 8 + [c_int32, _P, _P]),
+    "gcgcn_gat_collapse_bwd": (c_int32, [_P] * 8 + [c_int32] + [_P] * 8 + [_P]),
+    "gcgcn_pack_rows": (c_int32, [_P, c_int32, c_int32, _P, _P]),
     "gcgcn_pair_gather_fwd": (c_int32, [_BT, _P, c_int32, _P, c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "gcgcn_pair_gather_bwd": (c_int32, [_BT, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P,
                                         _P, c_size_t, _P]),

@@ -108,6 +108,13 @@ int launch_pair_bce_fwd(const gcgcn_batch* bt, const float* z, const float* y, i
 int launch_pair_bce_bwd(const gcgcn_batch* bt, const float* z, const float* y, int R, const float* dloss, float* dz,
                         cudaStream_t st);
 
+int launch_gat_collapse_fwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                            const float* br, const float* w, const float* b, int hid, float* out, cudaStream_t st);
+int launch_gat_collapse_bwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                            const float* br, const float* w, const float* dout, int hid, float* dWh, float* dbh, float* dWt,
+                            float* dbt, float* dWr, float* dbr, float* dw, float* db, cudaStream_t st);
+int launch_pack_rows(const float* const* ptrs, int count, int elems, float* out, cudaStream_t st);
+
 // ---- error text, launch counter, device cache --------------------------------------------------
 std::atomic<uint64_t> g_launches{0};
 std::atomic<bool> g_timing{false};
@@ -781,6 +788,34 @@ int gcgcn_unpack_stack_grads(const float* dWnX, const float* dWe, const float* d
     GCGCN_TRY(check_device_ptr(dwe_flat, "dwe_flat"));
     return launch_unpack_stack(dWnX, dWe, dWinner, heads, layers, slab, dwn_flat, dwe_flat,
                                static_cast<cudaStream_t>(stream));
+}
+
+// ---- parameter collapse / packing of the attention modules ------------------------------------------------
+int gcgcn_gat_collapse_fwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                           const float* br, const float* w, const float* b, int32_t hid, float* out, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(hid >= 1, "gat_collapse_fwd: hidden_dim < 1");
+    const void* ps[] = {Wh, bh, Wt, bt, Wr, br, w, b, out};
+    for (const void* p : ps) GCGCN_TRY(check_device_ptr(p, "gat_collapse operand"));
+    return launch_gat_collapse_fwd(Wh, bh, Wt, bt, Wr, br, w, b, hid, out, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_gat_collapse_bwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                           const float* br, const float* w, const float* dout, int32_t hid, float* dWh, float* dbh,
+                           float* dWt, float* dbt, float* dWr, float* dbr, float* dw, float* db, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(hid >= 1, "gat_collapse_bwd: hidden_dim < 1");
+    const void* ps[] = {Wh, bh, Wt, bt, Wr, br, w, dout, dWh, dbh, dWt, dbt, dWr, dbr, dw, db};
+    for (const void* p : ps) GCGCN_TRY(check_device_ptr(p, "gat_collapse operand"));
+    return launch_gat_collapse_bwd(Wh, bh, Wt, bt, Wr, br, w, dout, hid, dWh, dbh, dWt, dbt, dWr, dbr, dw, db,
+                                   static_cast<cudaStream_t>(stream));
+}
+int gcgcn_pack_rows(const void* ptrs, int32_t count, int32_t elems, float* out, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(count >= 0 && elems >= 0, "pack_rows: negative size");
+    if (count == 0 || elems == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(ptrs, "ptrs"));
+    GCGCN_TRY(check_device_ptr(out, "out"));
+    return launch_pack_rows(static_cast<const float* const*>(ptrs), count, elems, out, static_cast<cudaStream_t>(stream));
 }
 
 // ---- a8 pair gathers -------------------------------------------------------------------------

@@ -76,6 +76,91 @@ int launch_unpack_stack(const float* dWnX, const float* dWe, const float* dWinne
     return GCGCN_OK;
 }
 
+// ---- GATAttention parameter collapse (G:156-162) ------------------------------------------------------------
+// energy_ij = wt . [Wh x_j + bh ; Wt x_j + bt ; Wr e_ij + br] + b  ==  u . x_j + v . e_ij + c  with
+//   u = Wh^T w1 + Wt^T w2,  v = Wr^T w3,  c = w1.bh + w2.bt + w3.br + b        (w = wt.weight = [w1 | w2 | w3])
+// One CTA; thread k owns column k of the three [hid, 128] weights (coalesced rows).  out = [u(128) | v(128) | c].
+__global__ void __launch_bounds__(128)
+gat_collapse_fwd_kernel(const float* __restrict__ Wh, const float* __restrict__ bh, const float* __restrict__ Wt,
+                        const float* __restrict__ bt, const float* __restrict__ Wr, const float* __restrict__ br,
+                        const float* __restrict__ w, const float* __restrict__ b, int hid, float* __restrict__ out) {
+    const int k = threadIdx.x;
+    float u = 0.f, v = 0.f;
+    for (int o = 0; o < hid; ++o) {
+        u += Wh[o * D + k] * w[o] + Wt[o * D + k] * w[hid + o];
+        v += Wr[o * D + k] * w[2 * hid + o];
+    }
+    out[k] = u;
+    out[D + k] = v;
+    float c = 0.f;
+    for (int o = k; o < hid; o += D) c += w[o] * bh[o] + w[hid + o] * bt[o] + w[2 * hid + o] * br[o];
+    c = warp_sum(c);
+    __shared__ float red[4];
+    if ((k & 31) == 0) red[k >> 5] = c;
+    __syncthreads();
+    if (k == 0) out[2 * D] = red[0] + red[1] + red[2] + red[3] + b[0];
+}
+
+// gradients of all eight parameters from (du, dv, dc); grid = hid rows, thread k = column
+__global__ void __launch_bounds__(128)
+gat_collapse_bwd_kernel(const float* __restrict__ Wh, const float* __restrict__ bh, const float* __restrict__ Wt,
+                        const float* __restrict__ bt, const float* __restrict__ Wr, const float* __restrict__ br,
+                        const float* __restrict__ w, const float* __restrict__ dout, int hid, float* __restrict__ dWh,
+                        float* __restrict__ dbh, float* __restrict__ dWt, float* __restrict__ dbt, float* __restrict__ dWr,
+                        float* __restrict__ dbr, float* __restrict__ dw, float* __restrict__ db) {
+    const int o = blockIdx.x, k = threadIdx.x;
+    const float du = dout[k], dv = dout[D + k], dc = dout[2 * D];
+    const float w1 = w[o], w2 = w[hid + o], w3 = w[2 * hid + o];
+    dWh[o * D + k] = w1 * du;
+    dWt[o * D + k] = w2 * du;
+    dWr[o * D + k] = w3 * dv;
+    float a1 = Wh[o * D + k] * du, a2 = Wt[o * D + k] * du, a3 = Wr[o * D + k] * dv;
+    a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    __shared__ float red[3][4];
+    if ((k & 31) == 0) { red[0][k >> 5] = a1; red[1][k >> 5] = a2; red[2][k >> 5] = a3; }
+    __syncthreads();
+    if (k == 0) {
+        dw[o] = red[0][0] + red[0][1] + red[0][2] + red[0][3] + dc * bh[o];
+        dw[hid + o] = red[1][0] + red[1][1] + red[1][2] + red[1][3] + dc * bt[o];
+        dw[2 * hid + o] = red[2][0] + red[2][1] + red[2][2] + red[2][3] + dc * br[o];
+        dbh[o] = dc * w1;
+        dbt[o] = dc * w2;
+        dbr[o] = dc * w3;
+        if (o == 0) db[0] = dc;
+    }
+}
+
+int launch_gat_collapse_fwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                            const float* br, const float* w, const float* b, int hid, float* out, cudaStream_t st) {
+    gat_collapse_fwd_kernel<<<1, 128, 0, st>>>(Wh, bh, Wt, bt, Wr, br, w, b, hid, out);
+    GCGCN_CHECK_LAUNCH("gat_collapse_fwd");
+    return GCGCN_OK;
+}
+int launch_gat_collapse_bwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                            const float* br, const float* w, const float* dout, int hid, float* dWh, float* dbh, float* dWt,
+                            float* dbt, float* dWr, float* dbr, float* dw, float* db, cudaStream_t st) {
+    gat_collapse_bwd_kernel<<<hid, 128, 0, st>>>(Wh, bh, Wt, bt, Wr, br, w, dout, hid, dWh, dbh, dWt, dbt, dWr, dbr, dw, db);
+    GCGCN_CHECK_LAUNCH("gat_collapse_bwd");
+    return GCGCN_OK;
+}
+
+// ---- row-wise concatenation of equally shaped matrices through a pointer table (MultiHeadAttention's H query
+// projections [d_h, 128] + biases -> Wq [128, 128], bq [128]: one launch instead of two torch.cat) -------------------
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* const* __restrict__ ptrs, int count, int elems, float* __restrict__ out) {
+    const int i = blockIdx.y;
+    const float* src = ptrs[i];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < elems; idx += gridDim.x * blockDim.x)
+        out[static_cast<size_t>(i) * elems + idx] = src[idx];
+}
+int launch_pack_rows(const float* const* ptrs, int count, int elems, float* out, cudaStream_t st) {
+    if (count <= 0 || elems <= 0) return GCGCN_OK;
+    dim3 grid(std::max(1, std::min(8, (elems + 255) / 256)), count);
+    pack_rows_kernel<<<grid, 256, 0, st>>>(ptrs, count, elems, out);
+    GCGCN_CHECK_LAUNCH("pack_rows");
+    return GCGCN_OK;
+}
+
 // ---- fused Adam over the flat parameter bucket (config 5: one optimiser step per micro-batch) ----
 // torch.optim.Adam semantics (the reference trains with optim.Adam(lr), C:300): decoupled from autograd,
 // one pass over four flat fp32 arrays, float4 accesses.  grad_scale folds the 1/world (or 1/documents)

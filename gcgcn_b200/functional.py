@@ -138,9 +138,8 @@ class GatFn(Function):
         debar = None if debar is None else _cuda(debar, "debar")
         dx = torch.empty_like(x)
         de = torch.empty_like(e)
-        du = torch.empty(D, device=dev)
-        dv = torch.empty(D, device=dev)
-        dc = torch.empty(1, device=dev)
+        duvc = torch.empty(2 * D + 1, device=dev)          # [du | dv | dc] contiguous: GatCollapseFn consumes it as is
+        du, dv, dc = duvc[:D], duvc[D:2 * D], duvc[2 * D:]
         ws, wsb = _ws_for(bt, 1, dev)
         _lib.call("gcgcn_gat_bwd", bt.ref, _p(x), _p(e), ctx.dt, _p(u), _p(v), _p(mask_u8),
                   int(ctx.apply_mask), _p(keep), _p(P), _p(dA), _p(debar), _p(dx), _p(de), _p(du),
@@ -288,7 +287,8 @@ class CaggcFn(Function):
         dev = x.device
         dy = _cuda(dy, "dy")
         dx, de = torch.empty_like(x), torch.empty_like(e)
-        du, dv, dc = torch.empty(D, device=dev), torch.empty(D, device=dev), torch.empty(1, device=dev)
+        duvc = torch.empty(2 * D + 1, device=dev)          # [du | dv | dc] contiguous: GatCollapseFn consumes it as is
+        du, dv, dc = duvc[:D], duvc[D:2 * D], duvc[2 * D:]
         dWnX, dWe, dWout = torch.empty_like(WnX), torch.empty_like(We), torch.empty_like(Wout)
         dWinner = None if Winner is None else torch.empty_like(Winner)
         dbout = torch.empty(D, device=dev)
@@ -397,6 +397,62 @@ class PackStackFn(Function):
         for a, b in zip(gn, ge):
             out += [a, b]
         return tuple(out)
+
+
+class GatCollapseFn(Function):
+    """(linear_node_h, linear_node_t, linear_edge_r, wt) -> u [128], v [128], c []: the exact collapse of G:156-162
+    (energy_ij = u.x_j + v.e_ij + c) in one launch; the backward fills the eight parameter gradients in one launch."""
+
+    @staticmethod
+    def forward(ctx, Wh, bh, Wt, bt, Wr, br, w, b):
+        ts = [_cuda(t, "GAT parameter") for t in (Wh, bh, Wt, bt, Wr, br, w, b)]
+        hid = ts[0].shape[0]
+        if ts[0].shape[1] != D or ts[6].numel() != 3 * hid:
+            raise _lib.GcgcnError(f"GATAttention collapse: weights must be [hidden, {D}] and wt [1, 3*hidden]")
+        out = torch.empty(2 * D + 1, device=ts[0].device)
+        _lib.call("gcgcn_gat_collapse_fwd", *[_p(t) for t in ts], hid, _p(out), _stream(out.device))
+        ctx.save_for_backward(*ts[:7])
+        return out[:D], out[D:2 * D], out[2 * D]
+
+    @staticmethod
+    def backward(ctx, du, dv, dc):
+        Wh, bh, Wt, bt, Wr, br, w = ctx.saved_tensors
+        dev, hid = Wh.device, Wh.shape[0]
+        if (du is not None and dv is not None and dc is not None and du.is_contiguous() and dv.is_contiguous()
+                and dv.data_ptr() == du.data_ptr() + 4 * D and dc.data_ptr() == du.data_ptr() + 8 * D):
+            dout = du                                       # the consumer wrote [du | dv | dc] into one buffer
+        else:
+            dout = torch.zeros(2 * D + 1, device=dev)
+            if du is not None:
+                dout[:D] = du
+            if dv is not None:
+                dout[D:2 * D] = dv
+            if dc is not None:
+                dout[2 * D] = dc
+        g = [torch.empty_like(t) for t in (Wh, bh, Wt, bt, Wr, br, w)] + [torch.empty(1, device=dev)]
+        _lib.call("gcgcn_gat_collapse_bwd", _p(Wh), _p(bh), _p(Wt), _p(bt), _p(Wr), _p(br), _p(w), _p(dout), hid,
+                  *[_p(t) for t in g], _stream(dev))
+        return tuple(g)
+
+
+class PackRowsFn(Function):
+    """Concatenate equally shaped parameters along dim 0 through a device pointer table (one launch); the backward
+    hands out views of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, *params):
+        ps = [_cuda(p, "parameter") for p in params]
+        dev = ps[0].device
+        elems = ps[0].numel()
+        out = torch.empty((len(ps) * ps[0].shape[0],) + tuple(ps[0].shape[1:]), device=dev)
+        _lib.call("gcgcn_pack_rows", _p(_ptr_table(ps, dev)), len(ps), elems, _p(out), _stream(dev))
+        ctx.rows, ctx.count = ps[0].shape[0], len(ps)
+        ctx._keepalive = ps
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return tuple(dout[i * ctx.rows:(i + 1) * ctx.rows] for i in range(ctx.count))
 
 
 # ------------------------------------------------------------------------------- a8 pair gathers

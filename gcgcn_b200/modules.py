@@ -26,7 +26,7 @@ from torch import nn
 
 from . import _lib
 from .batch import PairTables, PoolTable, RaggedBatch, single_doc_batch
-from .functional import (CaggcFn, EdgeMeanFn, GatFn, LinearFn, MhaFn, MhaStackFn, PackStackFn, PairDenseFn, PairGatherFn, PoolFn, StackFn,
+from .functional import (CaggcFn, EdgeMeanFn, GatCollapseFn, GatFn, LinearFn, PackRowsFn, MhaFn, MhaStackFn, PackStackFn, PairDenseFn, PairGatherFn, PoolFn, StackFn,
                          block_supported)
 
 HIDDEN = 128
@@ -251,9 +251,15 @@ class MultiHeadAttention(nn.Module, _KeepMixin):
         out.stacked = att
         return out
 
+    def packed_q(self):
+        """Wq [128, 128], bq [128]: the H query projections stacked (G:129), one launch each on the GPU."""
+        ws, bs = [l.weight for l in self.linears_q], [l.bias for l in self.linears_q]
+        if ws[0].is_cuda:
+            return PackRowsFn.apply(*ws), PackRowsFn.apply(*bs)
+        return torch.cat(ws, 0), torch.cat(bs, 0)
+
     def forward_batched(self, x, batch: RaggedBatch):
-        wq = torch.cat([l.weight for l in self.linears_q], 0)     # [128, 128]
-        bq = torch.cat([l.bias for l in self.linears_q], 0)
+        wq, bq = self.packed_q()
         keep = None
         if self.dropout is not None and self._dropping():
             ks = [self._keep((batch.total_pairs,), self.dropout.p, x.device) for _ in range(self.head_num)]
@@ -283,7 +289,11 @@ class GATAttention(nn.Module, _KeepMixin):
 
     def collapse(self):
         """energy_ij = wt.[Wh x_j + bh ; Wt x_j + bt ; Wr e_ij + br] + b  ==  u.x_j + v.e_ij + c."""
-        h = self._hid
+        if self.wt.weight.is_cuda:          # one launch forward, one backward (no library gemv / dot calls)
+            return GatCollapseFn.apply(self.linear_node_h.weight, self.linear_node_h.bias, self.linear_node_t.weight,
+                                       self.linear_node_t.bias, self.linear_edge_r.weight, self.linear_edge_r.bias,
+                                       self.wt.weight, self.wt.bias)
+        h = self._hid                        # (host-side restatement, used by the CPU state_dict / shape tests only)
         w = self.wt.weight[0]
         w1, w2, w3 = w[:h], w[h:2 * h], w[2 * h:]
         u = self.linear_node_h.weight.t().mv(w1) + self.linear_node_t.weight.t().mv(w2)
@@ -383,8 +393,7 @@ class GraphBlocks(nn.Module, _KeepMixin):
         if ebar1 is None:
             ebar1 = EdgeMeanFn.apply(e1, batch)
         if mag_ok:
-            wq = torch.cat([l.weight for l in mha.linears_q], 0)
-            bq = torch.cat([l.bias for l in mha.linears_q], 0)
+            wq, bq = mha.packed_q()
             wn_x, w_e, winner = _pack_stack(mag.graphconv, mag.head_num, mag.layer_num, mag._g)
             drop = self._draw(mha.dropout.p if mha.training else 0.0, mag.gcn_dropout.p if mag.training else 0.0)
             self.last_drop["maggc"] = drop
@@ -394,9 +403,10 @@ class GraphBlocks(nn.Module, _KeepMixin):
             new = mag.forward_batched(y1, ebar1, a1, batch)                                     # G:337
         return self._blend(new, y1), a1
 
-    def forward(self, x0, e0, e1, batch: RaggedBatch, adj=None):
+    def forward(self, x0, e0, e1, batch: RaggedBatch, adj=None, with_node_feats: bool = True):
         """x0 [total_nodes,128]; e0, e1 [total_pairs,128] (fp32 or bf16); adj [total_pairs] or None.
-        Returns y1, y2 and node_feats = cat[x0, x0, y1] (append-before-update, G:338)."""
+        Returns y1, y2 and node_feats = cat[x0, x0, y1] (append-before-update, G:338; the classifier's input, skipped
+        with ``with_node_feats=False``)."""
         ebar1 = None
         if self.overlap and e1.is_cuda:
             main = torch.cuda.current_stream(e1.device)
@@ -411,7 +421,10 @@ class GraphBlocks(nn.Module, _KeepMixin):
         if ebar1 is not None:
             torch.cuda.current_stream(e1.device).wait_stream(self._side[e1.device])
         y2, a1 = self.hop1(y1, e1, batch, ebar1)
-        return {"y1": y1, "y2": y2, "a0": a0, "a1": a1, "node_feats": torch.cat([x0, x0, y1], 1)}
+        out = {"y1": y1, "y2": y2, "a0": a0, "a1": a1}
+        if with_node_feats:
+            out["node_feats"] = torch.cat([x0, x0, y1], 1)
+        return out
 
 
 def pool_nodes(context: torch.Tensor, table: PoolTable) -> torch.Tensor:

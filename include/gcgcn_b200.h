@@ -221,6 +221,18 @@ int gcgcn_pack_stack_weights(const void* wn_ptrs, const void* we_ptrs, int32_t h
 int gcgcn_unpack_stack_grads(const float* dWnX, const float* dWe, const float* dWinner, int32_t heads,
                              int32_t layers, int32_t slab, float* dwn_flat, float* dwe_flat, void* stream);
 
+/* ---- a2 parameter collapse: the eight GATAttention parameters -> (u, v, c) of gcgcn_gat_fwd, and back ------------
+ * Wh/Wt/Wr = linear_node_h / linear_node_t / linear_edge_r .weight [hid, 128], bh/bt/br their biases [hid],
+ * w = wt.weight [3*hid], b = wt.bias [1].  out = [u (128) | v (128) | c (1)];  bwd takes dout in the same layout.   */
+int gcgcn_gat_collapse_fwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                           const float* br, const float* w, const float* b, int32_t hid, float* out, void* stream);
+int gcgcn_gat_collapse_bwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
+                           const float* br, const float* w, const float* dout, int32_t hid, float* dWh, float* dbh,
+                           float* dWt, float* dbt, float* dWr, float* dbr, float* dw, float* db, void* stream);
+/* out[i] = *ptrs[i] for `count` equally sized float arrays of `elems` elements (ptrs: device array of device pointers):
+ * MultiHeadAttention's per-head query projections -> Wq [128,128] / bq [128] (G:129)                                */
+int gcgcn_pack_rows(const void* ptrs, int32_t count, int32_t elems, float* out, void* stream);
+
 /* ---- a8: pair gathers, replaces G:351-352 (+ G:306-307) -----------------------------------
  * out_h[p,:] = cat(feat[h_idx[p],:], dis[dis_h[p],:]),  out_t[p,:] = cat(feat[t_idx[p],:], dis[dis_t[p],:])
  * for every pair p of the batch.  Index tables are int32 [total_pairs] holding *global* node
