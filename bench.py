@@ -446,8 +446,11 @@ def aux_rates(dev, hbm_peak, tensor_peak, tiles=128, iters=10):
         out[name] = {"us": sec * 1e6, "pairs": P, "documents": cdocs, "fp32_equivalent_tflops": mult * flop / sec / 1e12,
                      "executed_tf32_tflops": 3.0 * mult * flop / sec / 1e12, "unit": "TFLOP/s",
                      "frac": 3.0 * mult * flop / sec / 1e12 / tensor_peak, "graphs_per_s": cdocs / sec,
-                     "note": "bilinear as Y = h W' on the tcgen05 GEMM (3xTF32) + row reductions, pairs in chunks of 8192; "
-                             "backward = forward product recomputed + two more products (3x the forward flops)"}
+                     "note": "forward: ONE tcgen05 pass, h resident in tensor memory per 128-pair tile, W' streamed as pre-split "
+                             "blobs, every accumulator tile contracted with t in the epilogue (h W' never stored); backward: "
+                             "two row-accumulate passes of the same kernel (dt, dh) + a weight-gradient GEMM whose "
+                             "[pairs, 97*128] operand is generated in its producers from t and dout; flops counted: "
+                             "2 P (128*128*97 + 256*97), x3 for forward+backward, x3 again for the executed TF32 passes"}
     del keep["z"], keep["loss"]
     torch.cuda.empty_cache()
 

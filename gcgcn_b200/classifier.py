@@ -19,6 +19,9 @@ from .batch import RaggedBatch
 from .functional import D, LinearFn, _cuda, _p, _stream, gemm, workspace
 
 CHUNK_PAIRS = 8192          # 8192 pairs x 97 x 128 floats = 407 MB of Y per chunk
+FUSED_BACKWARD = True       # False: the backward materialises Y / dY chunk by chunk (test hook; also the path below 8192 pairs)
+FUSED_MIN_PAIRS = 8192      # the generated-operand weight-gradient GEMM needs K >= 8192
+FUSED_CHUNK_PAIRS = 1 << 19  # pairs per fused backward call (1 KB of pre-split h per pair in the workspace)
 FUSED_FORWARD = True        # False: the forward materialises Y = h W' chunk by chunk like the backward does (test hook)
 
 
@@ -62,7 +65,20 @@ class BilinearFn(Function):
         dout = _cuda(dout, "dout")
         dh, dt = torch.empty_like(h), torch.empty_like(t)
         dWm = torch.zeros_like(Wm)
-        for p0 in range(0, P, CHUNK_PAIRS):
+        p_done = 0
+        if FUSED_BACKWARD and P >= FUSED_MIN_PAIRS:
+            # three tensor-core passes per chunk, nothing of size [pairs, R*128] is ever stored: dt and dh through the
+            # row-accumulate epilogue, dW' with its Khatri-Rao operand generated in the GEMM's producers
+            Wm2 = Wm.view(D, R, D).permute(2, 1, 0).reshape(D, R * D).contiguous()       # W viewed as [b][(r, a)]
+            lib = _lib.load()
+            while P - p_done >= FUSED_MIN_PAIRS:
+                p1 = P if P - p_done <= FUSED_CHUNK_PAIRS + FUSED_MIN_PAIRS else p_done + FUSED_CHUNK_PAIRS
+                rows = p1 - p_done
+                ws = workspace(dev, int(lib.gcgcn_bilinear_bwd_ws_bytes(rows, R)))
+                _lib.call("gcgcn_bilinear_bwd", _p(h[p_done:p1]), _p(t[p_done:p1]), _p(Wm), _p(Wm2), _p(dout[p_done:p1]), rows,
+                          R, 1.0, _p(dh[p_done:p1]), _p(dt[p_done:p1]), _p(dWm), ws.data_ptr(), ws.numel(), _stream(dev))
+                p_done = p1
+        for p0 in range(p_done, P, CHUNK_PAIRS):
             p1 = min(P, p0 + CHUNK_PAIRS)
             rows = p1 - p0
             Y = gemm(h[p0:p1], Wm)                                               # recomputed, not saved

@@ -100,8 +100,11 @@ int launch_bilinear_reduce(const float* Y, const float* t, const float* bias, in
                            int ldo, cudaStream_t st);
 int launch_bilinear_finish(const float* part, long long ld, const float* bias, int rows, int R, int accumulate, float* out,
                            int ldo, cudaStream_t st);
-int launch_gemm_rowdot(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* T, float* part,
-                       long long part_ld, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gemm_rowop(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* T,
+                      float* out, long long ld, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gemm_wgrad_scaled(int M, int tiles, int K, const float* A, int lda, const float* T, const float* scale, int lds,
+                             float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st, void* pre_ws,
+                             size_t pre_bytes);
 int launch_bilinear_outer(const float* dout, int ldd, const float* t, int rows, int R, float* dY, cudaStream_t st);
 int launch_bilinear_dt(const float* dout, int ldd, const float* Y, int rows, int R, float* dt, cudaStream_t st);
 int launch_pair_bce_fwd(const gcgcn_batch* bt, const float* z, const float* y, int R, float* loss, cudaStream_t st);
@@ -1103,9 +1106,39 @@ int gcgcn_bilinear_fwd(const float* h, const float* t, const float* Wm, const fl
     uint8_t* blobs = ar.take<uint8_t>(static_cast<size_t>(relations) * 4 * 33024);
     float* part = ar.take<float>(2 * static_cast<size_t>(relations) * ld);
     if (blobs == nullptr || part == nullptr) return fail(GCGCN_ERR_WORKSPACE, "bilinear_fwd: workspace too small");
-    GCGCN_TRY(launch_gemm_rowdot(rows, relations * D, D, h, D, Wm, relations * D, t, part, static_cast<long long>(ld), blobs,
-                                 static_cast<size_t>(relations) * 4 * 33024, st));
+    GCGCN_TRY(launch_gemm_rowop(1, rows, relations * D, D, h, D, Wm, relations * D, t, part, static_cast<long long>(ld), blobs,
+                                static_cast<size_t>(relations) * 4 * 33024, st));
     return launch_bilinear_finish(part, static_cast<long long>(ld), bias, rows, relations, accumulate, out, ldo, st);
+}
+
+size_t gcgcn_bilinear_bwd_ws_bytes(int32_t rows, int32_t relations) {
+    const size_t r = static_cast<size_t>(relations < 0 ? 0 : relations);
+    return align256(r * 4 * 33024) + align256(GEMM_WS_BYTES) + align256(gemm_presplit_bytes(rows < 0 ? 0 : rows)) + 4096;
+}
+
+int gcgcn_bilinear_bwd(const float* h, const float* t, const float* Wm, const float* Wm2, const float* dout, int32_t rows,
+                       int32_t relations, float beta, float* dh, float* dt, float* dWm, void* ws, size_t ws_bytes,
+                       void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_REQUIRE(rows >= 0 && relations >= 1, "bilinear_bwd: bad shape");
+    if (rows < 8192)
+        return fail(GCGCN_ERR_UNSUPPORTED, "bilinear_bwd: the fused backward needs >= 8192 rows (got %d); use "
+                    "gcgcn_bilinear_outer_bwd / gcgcn_bilinear_dt_bwd with gcgcn_gemm", rows);
+    const void* ps[] = {h, t, Wm, Wm2, dout, dh, dt, dWm};
+    for (const void* p : ps) GCGCN_TRY(check_device_ptr(p, "bilinear_bwd operand"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(ws, ws_bytes);
+    const size_t blob_bytes = static_cast<size_t>(relations) * 4 * 33024, pre_bytes = gemm_presplit_bytes(rows);
+    uint8_t* blobs = ar.take<uint8_t>(blob_bytes);
+    uint8_t* gws = ar.take<uint8_t>(GEMM_WS_BYTES);
+    uint8_t* pre = ar.take<uint8_t>(pre_bytes);
+    if (blobs == nullptr || gws == nullptr || pre == nullptr)
+        return fail(GCGCN_ERR_WORKSPACE, "bilinear_bwd: workspace too small");
+    const int N = relations * D;
+    GCGCN_TRY(launch_gemm_rowop(2, rows, N, D, h, D, Wm, N, dout, dt, relations, blobs, blob_bytes, st));
+    GCGCN_TRY(launch_gemm_rowop(2, rows, N, D, t, D, Wm2, N, dout, dh, relations, blobs, blob_bytes, st));
+    return launch_gemm_wgrad_scaled(D, relations, rows, h, D, t, dout, relations, beta, dWm, N, gws, GEMM_WS_BYTES, st, pre,
+                                    pre_bytes);
 }
 
 int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int32_t rows, int32_t relations, float* dY,

@@ -302,7 +302,7 @@ int launch_splitk_reduce(const float* partial, int splits, int M, int N, float a
 int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                    int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
                    cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC, void* pre_ws,
-                   size_t pre_bytes);
+                   size_t pre_bytes, const float* bscale = nullptr, int lds = 0);
 
 int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, void* ws,
@@ -343,6 +343,19 @@ int launch_gemm(int ta, int tb, int M, int N, int K, float alpha, const float* A
     timing_set_work(2.0 * M * N * K);
     GCGCN_CHECK_LAUNCH(ta ? (tb ? "gemm_tt" : "gemm_tn") : (tb ? "gemm_nt" : "gemm_nn"));
     if (splits > 1) GCGCN_TRY(launch_splitk_reduce(partial, splits, M, N, alpha, beta, C, ldc, bias, st));
+    return GCGCN_OK;
+}
+
+// C[M, tiles * 128] (+)= A^T [M, K] x KR, column tile nt of KR being  scale[k][nt] * T[k][0..127]  (T a [K, 128] matrix):
+// the weight gradient of a bilinear form, dW'[a][(r, b)] = sum_p h[p][a] dout[p][r] t[p][b], without materialising the
+// [K, tiles * 128] operand.  Tensor-core path only (K >= 8192, M <= 256): GCGCN_ERR_UNSUPPORTED otherwise.
+int launch_gemm_wgrad_scaled(int M, int tiles, int K, const float* A, int lda, const float* T, const float* scale, int lds,
+                             float beta, float* C, int ldc, void* ws, size_t ws_bytes, cudaStream_t st, void* pre_ws,
+                             size_t pre_bytes) {
+    int taken = 0;
+    GCGCN_TRY(launch_gemm_tc(1, 0, M, tiles * 128, K, 1.f, A, lda, T, 128, beta, C, ldc, nullptr, ws, ws_bytes, st, &taken, 1, 0,
+                             0, 0, pre_ws, pre_bytes, scale, lds));
+    if (!taken) return fail(GCGCN_ERR_UNSUPPORTED, "gemm_wgrad_scaled: shape not covered by the tensor-core path");
     return GCGCN_OK;
 }
 

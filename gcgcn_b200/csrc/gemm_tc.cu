@@ -57,11 +57,17 @@ struct TcArgs {
     int kblocks;                    // ceil(K / TC_BK), blob index stride of Bpre
     int batch;                      // independent products per launch (same shapes, strided operands)
     long long sA, sB, sC;           // element strides between consecutive products
-    // row-dot epilogue (gemm_tc_tmema_kernel<true>): instead of storing the 128 x 128 tile, every row is contracted with
+    // row-dot epilogue (gemm_tc_tmema_kernel<1>): instead of storing the 128 x 128 tile, every row is contracted with
     // the matching 128 values of rd_t: rd_out[(tile_n * 2 + half) * rd_ld + row] = sum_{c in half} acc[row][c] rd_t[row][c]
     const float* rd_t;              // [M][128]
     float* rd_out;                  // [tiles_n][2][rd_ld]
     long long rd_ld;
+    // row-accumulate epilogue (gemm_tc_tmema_kernel<2>): rd_out[row][c] = sum_nt rd_t[row * rd_ld + nt] * acc_nt[row][c]
+    // (rd_t is then a [M][rd_ld] matrix of per-(row, column tile) weights, rd_out a [M][128] matrix)
+    // generated B operand of the APRE path: column tile nt of op(B) is  bscale[k * lds + nt] * B[k][0..127]
+    // (B a [K, 128] matrix shared by all column tiles) -- the Khatri-Rao factor of the bilinear weight gradient
+    const float* bscale;
+    int lds;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -419,7 +425,24 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
             const int kbeg = ks * args.k_per_split, kend = min(args.K, kbeg + args.k_per_split);
             const int total_q = (kend - kbeg + TC_BK - 1) / TC_BK;
             auto fetch = [&](int q, float4 (&v)[8]) {
-                fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, kbeg + q * TC_BK, kend, b_vec, tid, v);
+                if (args.bscale == nullptr) {
+                    fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, kbeg + q * TC_BK, kend, b_vec, tid, v);
+                } else {
+                    // every column tile reads the same [K, 128] matrix, scaled per K row by this tile's weight
+                    const int kq = kbeg + q * TC_BK, nt = n0 / TC_BN;
+                    fetch_operand<B_KCONTIG>(args.B, args.ldb, 0, TC_BN, kq, kend, b_vec, tid, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        int r, c;
+                        tile_coord<B_KCONTIG>(tid, i, r, c);
+                        const int k = kq + 4 * c;
+                        const float* sp = args.bscale + static_cast<size_t>(k) * args.lds + nt;
+                        v[i].x *= k < kend ? sp[0] : 0.f;
+                        v[i].y *= k + 1 < kend ? sp[args.lds] : 0.f;
+                        v[i].z *= k + 2 < kend ? sp[2 * static_cast<size_t>(args.lds)] : 0.f;
+                        v[i].w *= k + 3 < kend ? sp[3 * static_cast<size_t>(args.lds)] : 0.f;
+                    }
+                }
             };
             auto commit = [&](int q, const float4 (&v)[8]) {
                 const int stage = q % TC_STAGES;
@@ -705,8 +728,9 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
-template <bool ROWDOT>
+template <int MODE>      // 0: store the tiles, 1: row-dot epilogue, 2: row-accumulate epilogue
 __global__ void __launch_bounds__(TA_THREADS, 1) gemm_tc_tmema_kernel(const TcArgs args) {
+    constexpr bool ROWDOT = MODE == 1, ROWACC = MODE == 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* b_stage = smem;                                           // [TA_BSTAGES][B_hi part, B_lo part]
     float* epi_stage = reinterpret_cast<float*>(b_stage + size_t(TA_BSTAGES) * TC_B_BLOB_BYTES);
@@ -869,6 +893,47 @@ __global__ void __launch_bounds__(TA_THREADS, 1) gemm_tc_tmema_kernel(const TcAr
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
+        } else if (ROWACC) {
+            // weighted sum of the column tiles: lane = row keeps the 64 running sums of its column half in registers
+            // over all column tiles of the row tile, and stores them once
+            static_assert(CH == 2, "row-accumulate epilogue assumes two 32-column chunks per epilogue warp");
+            const int half = ew / 4;
+            for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x) {
+                const int row = mi * TC_BM + quarter * 32 + lane;
+                const float* wrow = args.rd_t + static_cast<size_t>(row < args.M ? row : 0) * args.rd_ld;
+                float4 sum[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int n = 0; n < tiles_n; ++n) {
+                    const float wgt = row < args.M ? wrow[n] : 0.f;
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                               static_cast<uint32_t>(acc * TC_BN + (half * 2 + c) * 32);
+                        tmem_ld32(taddr, v);
+                        if (c == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4& a4 = sum[c * 8 + j];
+                            a4.x += wgt * __uint_as_float(v[4 * j]);     a4.y += wgt * __uint_as_float(v[4 * j + 1]);
+                            a4.z += wgt * __uint_as_float(v[4 * j + 2]); a4.w += wgt * __uint_as_float(v[4 * j + 3]);
+                        }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                if (row < args.M) {
+                    float* o = args.rd_out + static_cast<size_t>(row) * 128 + half * 64;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(o + 4 * j) = sum[j];
+                }
+            }
         } else {
             for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x)
                 for (int n = 0; n < tiles_n; ++n) {
@@ -939,7 +1004,7 @@ bool gemm_tc_enabled() {
 int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
                    int ldb, float beta, float* C, int ldc, const float* bias, void* ws, size_t ws_bytes,
                    cudaStream_t st, int* taken, int batch, long long sA, long long sB, long long sC, void* pre_ws,
-                   size_t pre_bytes) {
+                   size_t pre_bytes, const float* bscale, int lds) {
     *taken = 0;
     if (!gemm_tc_enabled() || K < 1 || batch < 1) return GCGCN_OK;
     if (static_cast<double>(M) * N * K * batch < 2.0e6) return GCGCN_OK;   // tiny: not worth a 128x128 tile
@@ -949,7 +1014,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     a.tiles_m = ceil_div(M, TC_BM);
     a.tiles_n = ceil_div(N, TC_BN);
     a.batch = batch; a.sA = sA; a.sB = sB; a.sC = sC;
-    a.rd_t = nullptr; a.rd_out = nullptr; a.rd_ld = 0;
+    a.rd_t = nullptr; a.rd_out = nullptr; a.rd_ld = 0; a.bscale = bscale; a.lds = lds;
     const int tiles = a.tiles_m * a.tiles_n * batch;
     const int sms = sm_count();
     int splits = 1;
@@ -990,6 +1055,9 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
                       a.tiles_n >= 2 &&
                       tiles * splits <= sms && pre_ws != nullptr && ablob_total <= pre_bytes &&
                       (reinterpret_cast<uintptr_t>(pre_ws) & 15) == 0;
+    if (bscale != nullptr && !apre)
+        return fail(GCGCN_ERR_UNSUPPORTED, "gemm: the generated-operand product needs the pre-split weight-gradient path "
+                    "(A transposed, K >= 8192, M <= 256, N >= 256, a pre-split workspace)");
     if (apre) {
         tc_presplit_b_kernel<<<a.tiles_m * a.kblocks, 256, 0, st>>>(A, lda, /*kcontig=*/0, M, K, a.kblocks,
                                                                   static_cast<uint8_t*>(pre_ws));
@@ -1016,11 +1084,11 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     if (resa && tmema_on && !ta) {
         static std::atomic<unsigned long long> attr_done2{0};
         if (!device_prepared(attr_done2)) {
-            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_tmema smem"));
             device_mark_prepared(attr_done2);
         }
-        gemm_tc_tmema_kernel<false><<<std::min(sms, a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
+        gemm_tc_tmema_kernel<0><<<std::min(sms, a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
     } else if (resa) {
         static std::atomic<unsigned long long> attr_done{0};
         if (!device_prepared(attr_done)) {
@@ -1047,37 +1115,51 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     return GCGCN_OK;
 }
 
-// Row-dot GEMM: part[(nt * 2 + half) * ld + m] = sum_{c in half of column tile nt} (A B)[m][128 nt + c] T[m][c]
-// -- the bilinear form out[p, r] = sum_b (h W')[p, r*128 + b] t[p, b] without ever storing h W' (97 x 128 floats per
-// pair).  A [M, K <= 128] row-major stays resident in tensor memory per row tile (split hi/lo), B [K, N] (N a multiple
-// of 128) streams through shared memory as pre-split blobs, the accumulator tiles are consumed from TMEM.
-int launch_gemm_rowdot(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* T, float* part,
-                       long long part_ld, void* ws, size_t ws_bytes, cudaStream_t st) {
+// Row-dot / row-accumulate GEMMs over a [M, K <= 128] row operand that stays resident in tensor memory per row tile
+// (split hi/lo) while B [K, N] (N a multiple of 128) streams through shared memory as pre-split blobs; the accumulator
+// tiles are consumed from TMEM and never stored:
+//   mode 1  part[(nt * 2 + half) * ld + m] = sum_{c in half of tile nt} (A B)[m][128 nt + c] T[m][c]
+//           -- the bilinear form out[p, r] = sum_b (h W')[p, r*128 + b] t[p, b]
+//   mode 2  out[m][c] = sum_nt T[m * ld + nt] (A B)[m][128 nt + c]
+//           -- its input gradients, dt[p, b] = sum_r dout[p, r] (h W')[p, r*128 + b]
+int launch_gemm_rowop(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* T,
+                      float* out, long long ld, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (M <= 0 || N <= 0) return GCGCN_OK;
     if (K < 1 || K > RA_KB * TC_BK || N % TC_BN != 0)
-        return fail(GCGCN_ERR_UNSUPPORTED, "gemm_rowdot: needs 1 <= K <= %d and N a multiple of %d (K %d, N %d)", RA_KB * TC_BK,
+        return fail(GCGCN_ERR_UNSUPPORTED, "gemm_rowop: needs 1 <= K <= %d and N a multiple of %d (K %d, N %d)", RA_KB * TC_BK,
                     TC_BN, K, N);
     TcArgs a;
     a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = 0;
     a.A = A; a.B = B; a.bias = nullptr; a.C = nullptr; a.partial = nullptr; a.alpha = 1.f; a.beta = 0.f;
     a.tiles_m = ceil_div(M, TC_BM); a.tiles_n = N / TC_BN; a.k_splits = 1; a.k_per_split = K;
     a.kblocks = ceil_div(K, TC_BK); a.batch = 1; a.sA = a.sB = a.sC = 0; a.Apre = nullptr;
-    a.rd_t = T; a.rd_out = part; a.rd_ld = part_ld;
+    a.rd_t = T; a.rd_out = out; a.rd_ld = ld; a.bscale = nullptr; a.lds = 0;
     const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
     if (ws == nullptr || blob_total > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
-        return fail(GCGCN_ERR_WORKSPACE, "gemm_rowdot: workspace of %zu bytes needed for the pre-split weights", blob_total);
+        return fail(GCGCN_ERR_WORKSPACE, "gemm_rowop: workspace of %zu bytes needed for the pre-split weights", blob_total);
     tc_presplit_b_kernel<<<a.tiles_n * a.kblocks, 256, 0, st>>>(B, ldb, 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
     GCGCN_CHECK_LAUNCH("gemm_presplit_b");
     a.Bpre = static_cast<const uint8_t*>(ws);
-    static std::atomic<unsigned long long> attr_done{0};
-    if (!device_prepared(attr_done)) {
-        GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_rowdot smem"));
-        device_mark_prepared(attr_done);
+    const int grid = std::min(sm_count(), a.tiles_m);
+    if (mode == 1) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (!device_prepared(attr_done)) {
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_rowdot smem"));
+            device_mark_prepared(attr_done);
+        }
+        gemm_tc_tmema_kernel<1><<<grid, TA_THREADS, TA_SMEM_BYTES, st>>>(a);
+    } else {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (!device_prepared(attr_done)) {
+            GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(gemm_tc_tmema_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(TA_SMEM_BYTES)), "gemm_tc_rowacc smem"));
+            device_mark_prepared(attr_done);
+        }
+        gemm_tc_tmema_kernel<2><<<grid, TA_THREADS, TA_SMEM_BYTES, st>>>(a);
     }
-    gemm_tc_tmema_kernel<true><<<std::min(sm_count(), a.tiles_m), TA_THREADS, TA_SMEM_BYTES, st>>>(a);
     timing_set_work(2.0 * M * N * K);
-    GCGCN_CHECK_LAUNCH("gemm_tc_rowdot<A in TMEM>");
+    GCGCN_CHECK_LAUNCH(mode == 1 ? "gemm_tc_rowdot<A in TMEM>" : "gemm_tc_rowacc<A in TMEM>");
     return GCGCN_OK;
 }
 

@@ -396,6 +396,17 @@ size_t gcgcn_bilinear_ws_bytes(int32_t rows, int32_t relations);
 int gcgcn_bilinear_fwd(const float* h, const float* t, const float* Wm, const float* bias, int32_t rows,
                        int32_t relations, int32_t accumulate, float* out, int32_t ldo, void* ws, size_t ws_bytes,
                        void* stream);
+/* Fused backward of the bilinear form for rows >= 8192 (GCGCN_ERR_UNSUPPORTED below that: use the three kernels
+ * further down), no [rows, relations*128] intermediate:
+ *   dt[p][b] = sum_r dout[p][r] (h W')[p][r*128 + b]      row-accumulate epilogue on the TMEM-resident GEMM, A = h, B = Wm
+ *   dh[p][a] = sum_r dout[p][r] (t W'')[p][r*128 + a]     the same with A = t, B = Wm2 (W viewed as [128 (b), relations*128 (r, a)])
+ *   dWm[a][r*128 + b] = beta dWm + sum_p h[p][a] dout[p][r] t[p][b]   weight-gradient GEMM whose [rows, relations*128]
+ *                       operand is generated in the producers from t and dout (never stored)
+ * dout [rows, relations] row-major.  ws >= gcgcn_bilinear_bwd_ws_bytes(rows, relations).                          */
+size_t gcgcn_bilinear_bwd_ws_bytes(int32_t rows, int32_t relations);
+int gcgcn_bilinear_bwd(const float* h, const float* t, const float* Wm, const float* Wm2, const float* dout, int32_t rows,
+                       int32_t relations, float beta, float* dh, float* dt, float* dWm, void* ws, size_t ws_bytes,
+                       void* stream);
 int gcgcn_bilinear_reduce_fwd(const float* Y, const float* t, const float* bias, int32_t rows, int32_t relations,
                               int32_t accumulate, float* out, int32_t ldo, void* stream);
 int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int32_t rows, int32_t relations, float* dY,
