@@ -148,10 +148,20 @@ word_pool_fwd_kernel(const EdgeTabs tb, const float* __restrict__ T, const float
     for (int l = lane; l < len; l += 32) at[l] *= inv;
     __syncwarp();
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int l = 0; l < len; ++l) {
-        const float w = at[l];
-        const float4 r = ld4(ctx + static_cast<size_t>(a0 + l) * D + 4 * lane);
-        acc.x += w * r.x; acc.y += w * r.y; acc.z += w * r.z; acc.w += w * r.w;
+    const float* crow = ctx + static_cast<size_t>(a0) * D + 4 * lane;
+    for (int l = 0; l < len; l += 8) {                  // eight context rows in flight per lane (the loop is latency bound)
+        float4 r[8];
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool ok = l + u < len;
+            r[u] = ok ? ld4(crow + static_cast<size_t>(l + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[u] = ok ? at[l + u] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc.x += w[u] * r[u].x; acc.y += w[u] * r[u].y; acc.z += w[u] * r[u].z; acc.w += w[u] * r[u].w;
+        }
     }
     st4(cwa + static_cast<size_t>(s) * 2 * D + side * D + 4 * lane, acc);
 }
@@ -169,10 +179,24 @@ word_pool_bwd_logit_kernel(const EdgeTabs tb, const float* __restrict__ ctx, con
     float* dl = dlog + tb.slot_att[s] + side * len;
     const float4 dc = ld4(dcwa + static_cast<size_t>(s) * 2 * D + side * D + 4 * lane);
     float dot = 0.f;
-    for (int l = 0; l < len; ++l) {
-        const float g = warp_sum(dot4(dc, ld4(ctx + static_cast<size_t>(a0 + l) * D + 4 * lane)));
-        if (lane == 0) dl[l] = g;
-        dot += at[l] * g;
+    const float* crow = ctx + static_cast<size_t>(a0) * D + 4 * lane;
+    for (int l = 0; l < len; l += 8) {                  // eight context rows in flight, then eight independent reductions
+        float p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            p[u] = l + u < len ? dot4(dc, ld4(crow + static_cast<size_t>(l + u) * D)) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) p[u] += __shfl_xor_sync(0xffffffffu, p[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (l + u < len) {
+                if (lane == 0) dl[l + u] = p[u];
+                dot += at[l + u] * p[u];
+            }
+        }
     }
     __syncwarp();
     for (int l = lane; l < len; l += 32) dl[l] = at[l] * (dl[l] - dot);
@@ -189,14 +213,25 @@ word_pool_bwd_token_kernel(const EdgeTabs tb, const float* __restrict__ att, con
     const int l = a - tb.tok_first[a];
     const int lo = tb.tok_slot_lo[a], hi = tb.tok_slot_hi[a];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = lo; s < hi; ++s) {
-        const int len = tb.slot_len[s];
-        if (l >= len) continue;
+    for (int s0 = lo; s0 < hi; s0 += 4) {               // four slots (eight gradient rows) in flight per lane
+        float4 d[8];
+        float w[8];
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const float w = att[tb.slot_att[s] + side * len + l];
-            const float4 d = ld4(dcwa + static_cast<size_t>(s) * 2 * D + side * D + 4 * lane);
-            acc.x += w * d.x; acc.y += w * d.y; acc.z += w * d.z; acc.w += w * d.w;
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u;
+            const int len = s < hi ? tb.slot_len[s] : 0;
+            const bool ok = l < len;
+            const int off = ok ? tb.slot_att[s] : 0;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                w[2 * u + side] = ok ? att[off + side * len + l] : 0.f;
+                d[2 * u + side] = ok ? ld4(dcwa + static_cast<size_t>(s) * 2 * D + side * D + 4 * lane)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc.x += w[u] * d[u].x; acc.y += w[u] * d[u].y; acc.z += w[u] * d[u].z; acc.w += w[u] * d[u].w;
         }
     }
     st4(dctx + static_cast<size_t>(a) * D + 4 * lane, acc);

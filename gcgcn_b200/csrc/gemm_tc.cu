@@ -68,6 +68,11 @@ struct TcArgs {
     // (B a [K, 128] matrix shared by all column tiles) -- the Khatri-Rao factor of the bilinear weight gradient
     const float* bscale;
     int lds;
+    // seq_k != 0 (APRE path, partial == nullptr): the k_splits K ranges of a tile are walked by ONE CTA in order
+    // (grid = tiles), each accumulated in TMEM from zero and added into C by the epilogue (beta = 1 after the first).
+    // Bounds the length of a single tensor-core accumulation: its fp32 adds truncate, and over tens of thousands of
+    // K steps the bias reaches 1e-4 of the result.
+    int seq_k;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -239,7 +244,8 @@ __device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, con
 // share of the accumulator is in registers.
 __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& args, uint32_t tmem_base, int acc, uint32_t tempty_bar_addr,
                                                  int quarter, float* stg, int m0, int n0, int bi, int ks, bool has_k,
-                                                 int lane, int chunk0 = 0, int chunks = TC_BN / 32) {
+                                                 int lane, int chunk0 = 0, int chunks = TC_BN / 32, float beta_override = -1.f) {
+    const float beta = beta_override >= 0.f ? beta_override : args.beta;
     const int row_base = m0 + quarter * 32;
     float* out_base;
     int ldo;
@@ -281,7 +287,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& args, uint32_t tm
             // each load behind the previous store (possible aliasing) and the epilogue becomes a chain of
             // eight global round trips per 32-column chunk
             float4 cold[8];
-            const bool rmw = final_out && args.beta != 0.f;
+            const bool rmw = final_out && beta != 0.f;
             if (rmw) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
@@ -301,8 +307,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& args, uint32_t tm
                         val.x = val.x * args.alpha + bias4.x; val.y = val.y * args.alpha + bias4.y;
                         val.z = val.z * args.alpha + bias4.z; val.w = val.w * args.alpha + bias4.w;
                         if (rmw) {
-                            val.x += args.beta * cold[it].x; val.y += args.beta * cold[it].y;
-                            val.z += args.beta * cold[it].z; val.w += args.beta * cold[it].w;
+                            val.x += beta * cold[it].x; val.y += beta * cold[it].y;
+                            val.z += beta * cold[it].z; val.w += beta * cold[it].w;
                         }
                     }
                     *p = val;
@@ -317,7 +323,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& args, uint32_t tm
                     float* p = out_base + static_cast<size_t>(row_base + rr) * ldo + col;
                     if (final_out) {
                         val = val * args.alpha + bias;
-                        if (args.beta != 0.f) val += args.beta * (*p);
+                        if (beta != 0.f) val += beta * (*p);
                     }
                     *p = val;
                 }
@@ -418,59 +424,64 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
                 q += GROUPS;
             }
         }
-        if (APRE && static_cast<int>(blockIdx.x) < total_tiles) {
-            // (batch == 1, one tile per CTA)  q = K block within this CTA's K range
-            const int t = blockIdx.x, ks = t / tiles_mn, rem = t - ks * tiles_mn;
-            const int mtile = rem / args.tiles_n, n0 = (rem % args.tiles_n) * TC_BN;
-            const int kbeg = ks * args.k_per_split, kend = min(args.K, kbeg + args.k_per_split);
-            const int total_q = (kend - kbeg + TC_BK - 1) / TC_BK;
-            auto fetch = [&](int q, float4 (&v)[8]) {
-                if (args.bscale == nullptr) {
-                    fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, kbeg + q * TC_BK, kend, b_vec, tid, v);
-                } else {
-                    // every column tile reads the same [K, 128] matrix, scaled per K row by this tile's weight
-                    const int kq = kbeg + q * TC_BK, nt = n0 / TC_BN;
-                    fetch_operand<B_KCONTIG>(args.B, args.ldb, 0, TC_BN, kq, kend, b_vec, tid, v);
+        if (APRE) {
+            // (batch == 1)  work items t = blockIdx.x, + gridDim.x, ...; jbase = K blocks of the earlier items, so that the
+            // stage / phase bookkeeping runs on across items exactly like the MMA warp's
+            int jbase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int ks = t / tiles_mn, rem = t - ks * tiles_mn;
+                const int mtile = rem / args.tiles_n, n0 = (rem % args.tiles_n) * TC_BN;
+                const int kbeg = ks * args.k_per_split, kend = min(args.K, kbeg + args.k_per_split);
+                const int total_q = kend > kbeg ? (kend - kbeg + TC_BK - 1) / TC_BK : 0;
+                auto fetch = [&](int q, float4 (&v)[8]) {
+                    if (args.bscale == nullptr) {
+                        fetch_operand<B_KCONTIG>(args.B, args.ldb, n0, args.N, kbeg + q * TC_BK, kend, b_vec, tid, v);
+                    } else {
+                        // every column tile reads the same [K, 128] matrix, scaled per K row by this tile's weight
+                        const int kq = kbeg + q * TC_BK, nt = n0 / TC_BN;
+                        fetch_operand<B_KCONTIG>(args.B, args.ldb, 0, TC_BN, kq, kend, b_vec, tid, v);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int r, c;
-                        tile_coord<B_KCONTIG>(tid, i, r, c);
-                        const int k = kq + 4 * c;
-                        const float* sp = args.bscale + static_cast<size_t>(k) * args.lds + nt;
-                        v[i].x *= k < kend ? sp[0] : 0.f;
-                        v[i].y *= k + 1 < kend ? sp[args.lds] : 0.f;
-                        v[i].z *= k + 2 < kend ? sp[2 * static_cast<size_t>(args.lds)] : 0.f;
-                        v[i].w *= k + 3 < kend ? sp[3 * static_cast<size_t>(args.lds)] : 0.f;
+                        for (int i = 0; i < 8; ++i) {
+                            int r, c;
+                            tile_coord<B_KCONTIG>(tid, i, r, c);
+                            const int k = kq + 4 * c;
+                            const float* sp = args.bscale + static_cast<size_t>(k) * args.lds + nt;
+                            v[i].x *= k < kend ? sp[0] : 0.f;
+                            v[i].y *= k + 1 < kend ? sp[args.lds] : 0.f;
+                            v[i].z *= k + 2 < kend ? sp[2 * static_cast<size_t>(args.lds)] : 0.f;
+                            v[i].w *= k + 3 < kend ? sp[3 * static_cast<size_t>(args.lds)] : 0.f;
+                        }
                     }
+                };
+                auto commit = [&](int q, const float4 (&v)[8]) {
+                    const int j = jbase + q, stage = j % TC_STAGES;
+                    const uint32_t phase = (j / TC_STAGES) & 1;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    uint8_t* stb = smem + size_t(stage) * TC_STAGE_BYTES;
+                    if (tid == 0) {
+                        const uint8_t* blob = args.Apre + (static_cast<size_t>(mtile) * args.kblocks + kbeg / TC_BK + q) * TC_B_BLOB_BYTES;
+                        mbar_arrive_expect_tx(full_bar(stage), TC_B_BLOB_BYTES);
+                        bulk_copy_g2s(smem_u32(stb), blob, TC_B_BLOB_BYTES, full_bar(stage));       // A_hi, A_lo parts
+                    }
+                    float* st = reinterpret_cast<float*>(stb);
+                    store_operand<B_KCONTIG>(st + 2 * (TC_PART_BYTES / 4), st + 3 * (TC_PART_BYTES / 4), tid, v);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(stage));
+                };
+                float4 vb0[8], vb1[8];
+                int q = ((group - jbase) % GROUPS + GROUPS) % GROUPS;       // first K block of the item with (jbase + q) % GROUPS == group
+                if (q < total_q) fetch(q, vb0);
+                while (q < total_q) {
+                    if (q + GROUPS < total_q) fetch(q + GROUPS, vb1);
+                    commit(q, vb0);
+                    q += GROUPS;
+                    if (q >= total_q) break;
+                    if (q + GROUPS < total_q) fetch(q + GROUPS, vb0);
+                    commit(q, vb1);
+                    q += GROUPS;
                 }
-            };
-            auto commit = [&](int q, const float4 (&v)[8]) {
-                const int stage = q % TC_STAGES;
-                const uint32_t phase = (q / TC_STAGES) & 1;
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                uint8_t* stb = smem + size_t(stage) * TC_STAGE_BYTES;
-                if (tid == 0) {
-                    const uint8_t* blob = args.Apre + (static_cast<size_t>(mtile) * args.kblocks + kbeg / TC_BK + q) * TC_B_BLOB_BYTES;
-                    mbar_arrive_expect_tx(full_bar(stage), TC_B_BLOB_BYTES);
-                    bulk_copy_g2s(smem_u32(stb), blob, TC_B_BLOB_BYTES, full_bar(stage));       // A_hi, A_lo parts
-                }
-                float* st = reinterpret_cast<float*>(stb);
-                store_operand<B_KCONTIG>(st + 2 * (TC_PART_BYTES / 4), st + 3 * (TC_PART_BYTES / 4), tid, v);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(stage));
-            };
-            float4 vb0[8], vb1[8];
-            int q = group;
-            if (q < total_q) fetch(q, vb0);
-            while (q < total_q) {
-                if (q + GROUPS < total_q) fetch(q + GROUPS, vb1);
-                commit(q, vb0);
-                q += GROUPS;
-                if (q >= total_q) break;
-                if (q + GROUPS < total_q) fetch(q + GROUPS, vb0);
-                commit(q, vb1);
-                q += GROUPS;
+                jbase += total_q;
             }
         }
         int j = 0;                                   // running K-block index of this CTA
@@ -551,7 +562,8 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
             const bool has_k = ks * args.k_per_split < args.K;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, m0, n0, bi, ks, has_k, lane);
+            tc_epilogue_tile(args, tmem_base, acc, tempty_bar(acc), quarter, stg, m0, n0, bi, ks, has_k, lane, 0, TC_BN / 32,
+                             (args.seq_k && ks > 0) ? 1.f : -1.f);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -1014,7 +1026,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     a.tiles_m = ceil_div(M, TC_BM);
     a.tiles_n = ceil_div(N, TC_BN);
     a.batch = batch; a.sA = sA; a.sB = sB; a.sC = sC;
-    a.rd_t = nullptr; a.rd_out = nullptr; a.rd_ld = 0; a.bscale = bscale; a.lds = lds;
+    a.rd_t = nullptr; a.rd_out = nullptr; a.rd_ld = 0; a.bscale = bscale; a.lds = lds; a.seq_k = 0;
     const int tiles = a.tiles_m * a.tiles_n * batch;
     const int sms = sm_count();
     int splits = 1;
@@ -1034,12 +1046,22 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
         a.partial = static_cast<float*>(ws);
     }
     a.k_splits = splits;
-    const int grid = std::min(sms, tiles * splits);
+    int grid = std::min(sms, tiles * splits);
+    // generated-operand weight gradient (K = every pair of the batch): one CTA per tile walks the K ranges in order and
+    // adds each range's accumulator into C, so that no single tensor-core accumulation is longer than 4096 rows
+    const bool seq = bscale != nullptr;
+    if (seq) {
+        a.k_per_split = 4096;
+        a.k_splits = splits = ceil_div(K, a.k_per_split);
+        a.partial = nullptr;
+        a.seq_k = 1;
+        grid = std::min(sms, tiles);
+    }
     a.Bpre = nullptr;
     a.kblocks = ceil_div(K, TC_BK);
     // weight-like B operand (small, reused by every 128-row tile of a tall A): pre-split it once per call
     const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
-    const bool bpre = gemm_tc_bpre_enabled() && batch == 1 && splits == 1 && !ta && M >= 4096 &&
+    const bool bpre = gemm_tc_bpre_enabled() && batch == 1 && splits == 1 && !seq && !ta && M >= 4096 &&
                       static_cast<size_t>(N) * K * sizeof(float) <= (size_t(8) << 20) && ws != nullptr &&
                       blob_total <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
     if (bpre) {
@@ -1053,7 +1075,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     // (worth it only when several column tiles re-use the blobs: a 128-wide output reads the operand once anyway)
     const bool apre = gemm_tc_bpre_enabled() && !bpre && batch == 1 && ta && !tb && K >= 8192 && M <= 2 * TC_BM &&
                       a.tiles_n >= 2 &&
-                      tiles * splits <= sms && pre_ws != nullptr && ablob_total <= pre_bytes &&
+                      (seq ? tiles <= sms : tiles * splits <= sms) && pre_ws != nullptr && ablob_total <= pre_bytes &&
                       (reinterpret_cast<uintptr_t>(pre_ws) & 15) == 0;
     if (bscale != nullptr && !apre)
         return fail(GCGCN_ERR_UNSUPPORTED, "gemm: the generated-operand product needs the pre-split weight-gradient path "
@@ -1109,7 +1131,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
                             : apre ? "gemm_tc_tn<presplit A>"
                             : bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
                             : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
-    if (splits > 1)
+    if (splits > 1 && !seq)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));
     *taken = 1;
     return GCGCN_OK;
@@ -1133,7 +1155,7 @@ int launch_gemm_rowop(int mode, int M, int N, int K, const float* A, int lda, co
     a.A = A; a.B = B; a.bias = nullptr; a.C = nullptr; a.partial = nullptr; a.alpha = 1.f; a.beta = 0.f;
     a.tiles_m = ceil_div(M, TC_BM); a.tiles_n = N / TC_BN; a.k_splits = 1; a.k_per_split = K;
     a.kblocks = ceil_div(K, TC_BK); a.batch = 1; a.sA = a.sB = a.sC = 0; a.Apre = nullptr;
-    a.rd_t = T; a.rd_out = out; a.rd_ld = ld; a.bscale = nullptr; a.lds = 0;
+    a.rd_t = T; a.rd_out = out; a.rd_ld = ld; a.bscale = nullptr; a.lds = 0; a.seq_k = 0;
     const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
     if (ws == nullptr || blob_total > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
         return fail(GCGCN_ERR_WORKSPACE, "gemm_rowop: workspace of %zu bytes needed for the pre-split weights", blob_total);

@@ -132,9 +132,13 @@ def test_bilinear_classifier_against_torch(P):
     t = torch.tanh(torch.randn(P, 128, generator=gen)).requires_grad_(True)
     up = torch.randn(P, 97, generator=gen)
     want = bili(h, t) + cls(torch.cat([h, t], -1))
-    (want * up).sum().backward()
-    ref = {"h": h.grad, "t": t.grad, "W": bili.weight.grad, "b": bili.bias.grad, "Wc": cls.weight.grad, "bc": cls.bias.grad}
+    # gradients: float64 reference (the parameter gradients sum P terms; an fp32 CPU sum of 20 000 terms is itself
+    # only good to ~1e-4 of its magnitude, which is what the comparison would then measure)
     import copy
+    b64, c64 = copy.deepcopy(bili).double(), copy.deepcopy(cls).double()
+    h64, t64 = h.detach().double().requires_grad_(True), t.detach().double().requires_grad_(True)
+    ((b64(h64, t64) + c64(torch.cat([h64, t64], -1))) * up.double()).sum().backward()
+    ref = {"h": h64.grad, "t": t64.grad, "W": b64.weight.grad, "b": b64.bias.grad, "Wc": c64.weight.grad, "bc": c64.bias.grad}
     bg, cg = copy.deepcopy(bili).to(DEV), copy.deepcopy(cls).to(DEV)
     for m in (bg, cg):
         m.zero_grad()
