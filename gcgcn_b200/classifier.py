@@ -119,12 +119,36 @@ class PairBceFn(Function):
         return dz, None, None
 
 
-def relation_logits(h: torch.Tensor, t: torch.Tensor, bili: nn.Bilinear, cls: nn.Linear) -> torch.Tensor:
+class DocBiasFn(Function):
+    """z + v[doc of pair]: the BERT variant's ``cls_feature`` (B:346-347) broadcast over each document's pair grid."""
+
+    @staticmethod
+    def forward(ctx, z, v, batch: RaggedBatch):
+        z, v = _cuda(z, "logits"), _cuda(v, "cls_feature")
+        if v.shape != (batch.num_docs, z.shape[1]):
+            raise _lib.GcgcnError(f"cls_feature must be [{batch.num_docs}, {z.shape[1]}], got {tuple(v.shape)}")
+        out = z.clone()
+        _lib.call("gcgcn_doc_bias_fwd", batch.ref, _p(v), z.shape[1], _p(out), _stream(z.device))
+        ctx.batch = batch
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        dz = _cuda(dz, "dlogits")
+        dv = torch.empty(ctx.batch.num_docs, dz.shape[1], device=dz.device)
+        _lib.call("gcgcn_doc_bias_bwd", ctx.batch.ref, _p(dz), dz.shape[1], _p(dv), _stream(dz.device))
+        return dz, dv, None
+
+
+def relation_logits(h: torch.Tensor, t: torch.Tensor, bili: nn.Bilinear, cls: nn.Linear, cls_feature=None,
+                    batch: RaggedBatch = None) -> torch.Tensor:
     """G:356-358: ``bili(h, t) + cls(cat[h, t])`` without forming the concatenation (the linear layer is split by
-    input columns into its h and t halves)."""
+    input columns into its h and t halves).  ``cls_feature`` [num_docs, R] (with ``batch``) adds the BERT variant's
+    per-document term, B:346-347."""
     w = cls.weight
     lin = LinearFn.apply(h, w[:, :D], cls.bias) + LinearFn.apply(t, w[:, D:], None)
-    return BilinearFn.apply(h, t, bili.weight, bili.bias) + lin
+    z = BilinearFn.apply(h, t, bili.weight, bili.bias) + lin
+    return z if cls_feature is None else DocBiasFn.apply(z, cls_feature, batch)
 
 
 def pair_bce_loss(logits: torch.Tensor, labels: torch.Tensor, batch: RaggedBatch) -> torch.Tensor:

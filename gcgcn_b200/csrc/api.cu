@@ -107,6 +107,8 @@ int launch_gemm_wgrad_scaled(int M, int tiles, int K, const float* A, int lda, c
                              size_t pre_bytes);
 int launch_bilinear_outer(const float* dout, int ldd, const float* t, int rows, int R, float* dY, cudaStream_t st);
 int launch_bilinear_dt(const float* dout, int ldd, const float* Y, int rows, int R, float* dt, cudaStream_t st);
+int launch_doc_bias_fwd(const gcgcn_batch* bt, const float* v, int R, float* z, cudaStream_t st);
+int launch_doc_bias_bwd(const gcgcn_batch* bt, const float* dz, int R, float* dv, cudaStream_t st);
 int launch_pair_bce_fwd(const gcgcn_batch* bt, const float* z, const float* y, int R, float* loss, cudaStream_t st);
 int launch_pair_bce_bwd(const gcgcn_batch* bt, const float* z, const float* y, int R, const float* dloss, float* dz,
                         cudaStream_t st);
@@ -1160,6 +1162,24 @@ int gcgcn_bilinear_dt_bwd(const float* dout, int32_t ldd, const float* Y, int32_
     GCGCN_TRY(check_device_ptr(Y, "Y"));
     GCGCN_TRY(check_device_ptr(dt, "dt"));
     return launch_bilinear_dt(dout, ldd, Y, rows, relations, dt, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_doc_bias_fwd(const gcgcn_batch* bt, const float* v, int32_t relations, float* z, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(relations >= 1, "doc_bias_fwd: relations < 1");
+    if (bt->total_pairs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(v, "v"));
+    GCGCN_TRY(check_device_ptr(z, "z"));
+    return launch_doc_bias_fwd(bt, v, relations, z, static_cast<cudaStream_t>(stream));
+}
+int gcgcn_doc_bias_bwd(const gcgcn_batch* bt, const float* dz, int32_t relations, float* dv, void* stream) {
+    GCGCN_API_ENTER(stream);
+    GCGCN_TRY(check_batch(bt));
+    GCGCN_REQUIRE(relations >= 1, "doc_bias_bwd: relations < 1");
+    if (bt->num_docs == 0) return GCGCN_OK;
+    GCGCN_TRY(check_device_ptr(dv, "dv"));
+    if (bt->total_pairs > 0) GCGCN_TRY(check_device_ptr(dz, "dz"));
+    return launch_doc_bias_bwd(bt, dz, relations, dv, static_cast<cudaStream_t>(stream));
 }
 int gcgcn_pair_bce_fwd(const gcgcn_batch* bt, const float* logits, const float* labels, int32_t relations, float* loss,
                        void* stream) {

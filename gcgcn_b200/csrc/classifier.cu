@@ -162,7 +162,46 @@ bilinear_finish_kernel(const float* __restrict__ part, long long ld, const float
     }
 }
 
+// ---- per-document vector added to every pair of the document (the BERT variant's cls_feature, B:346-347) ----------
+// fwd: z[p][r] += v[doc(p)][r];  bwd: dv[b][r] = sum over the n_b^2 pairs of document b of dz[p][r] (fixed order)
+__global__ void __launch_bounds__(256)
+doc_bias_fwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr, const float* __restrict__ v,
+                    int R, float* __restrict__ z) {
+    const int b = blockIdx.x;
+    const int n = node_ptr[b + 1] - node_ptr[b];
+    const long long cells = static_cast<long long>(n) * n * R;
+    float* zz = z + pair_ptr[b] * R;
+    const float* vv = v + static_cast<size_t>(b) * R;
+    for (long long c = threadIdx.x; c < cells; c += blockDim.x) zz[c] += vv[c % R];
+}
+__global__ void __launch_bounds__(256)
+doc_bias_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__ pair_ptr, const float* __restrict__ dz,
+                    int R, float* __restrict__ dv) {
+    const int b = blockIdx.x;
+    const int n = node_ptr[b + 1] - node_ptr[b];
+    const long long pairs = static_cast<long long>(n) * n;
+    const float* zz = dz + pair_ptr[b] * R;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float acc = 0.f;
+        for (long long p = 0; p < pairs; ++p) acc += zz[p * R + r];
+        dv[static_cast<size_t>(b) * R + r] = acc;
+    }
+}
+
 static int cl_grid(long long warps) { return static_cast<int>((warps + 7) / 8); }
+
+int launch_doc_bias_fwd(const gcgcn_batch* bt, const float* v, int R, float* z, cudaStream_t st) {
+    if (bt->num_docs <= 0 || R <= 0) return GCGCN_OK;
+    doc_bias_fwd_kernel<<<bt->num_docs, 256, 0, st>>>(bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), v, R, z);
+    GCGCN_CHECK_LAUNCH("doc_bias_fwd");
+    return GCGCN_OK;
+}
+int launch_doc_bias_bwd(const gcgcn_batch* bt, const float* dz, int R, float* dv, cudaStream_t st) {
+    if (bt->num_docs <= 0 || R <= 0) return GCGCN_OK;
+    doc_bias_bwd_kernel<<<bt->num_docs, 128, 0, st>>>(bt->node_ptr, reinterpret_cast<const long long*>(bt->pair_ptr), dz, R, dv);
+    GCGCN_CHECK_LAUNCH("doc_bias_bwd");
+    return GCGCN_OK;
+}
 
 int launch_bilinear_finish(const float* part, long long ld, const float* bias, int rows, int R, int accumulate, float* out,
                            int ldo, cudaStream_t st) {

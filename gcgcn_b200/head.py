@@ -45,8 +45,11 @@ class HeadBatch:
 
 
 class GraphHead(nn.Module):
+    """``GraphHead()`` = GCGCN_glove's head (G:250-279); ``GraphHead(4, 4, cls_dim=768)`` = the BERT variant's
+    (models/GraphCNN_multihead_bert_gate_cls.py:247-267), which adds ``linear_cls`` on BERT's first-token feature."""
+
     def __init__(self, layer_num=2, head_num=8, relation_num=97, dis_size=20, dis_num=21, entity_type_size=20,
-                 hidden_size=HIDDEN, graph_hop=2):
+                 hidden_size=HIDDEN, graph_hop=2, cls_dim: int = 0):
         super().__init__()
         blocks = GraphBlocks(layer_num, head_num, hidden_size=hidden_size, graph_hop=graph_hop, overlap=False)
         # the graph modules under the reference model's attribute names (G:254-262)
@@ -63,6 +66,8 @@ class GraphHead(nn.Module):
         self.dense_layer = nn.Linear(hidden_size * (graph_hop + 1) + dis_size + entity_type_size, hidden_size)   # G:272
         self.bili_layer_01 = nn.Bilinear(hidden_size, hidden_size, relation_num)                                 # G:275
         self.classification_layer_01 = nn.Linear(hidden_size * 2, relation_num)                                  # G:276
+        if cls_dim:
+            self.linear_cls = nn.Linear(cls_dim, relation_num)                                                   # B:265
         self.dis_embed = nn.Embedding(dis_num, dis_size)                                                         # G:279
         self.ner_emb = nn.Embedding(7, entity_type_size, padding_idx=0)                                          # G:242
 
@@ -71,9 +76,11 @@ class GraphHead(nn.Module):
         self._blocks.train(mode)
         return self
 
-    def forward(self, context: torch.Tensor, hb: HeadBatch, edge_dtype=torch.float32, labels: Optional[torch.Tensor] = None):
-        """context [total_tokens, 128] = ``context_output`` of every document back to back.  Returns a dict with
-        x0, e0, y1, e1, y2, entity_feature_h / _t, logits [total_pairs, R] and, given labels, the per-document loss."""
+    def forward(self, context: torch.Tensor, hb: HeadBatch, edge_dtype=torch.float32, labels: Optional[torch.Tensor] = None,
+                cls_feat: Optional[torch.Tensor] = None):
+        """context [total_tokens, 128] = ``context_output`` of every document back to back; cls_feat [num_docs, cls_dim]
+        = BERT's first-token feature of every document (BERT variant only, B:277).  Returns a dict with x0, e0, y1, e1,
+        y2, entity_feature_h / _t, logits [total_pairs, R] and, given labels, the per-document loss."""
         if not context.is_cuda:
             raise _lib.GcgcnError("GraphHead: gcgcn_b200 runs on CUDA only (no CPU fallback)")
         bt, blocks, edge = hb.batch, self._blocks, self._edge
@@ -87,7 +94,12 @@ class GraphHead(nn.Module):
         type_feats = nn.functional.embedding(hb.node_type, self.ner_emb.weight, padding_idx=0)
         feats = torch.cat([x0, x0, y1, type_feats], 1)                                 # G:343-347: cat[x0, x0, y1, type]
         fh, ft = pair_dense(feats, self.dense_layer, dis, hb.pairs, bt)                # G:351-355
-        logits = relation_logits(fh, ft, self.bili_layer_01, self.classification_layer_01)   # G:356-358
+        cls_feature = None
+        if hasattr(self, "linear_cls"):
+            if cls_feat is None:
+                raise _lib.GcgcnError("GraphHead(cls_dim=...) needs cls_feat [num_docs, cls_dim] (B:277)")
+            cls_feature = LinearFn.apply(cls_feat, self.linear_cls.weight, self.linear_cls.bias)              # B:346
+        logits = relation_logits(fh, ft, self.bili_layer_01, self.classification_layer_01, cls_feature, bt)   # G:356-358
         out = {"x0": x0, "e0": e0, "y1": y1, "e1": e1, "y2": y2, "a0": a0, "a1": a1, "entity_feature_h": fh,
                "entity_feature_t": ft, "logits": logits}
         if labels is not None:

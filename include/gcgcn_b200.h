@@ -413,6 +413,11 @@ int gcgcn_bilinear_outer_bwd(const float* dout, int32_t ldd, const float* t, int
                              void* stream);
 int gcgcn_bilinear_dt_bwd(const float* dout, int32_t ldd, const float* Y, int32_t rows, int32_t relations, float* dt,
                           void* stream);
+/* cls_feature of the BERT variant (models/GraphCNN_multihead_bert_gate_cls.py:346-347): a per-document vector
+ * v[b] = linear_cls(cls_feat_b) added to the logits of every pair of document b.  z [total_pairs, relations] in place;
+ * bwd: dv[b] = sum of dz over the document's pairs.                                                              */
+int gcgcn_doc_bias_fwd(const gcgcn_batch* bt, const float* v, int32_t relations, float* z, void* stream);
+int gcgcn_doc_bias_bwd(const gcgcn_batch* bt, const float* dz, int32_t relations, float* dv, void* stream);
 /* The trainer's loss, config/Config.py:355-364, per document of the batch: predict = sigmoid(logits) (C:355), then the
  * mean over the ordered pairs i != j of BCELoss(predict[i][j], label[i][j]) (mean over the R relation slots, C:361-364;
  * torch's clamping of the logs at -100 included).  logits, labels [total_pairs, R]; loss [num_docs].

@@ -14,9 +14,12 @@ logits: G = /root/reference/models/GCGCN_glove.py.
     graph_head           G:293-358   everything after ``context_output`` for one document
     loss_as_written      C:355-364   the trainer's per-pair BCE loop on sigmoid(logits)
 
-Parity pin: ``oracle/pin_edge_features.py`` runs every function against the reference's own classes (loaded by
-path, bit-exact on outputs and gradients); ``tests/golden/edge_*.npz`` are outputs of the reference itself
-(``tests/golden/make_golden_edge.py``).
+Parity pin: ``tests/golden/make_golden_edge.py`` (build container only) builds the UNMODIFIED reference models --
+GCGCN_glove and the BERT variant, loaded by path -- loads the deterministic head weights of
+``tests/helpers.head_state`` into them, runs their own ``forward`` and the trainer's literal loss loop, and requires
+``graph_head`` + ``loss_as_written`` below to reproduce logits, both hops' ``context_sent_att``, the loss, d loss / d
+``context_output`` and every head parameter's gradient (worst relative difference 2.9e-7); the same run writes
+``tests/golden/edge_head.npz`` / ``edge_head_bert.npz``, which the CPU and GPU tests compare against.
 
 Parameters use the reference's ``state_dict`` key names relative to each module (``attention_sent.weight`` ...).
 """
@@ -116,9 +119,11 @@ def loss_as_written(logits: Tensor, label: Tensor) -> Tensor:
 
 
 def graph_head(ctx: Tensor, node_pos: Tensor, sen: Tensor, pos_h: Tensor, pos_t: Tensor, adj: Tensor,
-               node_type: Tensor, rel_pos: Tensor, params: Params, layers: int, heads: int, alpha: float = 1.0) -> dict:
+               node_type: Tensor, rel_pos: Tensor, params: Params, layers: int, heads: int, alpha: float = 1.0,
+               cls_feat: Optional[Tensor] = None) -> dict:
     """G:293-358 for one document in eval mode: pooling, two hops of (edge-feature producer -> graph block),
-    classifier.  ``params`` uses the top-level model's key names."""
+    classifier.  ``params`` uses the top-level model's key names.  ``cls_feat`` [768] (BERT variant, B:277) adds
+    ``linear_cls(cls_feat)`` to every pair's logits (B:346-347)."""
     x0 = O.pool_nodes(node_pos, ctx.unsqueeze(0))                           # G:297-298
     node_feat, feats, edges = x0, [x0], []
     for i in range(2):                                                      # G:310 (graph_hop = 2)
@@ -137,5 +142,8 @@ def graph_head(ctx: Tensor, node_pos: Tensor, sen: Tensor, pos_h: Tensor, pos_t:
         node_feat = alpha * new + (1 - alpha) * node_feat                   # G:339
     node_feats = torch.cat(feats, 1)                                        # G:343
     logits, fh, ft = classifier(node_feats, node_type, rel_pos, params)
+    if cls_feat is not None:
+        n = logits.size(0)
+        logits = logits + _lin(cls_feat, params, "linear_cls").unsqueeze(0).unsqueeze(0).expand(n, n, -1)   # B:346-347
     return {"x0": x0, "e0": edges[0], "e1": edges[1], "y1": feats[2], "y2": node_feat, "logits": logits,
             "entity_feature_h": fh, "entity_feature_t": ft}

@@ -40,6 +40,25 @@ DOCS = [(8, 7, 150, None), (10, 9, 230, None), (2, 6, 90, 3), (10, 10, 600, None
 BIG_STRIDE = 997
 
 
+BERT_DOCS = [(8, 7, 150, None), (2, 6, 90, 3)]
+
+
+def build_reference_bert(state):
+    m = R.bert_module()
+    cfg = types.SimpleNamespace(entity_type_size=20, coref_size=20, max_length=512, keep_prob=1.0, graph_hop=2, dis_size=20,
+                                dis_num=21, dis_plus=10, relation_num=97, alpha=1.0)
+    torch.manual_seed(0)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = m.GraphCNN_multihead_bert_gate_cls(cfg)
+    sd = model.state_dict()
+    for k, shape in head_shapes(4, 4, cls_dim=768).items():
+        assert tuple(sd[k].shape) == tuple(shape), (k, sd[k].shape, shape)
+    missing = model.load_state_dict(state, strict=False)
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    return model.eval()
+
+
 def build_reference(state):
     m = R.glove_module()
     rng = np.random.RandomState(0)
@@ -58,7 +77,8 @@ def build_reference(state):
     return model.eval()
 
 
-def reference_pass(model, item, labels):
+def reference_pass(model, item, labels, shapes=None):
+    shapes = head_shapes() if shapes is None else shapes
     t = FO.from_list_to_tensor(item)
     L = min(len(item["document"]), 512)
     tt = lambda k, dt: torch.from_numpy(np.asarray(t[k])).to(dt)
@@ -68,6 +88,9 @@ def reference_pass(model, item, labels):
         out.retain_grad()
         captured["pre"] = out
     hooks = [model.linear_re.register_forward_hook(grab_pre)]
+    if hasattr(model, "bert"):                # BERT variant: the first-token feature of the (stubbed) encoder, B:277
+        hooks.append(model.bert.register_forward_hook(
+            lambda _, __, out: captured.__setitem__("cls_feat", out[0][0, 0, :].detach().clone())))
     for i in range(2):
         hooks.append(model.linear_sentence_att[i].register_forward_hook(
             lambda _, __, out, i=i: captured.__setitem__(f"e{i}", out.detach().clone())))
@@ -95,19 +118,19 @@ def reference_pass(model, item, labels):
     dctx = (pre.grad[0].double() / (1.0 - ctx.double() ** 2)).float()      # through tanh: d/dctx = d/dpre / (1 - ctx^2)
     # ner_emb is shared with the (out-of-scope) encoder input (G:286), so its gradient is not a head-only quantity
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()
-             if k in head_shapes() and k != "ner_emb.weight" and p.grad is not None}
-    return {"ctx": ctx, "e0": captured["e0"], "e1": captured["e1"], "logits": logits.detach(), "loss": loss.detach(),
+             if k in shapes and k != "ner_emb.weight" and p.grad is not None}
+    return {"cls_feat": captured.get("cls_feat"), "ctx": ctx, "e0": captured["e0"], "e1": captured["e1"], "logits": logits.detach(), "loss": loss.detach(),
             "dctx": dctx, "grads": grads, "tensors": t, "L": L}
 
 
-def oracle_pass(state, ref, labels):
+def oracle_pass(state, ref, labels, layers=2, heads=8):
     ps = {k: v.clone().requires_grad_(True) for k, v in state.items()}
     t = ref["tensors"]
     ctx = ref["ctx"].clone().requires_grad_(True)
     tt = lambda k, dt: torch.from_numpy(np.asarray(t[k])).to(dt)
     r = EO.graph_head(ctx, tt("node_pos", torch.float32), tt("sen_matrix", torch.bool), tt("pos_matrix_h", torch.int64),
                       tt("pos_matrix_t", torch.int64), tt("adj_matrix", torch.float32), tt("node_type", torch.int64),
-                      tt("node_relative_pos", torch.int64), ps, 2, 8)
+                      tt("node_relative_pos", torch.int64), ps, layers, heads, cls_feat=ref.get("cls_feat"))
     loss = EO.loss_as_written(r["logits"], labels)
     loss.backward()
     return r, loss.detach(), ctx.grad, {k: v.grad for k, v in ps.items() if v.grad is not None}
@@ -151,6 +174,37 @@ def main():
             out[p + "g_" + k] = a if a.size <= 40000 else a[::BIG_STRIDE].copy()
     np.savez_compressed(os.path.join(HERE, "edge_head.npz"), **out)
     print(f"wrote edge_head.npz ({os.path.getsize(os.path.join(HERE, 'edge_head.npz')) / 1e6:.2f} MB); "
+          f"oracle pinned: worst relative diff {worst:.2e}")
+
+    # ---- the BERT variant (models/GraphCNN_multihead_bert_gate_cls.py): L_s = 4, H = 4, + linear_cls on the encoder's
+    # first-token feature.  BertModel is the stub of oracle/reference_loader.py (the encoder is out of scope: its output
+    # is captured and becomes the head's input).
+    state = head_state(0, 4, 4, cls_dim=768)
+    shapes = head_shapes(4, 4, cls_dim=768)
+    model = build_reference_bert(state)
+    out, worst = {}, 0.0
+    for idx, (seed, n, L, Sx) in enumerate(BERT_DOCS):
+        item = S.make_record(seed, n=n, L=L, S=Sx)
+        labels = head_labels(seed, n)
+        ref = reference_pass(model, item, labels, shapes)
+        r, loss, dctx, grads = oracle_pass(state, ref, labels, 4, 4)
+        diffs = {"logits": (r["logits"] - ref["logits"]).abs().max().item(), "loss": (loss - ref["loss"]).abs().max().item(),
+                 "dctx": (dctx - ref["dctx"]).abs().max().item() / max(ref["dctx"].abs().max().item(), 1e-30)}
+        for k, g in ref["grads"].items():
+            diffs["g_" + k] = (grads[k] - g).abs().max().item() / max(g.abs().max().item(), 1e-3)
+        bad = {k: v for k, v in diffs.items() if v > 2e-5}
+        print(f"bert record {seed}: n={n} max oracle-vs-reference diff {max(diffs.values()):.2e}")
+        assert not bad, bad
+        worst = max(worst, max(diffs.values()))
+        p = f"d{idx}_"
+        out[p + "meta"] = np.asarray([seed, n, L, -1 if Sx is None else Sx, 0], dtype=np.int64)
+        for k in ("ctx", "cls_feat", "logits", "loss", "dctx"):
+            out[p + k] = ref[k].numpy()
+        for k, g in ref["grads"].items():
+            a = g.numpy().reshape(-1)
+            out[p + "g_" + k] = a if a.size <= 40000 else a[::BIG_STRIDE].copy()
+    np.savez_compressed(os.path.join(HERE, "edge_head_bert.npz"), **out)
+    print(f"wrote edge_head_bert.npz ({os.path.getsize(os.path.join(HERE, 'edge_head_bert.npz')) / 1e6:.2f} MB); "
           f"oracle pinned: worst relative diff {worst:.2e}")
 
 

@@ -91,7 +91,7 @@ def assert_close(a, b, tol, what=""):
 
 
 # ------------------------------------------------------------------------------- graph head
-def head_shapes(layers=2, heads=8, hidden=128, dis_size=20, type_size=20, relations=97, hops=2):
+def head_shapes(layers=2, heads=8, hidden=128, dis_size=20, type_size=20, relations=97, hops=2, cls_dim=0):
     """state_dict keys -> shapes of everything the reference model owns after ``context_output`` (G:254-279)."""
     g = hidden // layers
     s = {}
@@ -138,18 +138,21 @@ def head_shapes(layers=2, heads=8, hidden=128, dis_size=20, type_size=20, relati
     s["bili_layer_01.bias"] = (relations,)
     s["classification_layer_01.weight"] = (relations, 2 * hidden)
     s["classification_layer_01.bias"] = (relations,)
+    if cls_dim:                                     # BERT variant only (B:265)
+        s["linear_cls.weight"] = (relations, cls_dim)
+        s["linear_cls.bias"] = (relations,)
     s["dis_embed.weight"] = (21, dis_size)
     s["ner_emb.weight"] = (7, type_size)
     return s
 
 
-def head_state(seed=0, layers=2, heads=8):
+def head_state(seed=0, layers=2, heads=8, cls_dim=0):
     """Deterministic weights for every head parameter (uniform, fan-in scaled), independent of any module's init
     order: tests/golden/make_golden_edge.py loads the same values into the UNMODIFIED reference model, the GPU tests
     load them into the drop-in modules.  Embedding row 0 of ner_emb is the padding row (G:242)."""
     gen = torch.Generator().manual_seed(4321 + seed)
     out = {}
-    for name, shape in head_shapes(layers, heads).items():
+    for name, shape in head_shapes(layers, heads, cls_dim=cls_dim).items():
         if len(shape) == 1:
             bound = 0.1
         elif name.endswith("weights_node") or name.endswith("weights_edge"):

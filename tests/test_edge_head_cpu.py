@@ -91,3 +91,16 @@ def test_edge_tables_list_exactly_the_slots_that_survive_the_token0_mask(seed, n
         for e in ctr[ptr[r]:ptr[r + 1]].tolist():
             s, side = divmod(e, 2)
             assert (h["slot_rowj"][s] if side == 0 else h["slot_rowi"][s]) == r
+
+
+def test_oracle_bert_variant_reproduces_the_reference_golden():
+    g = golden("edge_head_bert.npz")
+    seed, n, L, Sx, _ = g["d1_meta"].tolist()
+    item = S.make_record(seed, n=n, L=L, S=None if Sx < 0 else Sx)
+    state = head_state(0, 4, 4, cls_dim=768)
+    with torch.no_grad():
+        r = EO.graph_head(torch.from_numpy(g["d1_ctx"]), *_dense(item), state, 4, 4, cls_feat=torch.from_numpy(g["d1_cls_feat"]))
+    assert float((r["logits"] - torch.from_numpy(g["d1_logits"])).abs().max()) <= 2e-5
+    from gcgcn_b200.head import GraphHead
+    res = GraphHead(4, 4, cls_dim=768).load_state_dict(state, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys

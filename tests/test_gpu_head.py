@@ -163,3 +163,36 @@ def test_bilinear_classifier_against_torch(P):
     assert float((chunked.detach() - got.detach()).abs().max()) <= 2e-5
     for k, g in (("h", hg.grad), ("t", tg.grad), ("W", bg.weight.grad)):
         assert rel(fused[k], g) <= 1e-4, k           # two summation orders of 12416-term 3xTF32 sums
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_bert_variant_head_matches_the_reference_model(idx):
+    """models/GraphCNN_multihead_bert_gate_cls.py: L_s = 4, H = 4 and ``linear_cls`` on the encoder's first-token feature
+    (B:346-347), against goldens from the unmodified reference model (its BERT encoder stubbed: ctx and cls_feat are the
+    head's inputs)."""
+    g = golden("edge_head_bert.npz")
+    seed, n, w = golden_doc(g, idx)
+    head = GraphHead(4, 4, cls_dim=768)
+    head.load_state_dict(head_state(0, 4, 4, cls_dim=768), strict=True)
+    head = head.to(DEV).eval()
+    hb = HeadBatch([w], DEV)
+    ctx = torch.from_numpy(g[f"d{idx}_ctx"]).to(DEV).requires_grad_(True)
+    cls_feat = torch.from_numpy(g[f"d{idx}_cls_feat"]).view(1, -1).to(DEV)
+    labels = head_labels(seed, n).view(-1, 97).to(DEV)
+    out = head(ctx, hb, labels=labels, cls_feat=cls_feat)
+    out["loss"].sum().backward()
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g[f"d{idx}_logits"])
+    logits = out["logits"].detach().cpu().view(n, n, 97)
+    assert float((logits - ref).abs().max()) <= FP32_TOL
+    assert float((logits.argmax(-1) == ref.argmax(-1)).float().mean()) >= 0.999
+    assert abs(float(out["loss"][0].detach()) - float(g[f"d{idx}_loss"].reshape(-1)[0])) <= 1e-5
+    assert rel(ctx.grad, g[f"d{idx}_dctx"]) <= 2e-4
+    checked = 0
+    for k, p in head.named_parameters():
+        key = f"d{idx}_g_{k}"
+        if key in g.files:
+            a = p.grad.detach().cpu().numpy().reshape(-1)
+            assert rel(a if a.size <= 40000 else a[::BIG_STRIDE], g[key]) <= 2e-4, k
+            checked += 1
+    assert checked == 43          # GAT 8, CAGGC 4*2 + 2, hop-0 producer 16, dense 2, bilinear 2, linear 2, linear_cls 2, dis_embed
