@@ -71,6 +71,7 @@ def parse():
                     "micro-batch per rank after one NCCL all-reduce of the flat gradient bucket; --steps is ignored "
                     "(the timed region is the whole pass over the documents)")
     ap.add_argument("--micro", type=int, default=6252, help="documents per micro-batch per rank with --train-docs")
+    ap.add_argument("--no-overlap", action="store_true", help="keep the hop-1 edge pass on the main stream (GraphBlocks(overlap=False))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the separate pooling / pair-gather timings")
@@ -724,7 +725,7 @@ def run_gpu_arm(args):
     edt = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     esz = 4 if args.dtype == "fp32" else 2
     torch.manual_seed(0)
-    gb = GraphBlocks(layers, heads).to(dev).eval()
+    gb = GraphBlocks(layers, heads, overlap=not args.no_overlap).to(dev).eval()
     if args.train:
         gb.train()
     if args.nodes:

@@ -971,7 +971,9 @@ tc_presplit_b_kernel(const float* __restrict__ B, int ldb, int b_kcontig, int N,
     const int n0 = nt * TC_BN, k0 = kb * TC_BK;
     float* hi = reinterpret_cast<float*>(blobs + static_cast<size_t>(blob) * TC_B_BLOB_BYTES);
     float* lo = hi + TC_PART_BYTES / 4;
-    for (int idx = threadIdx.x; idx < TC_BN * (TC_BK / 4); idx += 256) {
+    // (the four quarters of a blob are independent: gridDim.y = 4 blocks of one element each per thread, so that the
+    //  launch -- tens of them per step sit on the critical path -- is one memory round trip long, not four)
+    for (int idx = blockIdx.y * 256 + threadIdx.x; idx < TC_BN * (TC_BK / 4); idx += 256 * gridDim.y) {
         int r, c;
         if (b_kcontig) { c = idx & 7; r = idx >> 3; } else { r = idx & (TC_BN - 1); c = idx >> 7; }
         const int n = n0 + r, k = k0 + 4 * c;
@@ -1065,7 +1067,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
                       static_cast<size_t>(N) * K * sizeof(float) <= (size_t(8) << 20) && ws != nullptr &&
                       blob_total <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
     if (bpre) {
-        tc_presplit_b_kernel<<<a.tiles_n * a.kblocks, 256, 0, st>>>(B, ldb, tb != 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
+        tc_presplit_b_kernel<<<dim3(a.tiles_n * a.kblocks, 4), 256, 0, st>>>(B, ldb, tb != 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
         GCGCN_CHECK_LAUNCH("gemm_presplit_b");
         a.Bpre = static_cast<const uint8_t*>(ws);
     }
@@ -1081,7 +1083,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
         return fail(GCGCN_ERR_UNSUPPORTED, "gemm: the generated-operand product needs the pre-split weight-gradient path "
                     "(A transposed, K >= 8192, M <= 256, N >= 256, a pre-split workspace)");
     if (apre) {
-        tc_presplit_b_kernel<<<a.tiles_m * a.kblocks, 256, 0, st>>>(A, lda, /*kcontig=*/0, M, K, a.kblocks,
+        tc_presplit_b_kernel<<<dim3(a.tiles_m * a.kblocks, 4), 256, 0, st>>>(A, lda, /*kcontig=*/0, M, K, a.kblocks,
                                                                   static_cast<uint8_t*>(pre_ws));
         GCGCN_CHECK_LAUNCH("gemm_presplit_a");
         a.Apre = static_cast<const uint8_t*>(pre_ws);
@@ -1159,7 +1161,7 @@ int launch_gemm_rowop(int mode, int M, int N, int K, const float* A, int lda, co
     const size_t blob_total = static_cast<size_t>(a.tiles_n) * a.kblocks * TC_B_BLOB_BYTES;
     if (ws == nullptr || blob_total > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
         return fail(GCGCN_ERR_WORKSPACE, "gemm_rowop: workspace of %zu bytes needed for the pre-split weights", blob_total);
-    tc_presplit_b_kernel<<<a.tiles_n * a.kblocks, 256, 0, st>>>(B, ldb, 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
+    tc_presplit_b_kernel<<<dim3(a.tiles_n * a.kblocks, 4), 256, 0, st>>>(B, ldb, 0, N, K, a.kblocks, static_cast<uint8_t*>(ws));
     GCGCN_CHECK_LAUNCH("gemm_presplit_b");
     a.Bpre = static_cast<const uint8_t*>(ws);
     const int grid = std::min(sm_count(), a.tiles_m);

@@ -141,3 +141,40 @@ def test_flat_trainer_views_and_cpu_step_is_an_error():
     assert float(tr.flat.abs().sum()) == 0.0 and w.grad.data_ptr() >= tr.flat.data_ptr()
     with pytest.raises(_lib.GcgcnError):
         tr.step()
+
+
+def test_pool_table_concat_appends_rows_over_the_same_tokens():
+    """PoolTable.concat (one gather for the entity pooling and the producer's active context rows)."""
+    import numpy as np
+    from gcgcn_b200.batch import PoolTable
+    a = PoolTable.from_spans([[[[0, 2]], [[3, 4], [5, 7]]]], [10])
+    b = PoolTable(np.arange(4), np.asarray([0, 1, 2]), np.ones(3, np.float32), 10)
+    c = PoolTable.concat(a, b)
+    assert c.total_nodes == a.total_nodes + 3 and c.total_tokens == 10
+    dense = np.zeros((c.total_nodes, 10), np.float32)
+    for e in range(c.total_nodes):
+        k0, k1 = c.ent_ptr_host[e], c.ent_ptr_host[e + 1]
+        dense[e, c.tok_idx_host[k0:k1]] = c.w_host[k0:k1]
+    assert np.allclose(dense[0, :2], 0.5) and np.allclose(dense[1, [3, 5, 6]], [0.5, 0.25, 0.25])
+    assert np.array_equal(dense[2:], np.eye(10, dtype=np.float32)[:3])
+    # the transposed table (backward) lists, per token, the rows that read it
+    assert c.tok_ptr_host[-1] == c.tok_idx_host.size
+    rows_of_tok0 = c.ent_idx_host[c.tok_ptr_host[0]:c.tok_ptr_host[1]].tolist()
+    assert rows_of_tok0 == [0, 2]
+
+
+def test_synthetic_wire_documents_are_consistent():
+    from gcgcn_b200 import synthetic as S
+    for d in S.make_batch()[:4]:
+        w = S.make_wire(d)
+        assert w.n == d.n and w.length == d.L and 1 <= w.max_num <= 5
+        sl = w.slots
+        assert ((sl[:, 0] != sl[:, 1]) & (sl[:, 3] < sl[:, 4])).all()
+        # an edge exists iff it has a slot; slot numbers per edge start at 0 and are consecutive
+        edges = {tuple(e) for e in w.edges.tolist()}
+        assert edges == {(u, v) for u, v in sl[:, :2].tolist()}
+        for (u, v) in list(edges)[:10]:
+            js = sorted(sl[(sl[:, 0] == u) & (sl[:, 1] == v), 2].tolist())
+            assert js == list(range(len(js)))
+        # mentions lie inside the sentence of their slot (head mention starts in it)
+        assert ((sl[:, 5] >= sl[:, 3]) & (sl[:, 5] < sl[:, 4])).all()
