@@ -55,6 +55,8 @@ class EdgeTablesC(ctypes.Structure):
         ("slot_tok0", c_void_p), ("slot_len", c_void_p), ("slot_span", c_void_p), ("slot_att", c_void_p),
         ("slot_rowi", c_void_p), ("slot_rowj", c_void_p), ("pair_idx", c_void_p), ("pair_slot_ptr", c_void_p),
         ("pair_denom", c_void_p), ("node_ctr_ptr", c_void_p), ("node_ctr", c_void_p),
+        ("num_active_docs", c_int32), ("max_active_len", c_int32),
+        ("adoc_tok0", c_void_p), ("adoc_len", c_void_p), ("adoc_slot_lo", c_void_p), ("adoc_slot_hi", c_void_p),
     ]
 
 

@@ -118,6 +118,11 @@ struct EdgeTabs {
     const float* pair_denom;   // [pairs] float32(sent_num) + 1e-10  (G:206, 213)
     const int* node_ctr_ptr;   // [total_nodes + 1] contributions (slot * 2 + side) whose node embedding is this row
     const int* node_ctr;
+    int adocs, max_len;        // documents with at least one active slot; their longest first sentence
+    const int* adoc_tok0;      // [adocs] active-token index of the document's token 0
+    const int* adoc_len;       // [adocs] active tokens of the document
+    const int* adoc_slot_lo;   // [adocs] its active slots [lo, hi)
+    const int* adoc_slot_hi;
 };
 
 __global__ void __launch_bounds__(256)
@@ -256,6 +261,161 @@ word_pool_bwd_token_kernel(const EdgeTabs tb, const float* __restrict__ att, con
         }
     }
     if (lane < EF_BUCKETS) dT[static_cast<size_t>(a) * EF_BUCKETS + lane] = bin;
+}
+
+// ---- the same three kernels with one CTA per document and its first sentence in shared memory ----------------------
+// Every (slot, side) of a document walks the same <= 96 context rows and every token of it the same gradient rows: read
+// through L2 per warp (the kernels above) that is 30-40x redundant traffic and the L2 bandwidth becomes the limit
+// (4 GB per launch at the bench shard).  Here the context tile is loaded once per document, the gradient rows once per
+// chunk of 64 entries.  Used when the longest first sentence of the batch fits (WP_MAX_LEN tokens).
+constexpr int WP_MAX_LEN = 96, WP_ENT = 32;
+
+__global__ void __launch_bounds__(256)
+word_pool_fwd_doc_kernel(const EdgeTabs tb, const float* __restrict__ T, const float* __restrict__ ctx,
+                         float* __restrict__ att, float* __restrict__ cwa) {
+    extern __shared__ __align__(16) float wp_smem[];
+    const int d = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a0 = tb.adoc_tok0[d], L = tb.adoc_len[d], lo = tb.adoc_slot_lo[d], hi = tb.adoc_slot_hi[d];
+    float* ctx_s = wp_smem;                                   // [L][128]
+    float* T_s = ctx_s + L * D;                               // [L][21] word-score table rows of the document
+    for (int i = threadIdx.x; i < L * (D / 4); i += 256) st4(ctx_s + 4 * i, ld4(ctx + static_cast<size_t>(a0) * D + 4 * i));
+    for (int i = threadIdx.x; i < L * EF_BUCKETS; i += 256) T_s[i] = T[static_cast<size_t>(a0) * EF_BUCKETS + i];
+    __syncthreads();
+    for (int u = warp; u < 2 * (hi - lo); u += 8) {
+        const int s = lo + (u >> 1), side = u & 1;
+        const int len = tb.slot_len[s];
+        const int m0 = tb.slot_span[4 * s + 2 * side], m1 = tb.slot_span[4 * s + 2 * side + 1];
+        float* at = att + tb.slot_att[s] + side * len;
+        // (len <= L <= 96: at most three logits per lane, kept in registers)
+        float v[3];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int l = lane + 32 * r;
+            v[r] = l < len ? T_s[l * EF_BUCKETS + ef_pos_index(l, m0, m1, tb.dis_plus)] : -INFINITY;
+            mx = fmaxf(mx, v[r]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            v[r] = lane + 32 * r < len ? expf(v[r] - mx) : 0.f;
+            sum += v[r];
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            v[r] *= inv;
+            if (lane + 32 * r < len) at[lane + 32 * r] = v[r];
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < len; ++l) {
+            const float w = __shfl_sync(0xffffffffu, l < 32 ? v[0] : (l < 64 ? v[1] : v[2]), l & 31);
+            const float4 r = ld4(ctx_s + l * D + 4 * lane);
+            acc.x += w * r.x; acc.y += w * r.y; acc.z += w * r.z; acc.w += w * r.w;
+        }
+        st4(cwa + static_cast<size_t>(s) * 2 * D + side * D + 4 * lane, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+word_pool_bwd_doc_kernel(const EdgeTabs tb, const float* __restrict__ ctx, const float* __restrict__ att,
+                         const float* __restrict__ dcwa, float* __restrict__ dctx, float* __restrict__ dT) {
+    extern __shared__ __align__(16) float wp_smem[];
+    __shared__ int m_len[WP_ENT], m_off[WP_ENT], m_m0[WP_ENT], m_m1[WP_ENT];
+    const int d = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a0 = tb.adoc_tok0[d], L = tb.adoc_len[d], lo = tb.adoc_slot_lo[d], hi = tb.adoc_slot_hi[d];
+    const int LP = L + 1;                                     // row stride of the per-entry token arrays (bank spread)
+    float* ctx_s = wp_smem;                                   // [L][128]
+    float* d_s = ctx_s + L * D;                               // [WP_ENT][128] gradient rows of the current chunk
+    float* bin_s = d_s + WP_ENT * D;                          // [L][32] dT bins (column k = bucket k)
+    float* at_s = bin_s + L * 32;                             // [WP_ENT][LP] attention weights (0 past the sentence)
+    float* dl_s = at_s + WP_ENT * LP;                         // [WP_ENT][LP] d logits
+    for (int i = threadIdx.x; i < L * (D / 4); i += 256) st4(ctx_s + 4 * i, ld4(ctx + static_cast<size_t>(a0) * D + 4 * i));
+    for (int i = threadIdx.x; i < L * 32; i += 256) bin_s[i] = 0.f;
+    const int E = 2 * (hi - lo);
+    for (int e0 = 0; e0 < E; e0 += WP_ENT) {
+        const int en = min(WP_ENT, E - e0);
+        __syncthreads();                                      // previous chunk fully consumed (and the tile loads above done)
+        if (threadIdx.x < en) {
+            const int e = e0 + threadIdx.x, s = lo + (e >> 1), side = e & 1, len = tb.slot_len[s];
+            m_len[threadIdx.x] = len;
+            m_off[threadIdx.x] = tb.slot_att[s] + side * len;
+            m_m0[threadIdx.x] = tb.slot_span[4 * s + 2 * side];
+            m_m1[threadIdx.x] = tb.slot_span[4 * s + 2 * side + 1];
+        }
+        for (int i = threadIdx.x; i < en * (D / 4); i += 256) {
+            const int j = i / (D / 4), q = i % (D / 4), e = e0 + j;
+            st4(d_s + j * D + 4 * q, ld4(dcwa + static_cast<size_t>(lo + (e >> 1)) * 2 * D + (e & 1) * D + 4 * q));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < en * L; i += 256) {
+            const int j = i / L, l = i - j * L;
+            at_s[j * LP + l] = l < m_len[j] ? att[m_off[j] + l] : 0.f;
+        }
+        __syncthreads();
+        // (a) dlog[l] = att[l] (g[l] - sum_l att g), g[l] = dcwa . ctx[l]
+        for (int j = warp; j < en; j += 8) {
+            const int len = m_len[j];
+            const float4 dc = ld4(d_s + j * D + 4 * lane);
+            float dot = 0.f;
+            for (int l = 0; l < len; l += 4) {
+                float p[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) p[v] = l + v < len ? dot4(dc, ld4(ctx_s + (l + v) * D + 4 * lane)) : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) p[v] += __shfl_xor_sync(0xffffffffu, p[v], o);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (l + v < len) {
+                        if (lane == 0) dl_s[j * LP + l + v] = p[v];
+                        dot += at_s[j * LP + l + v] * p[v];
+                    }
+                }
+            }
+            __syncwarp();
+            for (int l = lane; l < L; l += 32) dl_s[j * LP + l] = l < len ? at_s[j * LP + l] * (dl_s[j * LP + l] - dot) : 0.f;
+        }
+        __syncthreads();
+        // (b) per token: dctx = sum over the entries covering it of att * dcwa;  dT bins of dlog by position bucket
+        for (int l = warp; l < L; l += 8) {
+            float w = 0.f, v = 0.f;
+            int k = -1;
+            if (lane < en && l < m_len[lane]) {
+                w = at_s[lane * LP + l];
+                v = dl_s[lane * LP + l];
+                k = ef_pos_index(l, m_m0[lane], m_m1[lane], tb.dis_plus);
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jj = 0; jj < en; ++jj) {                 // entries in order: a fixed summation order
+                const float wj = __shfl_sync(0xffffffffu, w, jj);
+                const float4 r = ld4(d_s + jj * D + 4 * lane);
+                acc.x += wj * r.x; acc.y += wj * r.y; acc.z += wj * r.z; acc.w += wj * r.w;
+            }
+            float bin = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < EF_BUCKETS; ++kk) {
+                const float t = warp_sum(k == kk ? v : 0.f);
+                if (lane == kk) bin = t;
+            }
+            float* o = dctx + static_cast<size_t>(a0 + l) * D + 4 * lane;
+            if (e0 > 0) {
+                const float4 old = ld4(o);
+                acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+            }
+            st4(o, acc);
+            bin_s[l * 32 + lane] += bin;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * EF_BUCKETS; i += 256) {
+        const int l = i / EF_BUCKETS, k = i - l * EF_BUCKETS;
+        dT[static_cast<size_t>(a0 + l) * EF_BUCKETS + k] = bin_s[l * 32 + k];
+    }
 }
 
 // ---- sentence-level attention over the active slots of one pair -----------------------------------------
@@ -412,6 +572,8 @@ static EdgeTabs make_tabs(const gcgcn_edge_tables* t) {
     tb.slot_rowi = t->slot_rowi; tb.slot_rowj = t->slot_rowj;
     tb.pair_idx = reinterpret_cast<const long long*>(t->pair_idx); tb.pair_slot_ptr = t->pair_slot_ptr;
     tb.pair_denom = t->pair_denom; tb.node_ctr_ptr = t->node_ctr_ptr; tb.node_ctr = t->node_ctr;
+    tb.adocs = t->num_active_docs; tb.max_len = t->max_active_len;
+    tb.adoc_tok0 = t->adoc_tok0; tb.adoc_len = t->adoc_len; tb.adoc_slot_lo = t->adoc_slot_lo; tb.adoc_slot_hi = t->adoc_slot_hi;
     return tb;
 }
 
@@ -436,9 +598,28 @@ int launch_word_table_bwd(const float* SF, const float* DF, const float* wa, con
     return launch_reduce_partials(partial, warps, WT_PARTIAL, out, WT_PARTIAL, nullptr, st);
 }
 
+static bool word_pool_doc_path(const gcgcn_edge_tables* t) {
+    return t->num_active_docs > 0 && t->max_active_len > 0 && t->max_active_len <= WP_MAX_LEN && t->adoc_tok0 != nullptr &&
+           t->adoc_len != nullptr && t->adoc_slot_lo != nullptr && t->adoc_slot_hi != nullptr;
+}
+template <typename K>
+static int word_pool_smem_attr(K kernel, size_t bytes, const char* name) {
+    // (the attribute is per device and the size varies with the batch: set it on every launch that needs it)
+    if (bytes > 48 * 1024)
+        return cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)), name);
+    return GCGCN_OK;
+}
+
 int launch_word_pool_fwd(const gcgcn_edge_tables* t, const float* T, const float* ctx, float* att, float* cwa,
                          cudaStream_t st) {
     if (t->num_slots <= 0) return GCGCN_OK;
+    if (word_pool_doc_path(t)) {
+        const size_t smem = static_cast<size_t>(t->max_active_len) * (D + EF_BUCKETS) * sizeof(float);
+        GCGCN_TRY(word_pool_smem_attr(word_pool_fwd_doc_kernel, smem, "word_pool_fwd smem"));
+        word_pool_fwd_doc_kernel<<<t->num_active_docs, 256, smem, st>>>(make_tabs(t), T, ctx, att, cwa);
+        GCGCN_CHECK_LAUNCH("word_pool_fwd<doc>");
+        return GCGCN_OK;
+    }
     word_pool_fwd_kernel<<<warps_grid(2LL * t->num_slots, 8), 256, 0, st>>>(make_tabs(t), T, ctx, att, cwa);
     GCGCN_CHECK_LAUNCH("word_pool_fwd");
     return GCGCN_OK;
@@ -448,6 +629,14 @@ int launch_word_pool_bwd(const gcgcn_edge_tables* t, const float* ctx, const flo
                          float* dctx, float* dT, cudaStream_t st) {
     if (t->num_slots <= 0 || t->num_tokens <= 0) return GCGCN_OK;
     const EdgeTabs tb = make_tabs(t);
+    if (word_pool_doc_path(t)) {
+        const size_t L = static_cast<size_t>(t->max_active_len);
+        const size_t smem = (L * (D + 32) + WP_ENT * D + 2 * WP_ENT * (L + 1)) * sizeof(float);
+        GCGCN_TRY(word_pool_smem_attr(word_pool_bwd_doc_kernel, smem, "word_pool_bwd smem"));
+        word_pool_bwd_doc_kernel<<<t->num_active_docs, 256, smem, st>>>(tb, ctx, att, dcwa, dctx, dT);
+        GCGCN_CHECK_LAUNCH("word_pool_bwd<doc>");
+        return GCGCN_OK;
+    }
     word_pool_bwd_logit_kernel<<<warps_grid(2LL * t->num_slots, 8), 256, 0, st>>>(tb, ctx, att, dcwa, dlog);
     GCGCN_CHECK_LAUNCH("word_pool_bwd_logit");
     word_pool_bwd_token_kernel<<<warps_grid(t->num_tokens, 8), 256, 0, st>>>(tb, att, dlog, dcwa, dctx, dT);

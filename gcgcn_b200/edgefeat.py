@@ -73,6 +73,11 @@ class EdgeTables:
             "slot_tok0": act_first[doc_of], "slot_len": r[:, 3], "slot_span": r[:, 4:8].reshape(-1),
             "slot_rowi": batch.node_ptr_host[doc_of] + r[:, 8], "slot_rowj": batch.node_ptr_host[doc_of] + r[:, 9],
         }
+        # documents with active slots (one CTA each in the word-attention kernels)
+        adocs = np.nonzero(lact > 0)[0]
+        host.update(adoc_tok0=act_first[adocs], adoc_len=lact[adocs], adoc_slot_lo=doc_slot_lo[adocs],
+                    adoc_slot_hi=doc_slot_hi[adocs])
+        self.num_active_docs, self.max_active_len = int(adocs.size), int(lact.max()) if len(docs) else 0
         att_off = np.zeros(A + 1, dtype=np.int64)
         np.cumsum(2 * r[:, 3], out=att_off[1:])
         host["slot_att"] = att_off[:-1]
@@ -118,7 +123,9 @@ class EdgeTables:
             self.num_tokens, self.num_slots, self.num_pairs, self.att_total, self.dis_plus, 0,
             ptr(d["tok_first"]), ptr(d["tok_slot_lo"]), ptr(d["tok_slot_hi"]), ptr(d["slot_tok0"]), ptr(d["slot_len"]),
             ptr(d["slot_span"]), ptr(d["slot_att"]), ptr(d["slot_rowi"]), ptr(d["slot_rowj"]), ptr(self.pair_idx),
-            ptr(d["pair_slot_ptr"]), ptr(self.pair_denom), ptr(d["node_ctr_ptr"]), ptr(d["node_ctr"]))
+            ptr(d["pair_slot_ptr"]), ptr(self.pair_denom), ptr(d["node_ctr_ptr"]), ptr(d["node_ctr"]),
+            self.num_active_docs, self.max_active_len, ptr(d["adoc_tok0"]), ptr(d["adoc_len"]), ptr(d["adoc_slot_lo"]),
+            ptr(d["adoc_slot_hi"]))
         return self
 
     @property

@@ -345,6 +345,13 @@ typedef struct gcgcn_edge_tables {
     const float* pair_denom;      /* [num_pairs]                                                           */
     const int32_t* node_ctr_ptr;  /* [total_nodes + 1] CSR: (slot * 2 + side) entries embedding this node row */
     const int32_t* node_ctr;
+    /* optional (may be 0 / NULL): the documents that have active slots, for the one-CTA-per-document word kernels   */
+    int32_t num_active_docs;
+    int32_t max_active_len;       /* longest run of active tokens of one document                              */
+    const int32_t* adoc_tok0;     /* [num_active_docs] active-token index of the document's token 0            */
+    const int32_t* adoc_len;      /* [num_active_docs] its active tokens                                       */
+    const int32_t* adoc_slot_lo;  /* [num_active_docs] its active slots [lo, hi)                               */
+    const int32_t* adoc_slot_hi;
 } gcgcn_edge_tables;
 /* scratch any entry point below needs */
 size_t gcgcn_edgefeat_ws_bytes(int32_t num_tokens, int32_t att_total, int32_t num_slots, int32_t num_pairs,
