@@ -21,7 +21,7 @@ from .functional import D, LinearFn, _cuda, _p, _stream, gemm, workspace
 CHUNK_PAIRS = 8192          # 8192 pairs x 97 x 128 floats = 407 MB of Y per chunk
 FUSED_BACKWARD = True       # False: the backward materialises Y / dY chunk by chunk (test hook; also the path below 8192 pairs)
 FUSED_MIN_PAIRS = 8192      # the generated-operand weight-gradient GEMM needs K >= 8192
-FUSED_CHUNK_PAIRS = 1 << 19  # pairs per fused backward call (1 KB of pre-split h per pair in the workspace)
+FUSED_CHUNK_PAIRS = 1 << 18  # pairs per fused backward call (workspace: 1 KB of pre-split h + 1.6 KB of split-K partials per pair)
 FUSED_FORWARD = True        # False: the forward materialises Y = h W' chunk by chunk like the backward does (test hook)
 
 

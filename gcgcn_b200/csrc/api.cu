@@ -1115,7 +1115,10 @@ int gcgcn_bilinear_fwd(const float* h, const float* t, const float* Wm, const fl
 
 size_t gcgcn_bilinear_bwd_ws_bytes(int32_t rows, int32_t relations) {
     const size_t r = static_cast<size_t>(relations < 0 ? 0 : relations);
-    return align256(r * 4 * 33024) + align256(GEMM_WS_BYTES) + align256(gemm_presplit_bytes(rows < 0 ? 0 : rows)) + 4096;
+    // pre-split W' blobs, one [128, relations*128] partial per 4096-row range of the weight-gradient GEMM, pre-split h
+    const size_t ranges = (static_cast<size_t>(rows < 0 ? 0 : rows) + 4095) / 4096;
+    return align256(r * 4 * 33024) + align256(std::max<size_t>(GEMM_WS_BYTES, ranges * D * r * D * sizeof(float))) +
+           align256(gemm_presplit_bytes(rows < 0 ? 0 : rows)) + 4096;
 }
 
 int gcgcn_bilinear_bwd(const float* h, const float* t, const float* Wm, const float* Wm2, const float* dout, int32_t rows,
@@ -1131,15 +1134,17 @@ int gcgcn_bilinear_bwd(const float* h, const float* t, const float* Wm, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar(ws, ws_bytes);
     const size_t blob_bytes = static_cast<size_t>(relations) * 4 * 33024, pre_bytes = gemm_presplit_bytes(rows);
+    const size_t ranges = (static_cast<size_t>(rows) + 4095) / 4096;
+    const size_t gws_bytes = std::max<size_t>(GEMM_WS_BYTES, ranges * D * static_cast<size_t>(relations) * D * sizeof(float));
     uint8_t* blobs = ar.take<uint8_t>(blob_bytes);
-    uint8_t* gws = ar.take<uint8_t>(GEMM_WS_BYTES);
+    uint8_t* gws = ar.take<uint8_t>(gws_bytes);
     uint8_t* pre = ar.take<uint8_t>(pre_bytes);
     if (blobs == nullptr || gws == nullptr || pre == nullptr)
         return fail(GCGCN_ERR_WORKSPACE, "bilinear_bwd: workspace too small");
     const int N = relations * D;
     GCGCN_TRY(launch_gemm_rowop(2, rows, N, D, h, D, Wm, N, dout, dt, relations, blobs, blob_bytes, st));
     GCGCN_TRY(launch_gemm_rowop(2, rows, N, D, t, D, Wm2, N, dout, dh, relations, blobs, blob_bytes, st));
-    return launch_gemm_wgrad_scaled(D, relations, rows, h, D, t, dout, relations, beta, dWm, N, gws, GEMM_WS_BYTES, st, pre,
+    return launch_gemm_wgrad_scaled(D, relations, rows, h, D, t, dout, relations, beta, dWm, N, gws, gws_bytes, st, pre,
                                     pre_bytes);
 }
 

@@ -1055,9 +1055,18 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     if (seq) {
         a.k_per_split = 4096;
         a.k_splits = splits = ceil_div(K, a.k_per_split);
-        a.partial = nullptr;
-        a.seq_k = 1;
-        grid = std::min(sms, tiles);
+        const size_t per = static_cast<size_t>(M) * N * sizeof(float);
+        if (splits > 1 && ws != nullptr && per * splits <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+            // room for one partial per range: plain split-K over the ranges, every CTA takes (tile, range) items
+            // round-robin (all SMs busy), the fp32 reduction adds them up
+            a.partial = static_cast<float*>(ws);
+            a.seq_k = 0;
+            grid = std::min(sms, tiles * splits);
+        } else {
+            a.partial = nullptr;
+            a.seq_k = splits > 1 ? 1 : 0;
+            grid = std::min(sms, tiles);
+        }
     }
     a.Bpre = nullptr;
     a.kblocks = ceil_div(K, TC_BK);
@@ -1077,7 +1086,8 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     // (worth it only when several column tiles re-use the blobs: a 128-wide output reads the operand once anyway)
     const bool apre = gemm_tc_bpre_enabled() && !bpre && batch == 1 && ta && !tb && K >= 8192 && M <= 2 * TC_BM &&
                       a.tiles_n >= 2 &&
-                      (seq ? tiles <= sms : tiles * splits <= sms) && pre_ws != nullptr && ablob_total <= pre_bytes &&
+                      (seq ? (a.partial != nullptr || tiles <= sms) : tiles * splits <= sms) && pre_ws != nullptr &&
+                      ablob_total <= pre_bytes &&
                       (reinterpret_cast<uintptr_t>(pre_ws) & 15) == 0;
     if (bscale != nullptr && !apre)
         return fail(GCGCN_ERR_UNSUPPORTED, "gemm: the generated-operand product needs the pre-split weight-gradient path "
@@ -1133,7 +1143,7 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
                             : apre ? "gemm_tc_tn<presplit A>"
                             : bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
                             : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
-    if (splits > 1 && !seq)
+    if (splits > 1 && a.partial != nullptr)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));
     *taken = 1;
     return GCGCN_OK;
