@@ -1083,9 +1083,11 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     // weight gradients: short M (the [rows, 128] operand, transposed), K = every row, one tile per CTA after split-K
     a.Apre = nullptr;
     const size_t ablob_total = static_cast<size_t>(a.tiles_m) * a.kblocks * TC_B_BLOB_BYTES;
-    // (worth it only when several column tiles re-use the blobs: a 128-wide output reads the operand once anyway)
+    // (worth it only when several column tiles re-use the blobs: a 128-wide output reads the operand once anyway;
+    //  GCGCN_APRE_MIN_TILES=1 switches it on for the one-tile weight gradients too -- measured)
+    static const int apre_min_tiles = getenv("GCGCN_APRE_MIN_TILES") != nullptr ? atoi(getenv("GCGCN_APRE_MIN_TILES")) : 2;
     const bool apre = gemm_tc_bpre_enabled() && !bpre && batch == 1 && ta && !tb && K >= 8192 && M <= 2 * TC_BM &&
-                      a.tiles_n >= 2 &&
+                      a.tiles_n >= apre_min_tiles &&
                       (seq ? (a.partial != nullptr || tiles <= sms) : tiles * splits <= sms) && pre_ws != nullptr &&
                       ablob_total <= pre_bytes &&
                       (reinterpret_cast<uintptr_t>(pre_ws) & 15) == 0;
