@@ -43,6 +43,7 @@ class Batch(ctypes.Structure):
         ("max_nodes", c_int32), ("reserved", c_int32),
         ("node_ptr", c_void_p), ("pair_ptr", c_void_p), ("row_doc", c_void_p),
         ("doc_order", c_void_p), ("class_end", c_int32 * 4),
+        ("tile_doc", c_void_p), ("num_tiles", c_int32), ("tile_rows", c_int32),
     ]
 
 
@@ -112,6 +113,7 @@ SIGNATURES = {
     "gcgcn_version": (c_char_p, []),
     "gcgcn_last_error": (c_char_p, []),
     "gcgcn_launch_count": (c_uint64, []),
+    "gcgcn_set_tile_blocks": (c_int32, [c_int32]),
     "gcgcn_device_info": (c_int32, [POINTER(c_int32)] * 3),
     "gcgcn_timing_begin": (c_int32, [_P]),
     "gcgcn_timing_end": (c_int32, [_P, c_char_p, c_size_t]),
@@ -215,6 +217,11 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().gcgcn_launch_count())
+
+
+def set_tile_blocks(enable: bool) -> bool:
+    """Switch the packed-tile tensor-core path of the MAGGC block on or off; returns the previous setting."""
+    return bool(load().gcgcn_set_tile_blocks(1 if enable else 0))
 
 
 def timing_begin(stream: int) -> None:

@@ -22,6 +22,28 @@ MAX_LENGTH = 512   # config/Config.py:67
 DIS_PLUS = 10      # config/Config.py:119
 
 
+TILE_ROWS = 96          # GCGCN_TILE_ROWS of include/gcgcn_b200.h
+
+
+def pack_tiles(sizes: np.ndarray) -> np.ndarray:
+    """Greedy packing of consecutive documents into tiles of at most TILE_ROWS node rows: returns ``tile_doc``
+    [num_tiles + 1] (int32), tile t = documents [tile_doc[t], tile_doc[t+1]).  Empty (size 1, no tiles) when there
+    are no documents or one of them alone exceeds a tile."""
+    ns = np.asarray(sizes, dtype=np.int64)
+    if ns.size == 0 or int(ns.max()) > TILE_ROWS:
+        return np.zeros(1, dtype=np.int32)
+    # vectorised greedy: a tile starting at document s ends before the first document whose cumulative row count
+    # from s exceeds TILE_ROWS -- found with searchsorted on the prefix sums
+    ptr = np.zeros(ns.size + 1, dtype=np.int64)
+    np.cumsum(ns, out=ptr[1:])
+    starts = [0]
+    s = 0
+    while s < ns.size:
+        s = int(np.searchsorted(ptr, ptr[s] + TILE_ROWS, side="right")) - 1
+        starts.append(s)
+    return np.asarray(starts, dtype=np.int32)
+
+
 class RaggedBatch:
     """Offsets of B document graphs laid out back to back (include/gcgcn_b200.h)."""
 
@@ -51,12 +73,17 @@ class RaggedBatch:
         self.doc_order_host = np.argsort(-ns, kind="stable").astype(np.int32)
         self.class_end_host = [int((ns > t).sum()) for t in (48, 32, 16, 0)]
         self.doc_order = torch.from_numpy(self.doc_order_host).to(self.device)
+        # packing hint: consecutive documents in tiles of <= 128 node rows (tensor-core block kernels)
+        self.tile_doc_host = pack_tiles(ns)
+        self.num_tiles = max(int(self.tile_doc_host.size) - 1, 0)
+        self.tile_doc = torch.from_numpy(self.tile_doc_host).to(self.device)
         self.c_struct = _lib.Batch(
             self.num_docs, self.total_nodes, self.total_pairs, self.max_nodes, 0,
             self.node_ptr.data_ptr(), self.pair_ptr.data_ptr(),
             self.row_doc.data_ptr() if self.total_nodes else None,
             self.doc_order.data_ptr() if self.num_docs else None,
-            (ctypes.c_int32 * 4)(*self.class_end_host))
+            (ctypes.c_int32 * 4)(*self.class_end_host),
+            self.tile_doc.data_ptr() if self.num_tiles else None, self.num_tiles, TILE_ROWS)
 
     @property
     def ref(self):

@@ -34,6 +34,7 @@ int launch_stack_bwd(const gcgcn_batch* bt, int heads, int layers, int slab, int
                      const float* G, const float* Winner, const float* keep, const float* dF, float* dZ,
                      float* dE, float* dA, float* frag_ws, cudaStream_t st);
 bool block_kernels_usable(const gcgcn_batch* bt, int heads, int layers, int slab, bool mha);
+bool set_tile_blocks(bool on);
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner, const float* x, float* G, float* F,
                      float* frag_ws, const BlockDrop& drop, cudaStream_t st);
@@ -291,6 +292,7 @@ extern "C" {
 const char* gcgcn_version(void) { return "gcgcn_b200 0.1.0 (sm_100a)"; }
 const char* gcgcn_last_error(void) { return error_buffer(); }
 uint64_t gcgcn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int32_t gcgcn_set_tile_blocks(int32_t enable) { return gcgcn::set_tile_blocks(enable != 0) ? 1 : 0; }
 
 int gcgcn_device_info(int32_t* sms, int32_t* major, int32_t* minor) {
     int dev = 0;

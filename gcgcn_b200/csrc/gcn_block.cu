@@ -841,10 +841,20 @@ static int launch_winner_frag(const float* Winner, int heads, int layers, float*
     return GCGCN_OK;
 }
 
+// gcn_tile.cu: the same block on packed 128-row tcgen05 tiles (MHA attention, two sub-layers, head width 16, eval mode)
+bool tile_blocks_enabled();
+size_t tile_wblob_bytes(int heads);
+int launch_tile_fwd(const gcgcn_batch* bt, int heads, int layers, const float* q, float* P, float* Z, const float* E,
+                    const float* Winner_rowmajor, const float* x, float* G, float* F, void* wblob_ws, cudaStream_t st);
+
 int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* A, const float* q, float* P,
                      float* Z, const float* E, const float* Winner_rowmajor, const float* x, float* G, float* F,
                      float* frag_ws, const BlockDrop& drop, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
+    if (A == nullptr && layers == 2 && heads == 8 && drop.thr_att == 0u && drop.thr_gcn == 0u && bt->tile_doc != nullptr &&
+        bt->num_tiles > 0 && bt->row_doc != nullptr && frag_ws != nullptr &&
+        tile_wblob_bytes(heads) <= block_frag_floats(heads, layers) * sizeof(float) && tile_blocks_enabled())
+        return launch_tile_fwd(bt, heads, layers, q, P, Z, E, Winner_rowmajor, x, G, F, frag_ws, st);
     GCGCN_TRY(launch_winner_frag(Winner_rowmajor, heads, layers, frag_ws, st));
     const float* Winner = frag_ws;                      // forward-ordered half
     const int gd = D / layers;

@@ -51,6 +51,8 @@ extern "C" {
 #define GCGCN_STACK_RESIDUAL 2   /* F_h = cat_l drop(g_l) + x  (G:75-76, G:112-113)             */
 #define GCGCN_STACK_LINEAR 4     /* y = Linear(cat_h F_h)      (G:78, G:117-118)                */
 
+#define GCGCN_TILE_ROWS 96
+
 typedef struct gcgcn_batch {
     int32_t num_docs;        /* B                                                        */
     int32_t total_nodes;     /* sum_b n_b                                                */
@@ -65,6 +67,13 @@ typedef struct gcgcn_batch {
      * grid per size class with right-sized shared memory instead of sizing every CTA for max_nodes. */
     const int32_t* doc_order; /* [B] device                                              */
     int32_t class_end[4];     /* cumulative counts in doc_order: n>48, n>32, n>16, n>0   */
+    /* optional packing hint (may be NULL / 0): consecutive documents grouped into tiles of at most tile_rows
+     * (= GCGCN_TILE_ROWS) node rows, tile t = documents [tile_doc[t], tile_doc[t+1]).  Lets the MAGGC block run on
+     * packed tensor-core tiles (csrc/gcn_tile.cu) instead of one CTA per document; absent (or a document with more
+     * entities than a tile holds) -> the per-document kernels. */
+    const int32_t* tile_doc;  /* [num_tiles+1] device                                    */
+    int32_t num_tiles;
+    int32_t tile_rows;
 } gcgcn_batch;
 
 /* ---- train-mode dropout of the block-level entry points ------------------------------------------
@@ -88,6 +97,10 @@ const char* gcgcn_version(void);
 const char* gcgcn_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t gcgcn_launch_count(void);
+/* Packed-tile tensor-core path of the MAGGC block (csrc/gcn_tile.cu): 1 = use it where its preconditions hold,
+ * 0 = per-document kernels everywhere.  Returns the previous setting; the initial one comes from the environment
+ * variable GCGCN_TILE_BLOCKS.  Both paths compute the same function (fp32 rounding apart). */
+int32_t gcgcn_set_tile_blocks(int32_t enable);
 /* fills SM count and compute capability of the current device */
 int gcgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* per-kernel timing for bench.py: begin() starts recording one CUDA event after every launch on

@@ -1,0 +1,84 @@
+"""A/B check of the packed-tile tensor-core MAGGC block (csrc/gcn_tile.cu) against the per-document kernels on the same
+inputs, then kernel timings at bench size.  Run on a GPU box:  python scripts/check_tile_blocks.py [--time]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from gpu_common import device_blocks, run_blocks  # noqa: E402
+from gcgcn_b200 import _lib, synthetic as S  # noqa: E402
+
+
+def compare(sizes, tag):
+    gb, _ = device_blocks(2, 8)
+    docs = [S.make_doc(900 + i, n=n, L=32) for i, n in enumerate(sizes)]
+    _lib.set_tile_blocks(False)
+    ref = run_blocks(gb, docs)
+    _lib.set_tile_blocks(True)
+    before = _lib.launch_count()
+    out = run_blocks(gb, docs)
+    launches = _lib.launch_count() - before
+    _lib.set_tile_blocks(False)
+    worst = 0.0
+    for k in ("y1", "y2", "dx0", "de0", "de1"):
+        d = float((out[k] - ref[k]).abs().max()) if ref[k].numel() else 0.0
+        worst = max(worst, d)
+        print(f"  {tag} {k}: max|diff| {d:.3e}  (max|ref| {float(ref[k].abs().max()) if ref[k].numel() else 0:.3e})")
+    for h in range(8):
+        worst = max(worst, float((out["a1"][h] - ref["a1"][h]).abs().max()))
+    print(f"  {tag} a1: max|diff| {float((out['a1'] - ref['a1']).abs().max()):.3e}")
+    if os.environ.get("TILE_DEBUG"):
+        bt = ref["bt"]
+        for k in ("de1", "dx0"):
+            parts_o = bt.split_pairs(out[k]) if k == "de1" else bt.split_nodes(out[k])
+            parts_r = bt.split_pairs(ref[k]) if k == "de1" else bt.split_nodes(ref[k])
+            print(f"  {tag} {k} per doc:", " ".join(f"{float((o - r_).abs().max()):.1e}" for o, r_ in zip(parts_o, parts_r)))
+    for k, v in ref["dparams"].items():
+        if v is None:
+            continue
+        d = float((out["dparams"][k] - v).abs().max())
+        scale = float(v.abs().max())
+        if d > 1e-4 * max(scale, 1.0):
+            print(f"  {tag} d{k}: max|diff| {d:.3e} (max {scale:.3e})  <-- large")
+        worst = max(worst, d / max(scale, 1.0))
+    print(f"{tag}: worst {worst:.3e}, {launches} launches")
+    return worst
+
+
+def main():
+    torch.manual_seed(0)
+    ok = True
+    for sizes, tag in (([5], "one small"), ([64, 64], "two big"), ([48, 48, 32, 32, 32, 1, 95], "full tiles"), ([1, 2, 3, 42, 1, 7, 33, 2, 64, 5], "ragged"),
+                       ([19] * 40, "many"), ([3, 17, 64, 63, 2, 61, 6], "straddling")):
+        ok &= compare(sizes, tag) <= 2e-5
+    print("PARITY", "OK" if ok else "FAILED")
+    if "--time" in sys.argv:
+        from gcgcn_b200.batch import RaggedBatch
+        from gcgcn_b200.modules import GraphBlocks
+        dev = torch.device("cuda:0")
+        sizes = S.shard_doc_sizes(6144)
+        bt = RaggedBatch(sizes, dev)
+        gb = GraphBlocks(2, 8).to(dev).eval()
+        x0 = torch.randn(bt.total_nodes, 128, device=dev, requires_grad=True)
+        e0 = torch.randn(bt.total_pairs, 128, device=dev, requires_grad=True)
+        e1 = torch.randn(bt.total_pairs, 128, device=dev, requires_grad=True)
+        st = torch.cuda.current_stream().cuda_stream
+        for on in (False, True, False, True):
+            _lib.set_tile_blocks(on)
+            for rep in range(3):
+                if rep == 2:
+                    _lib.timing_begin(st)
+                out = gb(x0, e0, e1, bt)
+                (out["y1"].sum() + out["y2"].sum()).backward()
+            t = _lib.timing_end(st)
+            tot = sum(v[1] for v in t.values())
+            pick = {k: round(v[1], 3) for k, v in t.items() if "block" in k or "tile" in k}
+            print(f"tile={on}: step kernels {tot:.3f} ms  {pick}")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
