@@ -258,33 +258,42 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        // Three passes over the row's 48 scores, 16 at a time straight from tensor memory (re-reading TMEM and taking
+        // the exponential twice is cheaper than keeping 48 values live: at 128 registers per thread they spilled).
         const int jb = half * TL_HALF;
-        uint32_t s[TL_HALF];
+        const uint32_t srow = lane_addr + TL_COL_PHI + jb;
         float m = -INFINITY;
         if (rowthread) {
-            tmem_ld16(lane_addr + TL_COL_PHI + jb, s);
-            tmem_ld16(lane_addr + TL_COL_PHI + jb + 16, s + 16);
-            tmem_ld16(lane_addr + TL_COL_PHI + jb + 32, s + 32);
-            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < TL_HALF; ++c) {
-                const int j = jb + c;
-                const float v = (j >= lo_col && j < hi_col) ? __uint_as_float(s[c]) * a.scale : -INFINITY;
-                s[c] = __float_as_uint(v);
-                m = fmaxf(m, v);
+            for (int c0 = 0; c0 < TL_HALF; c0 += 16) {
+                uint32_t s[16];
+                tmem_ld16(srow + c0, s);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int j = jb + c0 + c;
+                    if (j >= lo_col && j < hi_col) m = fmaxf(m, __uint_as_float(s[c]));
+                }
             }
             xch[half * 128 + r] = m;
         }
         __syncthreads();
         float zsum = 0.f;
+        float mk = 0.f;                // max * scale * log2(e): e = exp2(s * k - mk)
+        const float kexp = a.scale * 1.4426950408889634f;
         if (rowthread) {
             m = fmaxf(xch[r], xch[128 + r]);
+            mk = m * kexp;
 #pragma unroll
-            for (int c = 0; c < TL_HALF; ++c) {
-                const float v = __uint_as_float(s[c]);
-                const float e = v == -INFINITY ? 0.f : __expf(v - m);     // (also covers rows with no columns: m = -inf)
-                s[c] = __float_as_uint(e);
-                zsum += e;
+            for (int c0 = 0; c0 < TL_HALF; c0 += 16) {
+                uint32_t s[16];
+                tmem_ld16(srow + c0, s);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int j = jb + c0 + c;
+                    if (j >= lo_col && j < hi_col) zsum += exp2f(fmaf(__uint_as_float(s[c]), kexp, -mk));
+                }
             }
             xch[256 + half * 128 + r] = zsum;
         }
@@ -295,19 +304,24 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
             float psum = 0.f;
 #pragma unroll
             for (int c0 = 0; c0 < TL_HALF; c0 += 16) {
-                uint32_t hi[16], lo[16];
+                uint32_t s[16], lo[16];
+                tmem_ld16(srow + c0, s);
+                tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int j = jb + c0 + c;
-                    const float p = __uint_as_float(s[c0 + c]) * inv;
-                    if (j >= lo_col && j < hi_col) a.P[prow + j] = p;
+                    float p = 0.f;
+                    if (j >= lo_col && j < hi_col) {
+                        p = exp2f(fmaf(__uint_as_float(s[c]), kexp, -mk)) * inv;
+                        a.P[prow + j] = p;
+                    }
                     psum += p;
                     float ph, pl;
                     tl_split(p, ph, pl);
-                    hi[c] = __float_as_uint(ph);
+                    s[c] = __float_as_uint(ph);
                     lo[c] = __float_as_uint(pl);
                 }
-                tmem_st16(lane_addr + TL_COL_PHI + jb + c0, hi);
+                tmem_st16(srow + c0, s);                                   // P hi over S, in place
                 tmem_st16(lane_addr + TL_COL_PLO + jb + c0, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
 static std::atomic<int>& tile_flag() {
     static std::atomic<int> on{[] {
         const char* e = std::getenv("GCGCN_TILE_BLOCKS");
-        return (e != nullptr && e[0] == '1') ? 1 : 0;
+        return (e != nullptr && e[0] == '0') ? 0 : 1;         // on unless GCGCN_TILE_BLOCKS=0
     }()};
     return on;
 }

@@ -98,8 +98,8 @@ const char* gcgcn_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t gcgcn_launch_count(void);
 /* Packed-tile tensor-core path of the MAGGC block (csrc/gcn_tile.cu): 1 = use it where its preconditions hold,
- * 0 = per-document kernels everywhere.  Returns the previous setting; the initial one comes from the environment
- * variable GCGCN_TILE_BLOCKS.  Both paths compute the same function (fp32 rounding apart). */
+ * 0 = per-document kernels everywhere.  Returns the previous setting; initially on unless the environment variable
+ * GCGCN_TILE_BLOCKS is 0.  Both paths compute the same function (fp32 rounding apart). */
 int32_t gcgcn_set_tile_blocks(int32_t enable);
 /* fills SM count and compute capability of the current device */
 int gcgcn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

@@ -178,3 +178,26 @@ def test_synthetic_wire_documents_are_consistent():
             assert js == list(range(len(js)))
         # mentions lie inside the sentence of their slot (head mention starts in it)
         assert ((sl[:, 5] >= sl[:, 3]) & (sl[:, 5] < sl[:, 4])).all()
+
+
+def test_pack_tiles_is_a_greedy_partition_of_consecutive_documents():
+    """gcgcn_batch.tile_doc (the packed-tile MAGGC kernel's work list): every tile holds consecutive documents with
+    at most TILE_ROWS rows in total, no tile could take the next document, and the hint is off when one document alone
+    is too large or the batch is empty."""
+    from gcgcn_b200.batch import TILE_ROWS, pack_tiles
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        ns = rng.integers(0, 65, size=int(rng.integers(1, 50)))
+        td = pack_tiles(ns)
+        assert td.dtype == np.int32 and td[0] == 0 and td[-1] == ns.size
+        for a, b in zip(td[:-1], td[1:]):
+            assert b > a and ns[a:b].sum() <= TILE_ROWS
+            if b < ns.size:
+                assert ns[a:b + 1].sum() > TILE_ROWS
+    assert pack_tiles(np.array([TILE_ROWS, 1, TILE_ROWS - 1, 0, 0, 3])).tolist() == [0, 1, 5, 6]
+    assert pack_tiles(np.array([0, 0])).tolist() == [0, 2]
+    assert pack_tiles(np.array([TILE_ROWS + 1, 2])).tolist() == [0]
+    assert pack_tiles(np.array([], dtype=np.int64)).tolist() == [0]
+    bt = RaggedBatch([5, 92, 7], "cpu")
+    assert bt.num_tiles == 3 and bt.c_struct.num_tiles == 3 and bt.c_struct.tile_rows == TILE_ROWS
+    assert RaggedBatch([200], "cpu").num_tiles == 0
