@@ -182,10 +182,33 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
     const int items = a.num_tiles * a.heads;
     uint32_t phase = 0;
     int cur_h = -1;
+    // The first phase's operands are fetched one item ahead (tile geometry at the top of the previous item, q rows
+    // before its last wait), so an item starts with its data in registers instead of three dependent round trips to
+    // L2/HBM.  (Fetching the Zx_0 tile ahead as well was measured slower: 24 more live registers spill.)
+    int n_row0 = 0, n_rows = 0;
+    float4 n_q0 = make_float4(0.f, 0.f, 0.f, 0.f), n_q1 = n_q0;
+    auto fetch_geometry = [&](int item) {
+        if (item < items) {
+            const int tile = item % a.num_tiles;
+            const int d0 = a.tile_doc[tile], d1 = a.tile_doc[tile + 1];
+            n_row0 = a.node_ptr[d0];
+            n_rows = a.node_ptr[d1] - n_row0;
+        }
+    };
+    auto fetch_operands = [&](int item) {
+        const int h = item / a.num_tiles;
+        n_q0 = n_q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < items && rowthread && r < n_rows) {
+            const float* qp = a.q + static_cast<size_t>(n_row0 + r) * D + h * TL_DH + half * 8;
+            n_q0 = ld4g(qp);
+            n_q1 = ld4g(qp + 4);
+        }
+    };
+    fetch_geometry(blockIdx.x);
+    fetch_operands(blockIdx.x);
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int h = item / a.num_tiles, tile = item - h * a.num_tiles;
-        const int d0 = a.tile_doc[tile], d1 = a.tile_doc[tile + 1];
-        const int row0 = a.node_ptr[d0], rows = a.node_ptr[d1] - row0;
+        const int h = item / a.num_tiles;
+        const int row0 = n_row0, rows = n_rows;
         const bool rv = r < rows;                          // rows <= TL_ROWS
         // coalesced mapping: element offset of (row crow + 16 i, chunk c16) in the [rows, H*128] slabs / in x
         const size_t cslab = static_cast<size_t>(row0 + crow) * HD + h * D + c16 * 4;      // + i * 16 * HD + l * 64
@@ -193,20 +216,16 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
 
         // ---- stage q_h (A and B operand of S) and, when the head changes, its dense-connect weights ----
         if (rowthread) {
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, hi, lo;
-            if (rv) {
-                const float* qp = a.q + static_cast<size_t>(row0 + r) * D + h * TL_DH + half * 8;
-                v0 = ld4g(qp);
-                v1 = ld4g(qp + 4);
-            }
+            float4 hi, lo;
             const uint32_t dst = (2 * half) * TL_PLANE_M + r * 16;
-            tl_split4(v0, hi, lo);
+            tl_split4(n_q0, hi, lo);
             sts4(s_qhi + dst, hi);
             sts4(s_qlo + dst, lo);
-            tl_split4(v1, hi, lo);
+            tl_split4(n_q1, hi, lo);
             sts4(s_qhi + dst + TL_PLANE_M, hi);
             sts4(s_qlo + dst + TL_PLANE_M, lo);
         }
+        fetch_geometry(item + gridDim.x);
         if (h != cur_h) {
             const float4* src = reinterpret_cast<const float4*>(a.Wblob + static_cast<size_t>(h) * TL_WBLOB_BYTES);
             for (int i = tid; i < TL_WBLOB_BYTES / 16; i += TL_THREADS) sts4(sbase + TL_OFF_WHI + i * 16, __ldg(src + i));
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
             }
             umma_commit(bar);
         }
-        // ---- meanwhile: Zx_0 -> swizzled MN-major planes (coalesced), and this row's document range ----
+        // ---- meanwhile: the Zx_0 tile -> swizzled MN-major planes, and this row's document range ----
         {
             float4 z[6];
 #pragma unroll
@@ -355,6 +374,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
                 e4[i] = ok ? ld4g(a.E + cslab + static_cast<size_t>(i) * 16 * HD + l * TL_GD) : make_float4(0.f, 0.f, 0.f, 0.f);
                 x4[i] = ok ? ld4g(a.x + cx + static_cast<size_t>(i) * 16 * D + l * TL_GD) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (l == 1) fetch_operands(item + gridDim.x);      // the next item's q rows
             mbar_wait(bar, phase);
             phase ^= 1;
             tc_fence_after();
