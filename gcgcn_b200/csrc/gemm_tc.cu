@@ -162,6 +162,62 @@ __device__ __forceinline__ void store_operand(float* hi, float* lo, int tid, con
     }
 }
 
+// ---- MN-major operand tiles (both operands of a weight gradient C = A^T B are stored [K][MN], MN contiguous) -------
+// The tensor core reads 32-bit operands in MN-major form through exactly one shared-memory layout, "128-byte swizzle
+// with 32-byte base": column blocks of [k rows][32 mn] fp32, rows 128 B apart, the 32-byte chunk index XORed with
+// (k % 4).  That is the operand's own row-major layout up to the XOR, so a K block is moved by coalesced 16-byte
+// loads and 16-byte stores with no transposition in registers (the K-major route above pays 4-byte loads for it).
+// One [32 k][128 mn] part = 4 column blocks of 4096 B; the four parts of a stage sit at multiples of 16 KB.
+constexpr int TC_MN_BLOCK_BYTES = TC_BK * 128;              // one [32 k][32 mn] column block
+constexpr int TC_MN_PART_BYTES = 4 * TC_MN_BLOCK_BYTES;     // 16 KB
+static_assert(4 * TC_MN_PART_BYTES <= TC_STAGE_BYTES, "MN-major parts fit a stage");
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = (smem_addr >> 4) & 0x3FFFu;
+    d |= static_cast<uint64_t>(TC_MN_BLOCK_BYTES >> 4) << 16;   // leading byte offset: the next 32-wide column block
+    d |= static_cast<uint64_t>(512 >> 4) << 32;                 // stride byte offset: the next atom of 4 k rows
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(1) << 61;                        // SWIZZLE_128B_BASE32B
+    return d;
+}
+constexpr uint32_t TC_IDESC_MN = TC_IDESC | (1u << 15) | (1u << 16);   // A and B MN-major
+// thread -> (k row, 16-byte chunk) of its i-th float4: warp w of the group owns column block w, a warp instruction
+// covers 4 k rows x 128 B (four whole lines in HBM, 512 contiguous bytes in shared memory)
+__device__ __forceinline__ void fetch_operand_mn(const float* __restrict__ src, int ld, int mn0, int mn_total, int k0, int kend,
+                                                 bool vec_ok, int tid, float4 (&v)[8]) {
+    const int w = tid >> 5, l = tid & 31;
+    const int mn = mn0 + 32 * w + 4 * (l & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = k0 + 4 * i + (l >> 3);
+        const float* p = src + static_cast<size_t>(k) * ld + mn;
+        if (k < kend && vec_ok && mn + 4 <= mn_total) {
+            v[i] = *reinterpret_cast<const float4*>(p);
+        } else {
+            float t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] = (k < kend && mn + q < mn_total) ? p[q] : 0.f;
+            v[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    }
+}
+__device__ __forceinline__ void store_operand_mn(uint8_t* hi, uint8_t* lo, int tid, const float4 (&v)[8]) {
+    const int w = tid >> 5, l = tid & 31, c = l & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int krow = 4 * i + (l >> 3);
+        const int off = w * TC_MN_BLOCK_BYTES + krow * 128 + (((((c >> 1) ^ (krow & 3)) << 1) | (c & 1)) << 4);
+        const float4 a = v[i];
+        float4 h, lw;
+        h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u);
+        lw.x = a.x - h.x; lw.y = a.y - h.y; lw.z = a.z - h.z; lw.w = a.w - h.w;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = lw;
+    }
+}
+
 // Epilogue of one 128 x 128 output tile for the warp that owns TMEM lane quarter `quarter`: tcgen05.ld gives
 // lane = row, register = column; a 32 x 32 block is transposed through a padded per-warp shared buffer so that every
 // global store instruction writes contiguous 128-byte row segments.  Arrives on tempty_bar_addr once the warp's
@@ -264,7 +320,8 @@ constexpr uint32_t TC_B_BLOB_BYTES = 2 * TC_PART_BYTES;     // B_hi part, B_lo p
 
 // APRE: the mirror image for the weight-gradient products (K = every node row): the small [rows, 128] operand is
 // pre-split into blobs, the producers keep the wide M/N-contiguous operand (double-buffered), one tile per CTA.
-template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS, bool BPRE, bool APRE = false>
+// MNMAJ: both operands stored [K][MN] (C = A^T B) and fed to the tensor core MN-major (A_KCONTIG = B_KCONTIG = false).
+template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS, bool BPRE, bool APRE = false, bool MNMAJ = false>
 __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const TcArgs args) {
     constexpr int TC_PRODUCER_WARPS = 4 * GROUPS, TC_MMA_WARP = 4 * GROUPS, TC_GROUPS = GROUPS;
     // (no integer round trip on this pointer: the compiler must keep seeing shared memory, or every
@@ -422,12 +479,23 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
                 const int stage = j % TC_STAGES;
                 const uint32_t phase = (j / TC_STAGES) & 1;
                 float4 va[8], vb[8];
-                fetch_operand<A_KCONTIG>(Ab, args.lda, m0, args.M, k0, kend, a_vec, tid, va);
-                fetch_operand<B_KCONTIG>(Bb, args.ldb, n0, args.N, k0, kend, b_vec, tid, vb);
+                if (MNMAJ) {
+                    fetch_operand_mn(Ab, args.lda, m0, args.M, k0, kend, a_vec, tid, va);
+                    fetch_operand_mn(Bb, args.ldb, n0, args.N, k0, kend, b_vec, tid, vb);
+                } else {
+                    fetch_operand<A_KCONTIG>(Ab, args.lda, m0, args.M, k0, kend, a_vec, tid, va);
+                    fetch_operand<B_KCONTIG>(Bb, args.ldb, n0, args.N, k0, kend, b_vec, tid, vb);
+                }
                 mbar_wait(empty_bar(stage), phase ^ 1);      // the MMAs that read this stage have retired
                 float* st = reinterpret_cast<float*>(smem + size_t(stage) * TC_STAGE_BYTES);
-                store_operand<A_KCONTIG>(st, st + TC_PART_BYTES / 4, tid, va);
-                store_operand<B_KCONTIG>(st + 2 * (TC_PART_BYTES / 4), st + 3 * (TC_PART_BYTES / 4), tid, vb);
+                if (MNMAJ) {
+                    uint8_t* sb = smem + size_t(stage) * TC_STAGE_BYTES;
+                    store_operand_mn(sb, sb + TC_MN_PART_BYTES, tid, va);
+                    store_operand_mn(sb + 2 * TC_MN_PART_BYTES, sb + 3 * TC_MN_PART_BYTES, tid, vb);
+                } else {
+                    store_operand<A_KCONTIG>(st, st + TC_PART_BYTES / 4, tid, va);
+                    store_operand<B_KCONTIG>(st + 2 * (TC_PART_BYTES / 4), st + 3 * (TC_PART_BYTES / 4), tid, vb);
+                }
                 fence_proxy_async();          // generic-proxy stores -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(stage));
@@ -452,15 +520,28 @@ __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const Tc
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + size_t(stage) * TC_STAGE_BYTES);
-                    const uint32_t a_hi = sa, a_lo = sa + TC_PART_BYTES;
-                    const uint32_t b_hi = sa + 2 * TC_PART_BYTES, b_lo = sa + 3 * TC_PART_BYTES;
+                    if (MNMAJ) {
+                        const uint32_t a_hi = sa, a_lo = sa + TC_MN_PART_BYTES;
+                        const uint32_t b_hi = sa + 2 * TC_MN_PART_BYTES, b_lo = sa + 3 * TC_MN_PART_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                        const uint32_t koff = kk * 2 * TC_PLANE_BYTES;   // two 16-byte K chunks per MMA
-                        umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), TC_IDESC, accumulate);
-                        umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), TC_IDESC, 1u);
-                        umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), TC_IDESC, 1u);
-                        accumulate = 1u;
+                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                            const uint32_t koff = kk * 8 * 128;          // eight k rows per MMA
+                            umma_tf32(d_tmem, make_desc_mn(a_lo + koff), make_desc_mn(b_hi + koff), TC_IDESC_MN, accumulate);
+                            umma_tf32(d_tmem, make_desc_mn(a_hi + koff), make_desc_mn(b_lo + koff), TC_IDESC_MN, 1u);
+                            umma_tf32(d_tmem, make_desc_mn(a_hi + koff), make_desc_mn(b_hi + koff), TC_IDESC_MN, 1u);
+                            accumulate = 1u;
+                        }
+                    } else {
+                        const uint32_t a_hi = sa, a_lo = sa + TC_PART_BYTES;
+                        const uint32_t b_hi = sa + 2 * TC_PART_BYTES, b_lo = sa + 3 * TC_PART_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                            const uint32_t koff = kk * 2 * TC_PLANE_BYTES;   // two 16-byte K chunks per MMA
+                            umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), TC_IDESC, accumulate);
+                            umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), TC_IDESC, 1u);
+                            umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), TC_IDESC, 1u);
+                            accumulate = 1u;
+                        }
                     }
                     umma_commit(empty_bar(stage));             // stage is free once these MMAs retire
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -991,8 +1072,12 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     // (worth it only when several column tiles re-use the blobs: a 128-wide output reads the operand once anyway;
     //  GCGCN_APRE_MIN_TILES=1 switches it on for the one-tile weight gradients too -- measured)
     static const int apre_min_tiles = getenv("GCGCN_APRE_MIN_TILES") != nullptr ? atoi(getenv("GCGCN_APRE_MIN_TILES")) : 2;
+    static const bool mn_on = getenv("GCGCN_GEMM_MN") == nullptr || getenv("GCGCN_GEMM_MN")[0] != '0';   // =0: K-major route with register transposes
+    // (since the MN-major route exists the pre-split A blobs only pay for themselves where they are required: the
+    //  generated Khatri-Rao operand of the bilinear weight gradient.  Measured on [119808 x 128]^T [119808 x N]:
+    //  N = 256: 95 us with blobs, 66 us MN-major; N = 1024: 230 us against 216 us.)
     const bool apre = gemm_tc_bpre_enabled() && !bpre && batch == 1 && ta && !tb && K >= 8192 && M <= 2 * TC_BM &&
-                      a.tiles_n >= apre_min_tiles &&
+                      a.tiles_n >= apre_min_tiles && (bscale != nullptr || !mn_on) &&
                       (seq ? (a.partial != nullptr || tiles <= sms) : tiles * splits <= sms) && pre_ws != nullptr &&
                       ablob_total <= pre_bytes &&
                       (reinterpret_cast<uintptr_t>(pre_ws) & 15) == 0;
@@ -1043,13 +1128,14 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     else if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3, false);
     else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3, false);
     else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3, false);
+    else if (mn_on) GCGCN_TC_LAUNCH(false, false, 3, false, false, true);
     else GCGCN_TC_LAUNCH(false, false, 2, false);
 #undef GCGCN_TC_LAUNCH
     timing_set_work(2.0 * M * N * K * batch);
     GCGCN_CHECK_LAUNCH(resa ? ((tmema_on && !ta) ? "gemm_tc_nn<A in TMEM>" : "gemm_tc_nn<resident A>")
                             : apre ? "gemm_tc_tn<presplit A>"
                             : bpre ? (tb ? "gemm_tc_nt<presplit B>" : "gemm_tc_nn<presplit B>")
-                            : ta ? (tb ? "gemm_tc_tt" : "gemm_tc_tn") : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
+                            : ta ? (tb ? "gemm_tc_tt" : (mn_on ? "gemm_tc_tn<MN-major>" : "gemm_tc_tn")) : (tb ? "gemm_tc_nt" : "gemm_tc_nn"));
     if (splits > 1 && a.partial != nullptr)
         GCGCN_TRY(launch_splitk_reduce(a.partial, splits, M, N, alpha, beta, C, ldc, bias, st, batch, sC));
     *taken = 1;
