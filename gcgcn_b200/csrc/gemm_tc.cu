@@ -324,6 +324,7 @@ constexpr uint32_t TC_B_BLOB_BYTES = 2 * TC_PART_BYTES;     // B_hi part, B_lo p
 template <bool A_KCONTIG, bool B_KCONTIG, int GROUPS, bool BPRE, bool APRE = false, bool MNMAJ = false>
 __global__ void __launch_bounds__(tc_threads(GROUPS), 1) gemm_tc_kernel(const TcArgs args) {
     constexpr int TC_PRODUCER_WARPS = 4 * GROUPS, TC_MMA_WARP = 4 * GROUPS, TC_GROUPS = GROUPS;
+    static_assert(GROUPS <= TC_STAGES, "a producer group may run at most one stage-round ahead of the MMA warp");
     // (no integer round trip on this pointer: the compiler must keep seeing shared memory, or every
     //  operand store degrades to a generic ST)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -1128,6 +1129,8 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
     else if (a_kc && b_kc) GCGCN_TC_LAUNCH(true, true, 3, false);
     else if (a_kc && !b_kc) GCGCN_TC_LAUNCH(true, false, 3, false);
     else if (!a_kc && b_kc) GCGCN_TC_LAUNCH(false, true, 3, false);
+    // (never more producer groups than stages: a group two stage-rounds ahead would pass its parity wait on the
+    //  empty barrier one phase early and overwrite a stage the MMA warp has not consumed -- 4 groups hang)
     else if (mn_on) GCGCN_TC_LAUNCH(false, false, 3, false, false, true);
     else GCGCN_TC_LAUNCH(false, false, 2, false);
 #undef GCGCN_TC_LAUNCH

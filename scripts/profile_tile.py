@@ -34,6 +34,11 @@ def main():
     t = _lib.timing_end(st)
     torch.cuda.synchronize()
     print({k: round(v[1], 3) for k, v in t.items() if "block" in k or "tile" in k}, f"tiles {bt.num_tiles}")
+    if "--all" in sys.argv:
+        tot = sum(v[1] for v in t.values())
+        print(f"all gcgcn kernels of the step: {tot:.3f} ms")
+        for k, v in sorted(t.items(), key=lambda kv: -kv[1][1]):
+            print(f"   {k:34s} x{v[0]:3d} {v[1]:8.3f} ms  {100 * v[1] / tot:5.1f}%")
 
 
 if __name__ == "__main__":
