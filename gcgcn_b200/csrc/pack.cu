@@ -79,26 +79,42 @@ int launch_unpack_stack(const float* dWnX, const float* dWe, const float* dWinne
 // ---- GATAttention parameter collapse (G:156-162) ------------------------------------------------------------
 // energy_ij = wt . [Wh x_j + bh ; Wt x_j + bt ; Wr e_ij + br] + b  ==  u . x_j + v . e_ij + c  with
 //   u = Wh^T w1 + Wt^T w2,  v = Wr^T w3,  c = w1.bh + w2.bt + w3.br + b        (w = wt.weight = [w1 | w2 | w3])
-// One CTA; thread k owns column k of the three [hid, 128] weights (coalesced rows).  out = [u(128) | v(128) | c].
-__global__ void __launch_bounds__(128)
+// One CTA of 8 row groups x 128 columns: thread (g, k) sums rows g, g + 8, ... of column k of the three [hid, 128]
+// weights (coalesced rows, independent loads in flight; one thread per column walked 128 dependent rows: 54 us),
+// partial sums meet in shared memory.  out = [u(128) | v(128) | c].
+constexpr int GC_GROUPS = 8;
+__global__ void __launch_bounds__(GC_GROUPS * D)
 gat_collapse_fwd_kernel(const float* __restrict__ Wh, const float* __restrict__ bh, const float* __restrict__ Wt,
                         const float* __restrict__ bt, const float* __restrict__ Wr, const float* __restrict__ br,
                         const float* __restrict__ w, const float* __restrict__ b, int hid, float* __restrict__ out) {
-    const int k = threadIdx.x;
+    __shared__ float su[GC_GROUPS][D], sv[GC_GROUPS][D], red[GC_GROUPS * D / 32];
+    const int k = threadIdx.x % D, g = threadIdx.x / D;
     float u = 0.f, v = 0.f;
-    for (int o = 0; o < hid; ++o) {
+#pragma unroll 4
+    for (int o = g; o < hid; o += GC_GROUPS) {
         u += Wh[o * D + k] * w[o] + Wt[o * D + k] * w[hid + o];
         v += Wr[o * D + k] * w[2 * hid + o];
     }
-    out[k] = u;
-    out[D + k] = v;
+    su[g][k] = u;
+    sv[g][k] = v;
     float c = 0.f;
-    for (int o = k; o < hid; o += D) c += w[o] * bh[o] + w[hid + o] * bt[o] + w[2 * hid + o] * br[o];
+    for (int o = threadIdx.x; o < hid; o += GC_GROUPS * D) c += w[o] * bh[o] + w[hid + o] * bt[o] + w[2 * hid + o] * br[o];
     c = warp_sum(c);
-    __shared__ float red[4];
-    if ((k & 31) == 0) red[k >> 5] = c;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
     __syncthreads();
-    if (k == 0) out[2 * D] = red[0] + red[1] + red[2] + red[3] + b[0];
+    if (g == 0) {
+        float tu = 0.f, tv = 0.f;
+#pragma unroll
+        for (int i = 0; i < GC_GROUPS; ++i) { tu += su[i][k]; tv += sv[i][k]; }
+        out[k] = tu;
+        out[D + k] = tv;
+        if (k == 0) {
+            float tc = b[0];
+#pragma unroll
+            for (int i = 0; i < GC_GROUPS * D / 32; ++i) tc += red[i];
+            out[2 * D] = tc;
+        }
+    }
 }
 
 // gradients of all eight parameters from (du, dv, dc); grid = hid rows, thread k = column
@@ -132,7 +148,7 @@ gat_collapse_bwd_kernel(const float* __restrict__ Wh, const float* __restrict__ 
 
 int launch_gat_collapse_fwd(const float* Wh, const float* bh, const float* Wt, const float* bt, const float* Wr,
                             const float* br, const float* w, const float* b, int hid, float* out, cudaStream_t st) {
-    gat_collapse_fwd_kernel<<<1, 128, 0, st>>>(Wh, bh, Wt, bt, Wr, br, w, b, hid, out);
+    gat_collapse_fwd_kernel<<<1, GC_GROUPS * D, 0, st>>>(Wh, bh, Wt, bt, Wr, br, w, b, hid, out);
     GCGCN_CHECK_LAUNCH("gat_collapse_fwd");
     return GCGCN_OK;
 }
