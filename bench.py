@@ -286,6 +286,7 @@ def kernel_bytes(name: str, bt, H: int, L: int, esz: int) -> float:
         "edge_row_bwd<mean>": n2 * d * esz + node,                             # write de1
         # MAGGC block kernels (H heads): read Zx, E, x, q; write Z_(l>0), G, F, P
         "block_fwd<mha>": 2 * slab + 2 * node + slab * (L - 1) / L + 2 * slab + H * n2 * 4,
+        "tile_fwd": 2 * slab + 2 * node + slab * (L - 1) / L + 2 * slab + H * n2 * 4,      # the same block on packed tiles
         # read P, Z, G, dF, q; write dZ, dE, dq
         "block_bwd<dq>": H * n2 * 4 + 3 * slab + node + 2 * slab + node,
         # CAGGC block kernels (one head): read A, Zx, E, x; write Z_(l>0), G, F  /  read A, Z, G, dF; write dZ, dE, dS
