@@ -449,7 +449,15 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
     const int node0 = node_ptr[b];
     const int n = node_ptr[b + 1] - node0;
     if (n == 0) return;
-    constexpr int S = D, layers = D / GD, LDN = GD + 12, CG = GD / 4, RPP = BK_THREADS / CG;
+    constexpr int S = D, layers = D / GD, CG = GD / 4, RPP = BK_THREADS / CG;
+    // dN / T planes [NP][LDN].  Sub-layer width 64: rows of exactly 64 words with the 16-byte chunk index XORed with
+    // plane_mask(row) -- ldmatrix (8 rows x one chunk) and the B fragments of dZ = A^T dN (rows k0 + t, columns g,
+    // read as scalars: ldmatrix cannot transpose 32-bit elements) are then both bank-conflict free; with the padded
+    // row-major layout the latter were 2-way conflicted and made up a quarter of the kernel's shared-memory
+    // wavefronts, on the pipe that bounds it (ncu: l1tex data pipe 71-88 %).  Width 32 keeps the padded layout (its
+    // dq operands need the larger area).
+    constexpr bool SWZ = (GD == 64);
+    constexpr int LDN = SWZ ? GD : GD + 12;
     constexpr int DHH = DH > 0 ? DH : 8;
     constexpr int NTW = col_tiles_per_warp(MTC, GD / 8), NG = (GD / 8) / NTW, UNITS = MTC * NG;           // [NP] x [GD] products
     constexpr int NTW_C = MTC, NG_C = 2, UNITS_C = 2 * MTC;          // [NP] x [NP]: a row tile x half the columns per warp
@@ -475,6 +483,12 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 
     const int tid = threadIdx.x;
     const LaneGeo L;
+    // word offset of (row, col) in a dN / T plane; mask = {0,2,4,6,1,3,5,7}[row & 7]
+    auto pl = [](int row, int col) -> int {
+        if (!SWZ) return row * LDN + col;
+        const int mask = ((row & 3) << 1) | ((row >> 2) & 1);
+        return row * LDN + ((((col >> 2) ^ mask) << 2) | (col & 3));
+    };
     const long long abase = static_cast<long long>(h) * total_pairs + pair_ptr[b];
     const float* Ab = A + abase;
     const size_t hbase = static_cast<size_t>(node0) * HD + h * S;       // + i*HD + l*GD + col  (32-bit offsets)
@@ -526,7 +540,7 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                     dg.x *= k01.x; dg.y *= k01.y; dg.z *= k23.x; dg.w *= k23.y;
                 }
                 if (!first_layer) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(dGs + i * LDP + l * GD + c0);
+                    const float4 s4 = *reinterpret_cast<const float4*>(dGs + (TWO ? pl(i, l * GD + c0) : i * LDP + l * GD + c0));
                     dg.x += s4.x; dg.y += s4.y; dg.z += s4.z; dg.w += s4.w;
                 }
                 dg.x = g4.x > 0.f ? dg.x : 0.f; dg.y = g4.y > 0.f ? dg.y : 0.f;
@@ -538,11 +552,11 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
             }
             float4 hi, lo;
             split_f4(dn, hi, lo);
-            *reinterpret_cast<float4*>(dNh + i * LDN + c0) = hi;
-            *reinterpret_cast<float4*>(dNl + i * LDN + c0) = lo;
+            *reinterpret_cast<float4*>(dNh + pl(i, c0)) = hi;
+            *reinterpret_cast<float4*>(dNl + pl(i, c0)) = lo;
             split_f4(zl, hi, lo);
-            *reinterpret_cast<float4*>(Th + i * LDN + c0) = hi;
-            *reinterpret_cast<float4*>(Tl + i * LDN + c0) = lo;
+            *reinterpret_cast<float4*>(Th + pl(i, c0)) = hi;
+            *reinterpret_cast<float4*>(Tl + pl(i, c0)) = lo;
 #pragma unroll
             for (int o = CG / 2; o > 0; o >>= 1) drp += __shfl_xor_sync(0xffffffffu, drp, o);
             if (cg == 0 && i < n) drs[i] += drp;
@@ -553,17 +567,19 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
         if (L.warp < UNITS_C) {
             const int mt = L.warp / NG_C, jg = L.warp - mt * NG_C;
             float (&c)[NTW_C][4] = cA;
-            const float* pa = dNh + (16 * mt + L.a_row) * LDN + L.a_col;
-            const float* pb = (L.b_lo ? Tl : Th) + (8 * NTW_C * jg + L.b_row) * LDN + L.b_col;
+            const int arow = 16 * mt + L.a_row, brow = 8 * NTW_C * jg + L.b_row;     // (+ 8 nt: same row & 7, same mask)
+            const float* pb = L.b_lo ? Tl : Th;
 #pragma unroll
             for (int k0 = 0; k0 < GD; k0 += 8) {
                 uint32_t ah[4], al[4];
-                ldsm4(ah, pa + k0);
-                ldsm4(al, pa + NP * LDN + k0);
+                const float* pa = dNh + pl(arow, L.a_col + k0);
+                ldsm4(ah, pa);
+                ldsm4(al, pa + NP * LDN);
+                const int boff = pl(brow, L.b_col + k0);
 #pragma unroll
                 for (int nt = 0; nt < NTW_C; ++nt) {
                     uint32_t bb[4];
-                    ldsm4(bb, pb + 8 * nt * LDN + k0);
+                    ldsm4(bb, pb + boff + 8 * nt * LDN);
                     mma3(c[nt], ah, al, bb[0], bb[1], bb[2], bb[3]);
                 }
             }
@@ -578,7 +594,6 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
             for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
             if (busy) {
                 const float* pa = AtS + (16 * jt + L.a_row) * LDA + L.a_col;
-                const float* nb = dNh + L.t * LDN + col0 + L.g;
 #pragma unroll
                 for (int k0 = 0; k0 < NP; k0 += 8) {
                     uint32_t ah[4], al[4];
@@ -591,10 +606,12 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                         al[e] = __float_as_uint(lo);
                     }
 #pragma unroll
-                    for (int nt = 0; nt < NTW; ++nt)
-                        mma3(c[nt], ah, al, __float_as_uint(nb[k0 * LDN + 8 * nt]), __float_as_uint(nb[(k0 + 4) * LDN + 8 * nt]),
-                             __float_as_uint(nb[NP * LDN + k0 * LDN + 8 * nt]),
-                             __float_as_uint(nb[NP * LDN + (k0 + 4) * LDN + 8 * nt]));
+                    for (int nt = 0; nt < NTW; ++nt) {
+                        const float* n0 = dNh + pl(k0 + L.t, col0 + 8 * nt + L.g);
+                        const float* n1 = dNh + pl(k0 + 4 + L.t, col0 + 8 * nt + L.g);
+                        mma3(c[nt], ah, al, __float_as_uint(n0[0]), __float_as_uint(n1[0]), __float_as_uint(n0[NP * LDN]),
+                             __float_as_uint(n1[NP * LDN]));
+                    }
                 }
             }
             __syncthreads();           // every warp is done reading Z_l (phase c): the T planes may be overwritten
@@ -608,8 +625,8 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                         float2 hi, lo;
                         split_f(v.x, hi.x, lo.x);
                         split_f(v.y, hi.y, lo.y);
-                        *reinterpret_cast<float2*>(Th + j * LDN + col) = hi;
-                        *reinterpret_cast<float2*>(Tl + j * LDN + col) = lo;
+                        *reinterpret_cast<float2*>(Th + pl(j, col)) = hi;
+                        *reinterpret_cast<float2*>(Tl + pl(j, col)) = lo;
                         if (j < n) *reinterpret_cast<float2*>(dZ + hbase + (j * HD + l * GD + col)) = v;
                     }
             }
@@ -623,12 +640,12 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
 #pragma unroll
                 for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
                 const float* wb = wsrc + m * (GD * GD * 2) + (col0 / 8) * 128 + L.lane;
-                const float* pa = Th + (16 * jt + L.a_row) * LDN + L.a_col;
 #pragma unroll 2
                 for (int k0 = 0; k0 < GD; k0 += 8) {
                     uint32_t ah[4], al[4];
-                    ldsm4(ah, pa + k0);
-                    ldsm4(al, pa + NP * LDN + k0);
+                    const float* pa = Th + pl(16 * jt + L.a_row, L.a_col + k0);
+                    ldsm4(ah, pa);
+                    ldsm4(al, pa + NP * LDN);
 #pragma unroll
                     for (int nt = 0; nt < NTW; ++nt) {
                         const float* f = wb + (k0 / 8) * (GD / 8) * 128 + nt * 128;
@@ -640,7 +657,8 @@ block_bwd_kernel(const int* __restrict__ node_ptr, const long long* __restrict__
                 for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        float2* p = reinterpret_cast<float2*>(dGs + (16 * jt + L.g + 8 * half) * LDP + m * GD + col0 + 8 * nt + 2 * L.t);
+                        float2* p = reinterpret_cast<float2*>(dGs + (TWO ? pl(16 * jt + L.g + 8 * half, m * GD + col0 + 8 * nt + 2 * L.t)
+                                                                        : (16 * jt + L.g + 8 * half) * LDP + m * GD + col0 + 8 * nt + 2 * L.t));
                         float2 v = make_float2(c[nt][2 * half], c[nt][2 * half + 1]);
                         if (!first_layer) { const float2 cur = *p; v.x += cur.x; v.y += cur.y; }
                         *p = v;
@@ -758,7 +776,7 @@ static size_t block_fwd_smem(int np, int layers, int gd) {
 }
 static size_t block_bwd_smem(int np, int layers, int gd) {
     const int ki = (layers - 1) * gd;
-    size_t fl = static_cast<size_t>(np) * (np + 4) + 4 * static_cast<size_t>(np) * (gd + 12) + 2 * np;
+    size_t fl = static_cast<size_t>(np) * (np + 4) + 4 * static_cast<size_t>(np) * (gd == 64 ? gd : gd + 12) + 2 * np;
     if (layers != 2) fl += static_cast<size_t>(np) * (np + 4) + static_cast<size_t>(np) * (ki + 4);   // dA scratch, parked dG
     return fl * sizeof(float);
 }
