@@ -142,7 +142,6 @@ struct TileFwdArgs {
     int heads, num_tiles;
     long long total_pairs;
     float scale;
-    int debug;
 };
 
 // Two thread mappings:
@@ -404,7 +403,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
                 if (row < rows) {
                     const size_t off = cslab + static_cast<size_t>(i) * 16 * HD + l * TL_GD;
                     *reinterpret_cast<float4*>(a.G + off) = g;
-                    *reinterpret_cast<float4*>(a.F + off) = a.debug ? nv : make_float4(g.x + x4[i].x, g.y + x4[i].y, g.z + x4[i].z, g.w + x4[i].w);
+                    *reinterpret_cast<float4*>(a.F + off) = make_float4(g.x + x4[i].x, g.y + x4[i].y, g.z + x4[i].z, g.w + x4[i].w);
                 }
                 if (l == 0) {          // g_0 -> K-major A-operand planes of the dense-connect product (over the dead Z_0 tile)
                     float4 hi, lo;
@@ -515,7 +514,6 @@ int launch_tile_fwd(const gcgcn_batch* bt, int heads, int layers, const float* q
     a.num_tiles = bt->num_tiles;
     a.total_pairs = bt->total_pairs;
     a.scale = 1.0f / sqrtf(static_cast<float>(TL_DH));
-    a.debug = std::getenv("GCGCN_TILE_DEBUG") != nullptr;
     const int items = bt->num_tiles * heads;
     const int grid = items < 2 * sm_count() ? items : 2 * sm_count();
     tile_fwd_kernel<<<grid, TL_THREADS, TL_SMEM_BYTES, st>>>(a);
