@@ -869,7 +869,7 @@ int launch_block_fwd(const gcgcn_batch* bt, int heads, int layers, const float* 
                      float* Z, const float* E, const float* Winner_rowmajor, const float* x, float* G, float* F,
                      float* frag_ws, const BlockDrop& drop, cudaStream_t st) {
     if (bt->num_docs == 0) return GCGCN_OK;
-    if (A == nullptr && layers == 2 && heads == 8 && drop.thr_att == 0u && drop.thr_gcn == 0u && bt->tile_doc != nullptr &&
+    if (A == nullptr && layers == 2 && (heads == 8 || heads == 4) && drop.thr_att == 0u && drop.thr_gcn == 0u && bt->tile_doc != nullptr &&
         bt->num_tiles > 0 && bt->row_doc != nullptr && frag_ws != nullptr &&
         tile_wblob_bytes(heads) <= block_frag_floats(heads, layers) * sizeof(float) && tile_blocks_enabled())
         return launch_tile_fwd(bt, heads, layers, q, P, Z, E, Winner_rowmajor, x, G, F, frag_ws, st);

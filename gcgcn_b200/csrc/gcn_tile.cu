@@ -14,8 +14,8 @@
 //   Z_1 = Zx_1 + g_0 Winner_1           tcgen05.mma 128x64x64, A = g_0 planes, B = pre-split weight blob
 //
 // All products are 3xTF32 (hi/lo operand split, fp32 accumulate in TMEM; see gemm_tc.cu).  Configuration: the GloVe
-// model's MAGGC block only (two sub-layers of 64 columns, head width 16, eval mode); everything else takes the
-// per-document kernels.  Results match them to fp32 rounding (different summation order in the softmax and the MMAs).
+// model's MAGGC block (two sub-layers of 64 columns, 8 heads of width 16) and its 4-head variant of the entity sweep
+// (head width 32), eval mode; everything else takes the per-document kernels.  Results match them to fp32 rounding (different summation order in the softmax and the MMAs).
 #include "common.cuh"
 #include "mma_tf32.cuh"
 #include "tc_ptx.cuh"
@@ -25,7 +25,7 @@
 namespace gcgcn {
 
 constexpr int TL_THREADS = 256;
-constexpr int TL_GD = 64, TL_DH = 16;
+constexpr int TL_GD = 64;                        // sub-layer width (two sub-layers); head width DH = 16 or 32 is a template parameter
 constexpr int TL_ROWS = GCGCN_TILE_ROWS;         // node rows per tile = K extent of P Z
 static_assert(TL_ROWS == 96, "thread mapping and TMEM layout below assume 96-row tiles");
 constexpr int TL_HALF = TL_ROWS / 2;             // attention columns per thread
@@ -38,7 +38,8 @@ constexpr int TL_HALF = TL_ROWS / 2;             // attention columns per thread
 //     -- the canonical UMMA "Major-MN / SWIZZLE_128B_BASE32B" atom, 4 k x 128 B
 constexpr int TL_PLANE_M = TL_ROWS * 16 + 16;
 constexpr int TL_PLANE_N = 64 * 16 + 16;
-constexpr int TL_Q_PART = (TL_DH / 4) * TL_PLANE_M;      // q_h              [96 rows][16 k]   K-major
+template <int DH>
+constexpr int TL_Q_PART_OF = (DH / 4) * TL_PLANE_M;      // q_h  [96 rows][DH k]   K-major
 constexpr int TL_ZBLK = TL_ROWS * 128;                   // one [96 k][32 n] column block of Z_l
 constexpr int TL_B_PART = 2 * TL_ZBLK;                   // Z_l              [96 k][64 n]      MN-major SW128
 constexpr int TL_G_PART = (TL_GD / 4) * TL_PLANE_M;      // g_0              [96 rows][64 k]   K-major (aliases the Z region)
@@ -46,7 +47,7 @@ constexpr int TL_W_PART = (TL_GD / 4) * TL_PLANE_N;      // Winner_1^T       [64
 constexpr int TL_ZG_BYTES = ((2 * (TL_G_PART > TL_B_PART ? TL_G_PART : TL_B_PART)) + 1023) / 1024 * 1024;
 constexpr int TL_STAGE_LD = 64 * 4 + 16;                 // staging row: 64 fp32 + 16 B (conflict-free row-per-lane 16 B stores)
 constexpr int TL_STAGE_BYTES = TL_ROWS * TL_STAGE_LD;    // accumulator tiles on their way from TMEM to coalesced stores
-static_assert(2 * TL_Q_PART <= TL_STAGE_BYTES, "the q planes live in the staging buffer until S is done");
+static_assert(2 * TL_Q_PART_OF<32> <= TL_STAGE_BYTES, "the q planes live in the staging buffer until S is done");
 constexpr int TL_OFF_ZG = 0;                             // 1024-aligned (swizzle atoms)
 constexpr int TL_OFF_WHI = TL_OFF_ZG + TL_ZG_BYTES, TL_OFF_WLO = TL_OFF_WHI + TL_W_PART;
 constexpr int TL_OFF_STAGE = TL_OFF_WLO + TL_W_PART;
@@ -151,7 +152,9 @@ struct TileFwdArgs {
 //     touches two whole 256-byte row segments per instruction.  (With one row per lane every 16-byte global access of
 //     a warp hit 32 different lines and the L1 data pipe, not HBM, bounded the kernel: ncu, profiles/r02_tile_fwd.md.)
 // Accumulator tiles cross from the first mapping to the second through the staging buffer.
+template <int DH>
 __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdArgs a) {
+    constexpr int TL_Q_PART = TL_Q_PART_OF<DH>, QV = DH / 8;      // QV float4 of q per thread (half of the head slice)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sraw = smem_u32(smem_raw);
     const uint32_t sbase = (sraw + 1023u) & ~1023u;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
     // before its last wait), so an item starts with its data in registers instead of three dependent round trips to
     // L2/HBM.  (Fetching the Zx_0 tile ahead as well was measured slower: 24 more live registers spill.)
     int n_row0 = 0, n_rows = 0;
-    float4 n_q0 = make_float4(0.f, 0.f, 0.f, 0.f), n_q1 = n_q0;
+    float4 n_q[QV];
     auto fetch_geometry = [&](int item) {
         if (item < items) {
             const int tile = item % a.num_tiles;
@@ -196,11 +199,12 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
     };
     auto fetch_operands = [&](int item) {
         const int h = item / a.num_tiles;
-        n_q0 = n_q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < QV; ++i) n_q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (item < items && rowthread && r < n_rows) {
-            const float* qp = a.q + static_cast<size_t>(n_row0 + r) * D + h * TL_DH + half * 8;
-            n_q0 = ld4g(qp);
-            n_q1 = ld4g(qp + 4);
+            const float* qp = a.q + static_cast<size_t>(n_row0 + r) * D + h * DH + half * (DH / 2);
+#pragma unroll
+            for (int i = 0; i < QV; ++i) n_q[i] = ld4g(qp + 4 * i);
         }
     };
     fetch_geometry(blockIdx.x);
@@ -215,14 +219,14 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
 
         // ---- stage q_h (A and B operand of S) and, when the head changes, its dense-connect weights ----
         if (rowthread) {
-            float4 hi, lo;
-            const uint32_t dst = (2 * half) * TL_PLANE_M + r * 16;
-            tl_split4(n_q0, hi, lo);
-            sts4(s_qhi + dst, hi);
-            sts4(s_qlo + dst, lo);
-            tl_split4(n_q1, hi, lo);
-            sts4(s_qhi + dst + TL_PLANE_M, hi);
-            sts4(s_qlo + dst + TL_PLANE_M, lo);
+            const uint32_t dst = (QV * half) * TL_PLANE_M + r * 16;
+#pragma unroll
+            for (int i = 0; i < QV; ++i) {
+                float4 hi, lo;
+                tl_split4(n_q[i], hi, lo);
+                sts4(s_qhi + dst + i * TL_PLANE_M, hi);
+                sts4(s_qlo + dst + i * TL_PLANE_M, lo);
+            }
         }
         fetch_geometry(item + gridDim.x);
         if (h != cur_h) {
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_fwd_kernel(const TileFwdAr
             tc_fence_after();
             constexpr uint32_t IDESC = TL_IDESC<TL_ROWS, false>;
 #pragma unroll
-            for (int kk = 0; kk < TL_DH / 8; ++kk) {
+            for (int kk = 0; kk < DH / 8; ++kk) {
                 const uint32_t koff = kk * 2 * TL_PLANE_M;
                 const uint64_t dh = tl_desc(s_qhi + koff, TL_PLANE_M);
                 const uint64_t dl = tl_desc(s_qlo + koff, TL_PLANE_M);
@@ -490,7 +494,7 @@ bool set_tile_blocks(bool on) { return tile_flag().exchange(on ? 1 : 0) != 0; }
 size_t tile_wblob_bytes(int heads) { return static_cast<size_t>(heads) * TL_WBLOB_BYTES; }
 
 // MHA attention + MAGGC block forward on packed 128-row tiles.  Preconditions (checked by the caller): two sub-layers,
-// head width 16, no dropout, bt->tile_doc present.
+// head width 16 or 32, no dropout, bt->tile_doc present.
 int launch_tile_fwd(const gcgcn_batch* bt, int heads, int layers, const float* q, float* P, float* Z, const float* E,
                     const float* Winner_rowmajor, const float* x, float* G, float* F, void* wblob_ws, cudaStream_t st) {
     if (bt->num_tiles <= 0) return GCGCN_OK;
@@ -500,7 +504,9 @@ int launch_tile_fwd(const gcgcn_batch* bt, int heads, int layers, const float* q
     GCGCN_CHECK_LAUNCH("tile_wprep");
     static std::atomic<unsigned long long> ready{0};
     if (!device_prepared(ready)) {
-        GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(tile_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES),
+        GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(tile_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES),
+                          "tile_fwd"));
+        GCGCN_TRY(cuda_ok(cudaFuncSetAttribute(tile_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_BYTES),
                           "tile_fwd"));
         device_mark_prepared(ready);
     }
@@ -513,10 +519,13 @@ int launch_tile_fwd(const gcgcn_batch* bt, int heads, int layers, const float* q
     a.heads = heads;
     a.num_tiles = bt->num_tiles;
     a.total_pairs = bt->total_pairs;
-    a.scale = 1.0f / sqrtf(static_cast<float>(TL_DH));
+    const int dh = D / heads;
+    a.scale = 1.0f / sqrtf(static_cast<float>(dh));
     const int items = bt->num_tiles * heads;
     const int grid = items < 2 * sm_count() ? items : 2 * sm_count();
-    tile_fwd_kernel<<<grid, TL_THREADS, TL_SMEM_BYTES, st>>>(a);
+    if (dh == 16) tile_fwd_kernel<16><<<grid, TL_THREADS, TL_SMEM_BYTES, st>>>(a);
+    else if (dh == 32) tile_fwd_kernel<32><<<grid, TL_THREADS, TL_SMEM_BYTES, st>>>(a);
+    else return fail(GCGCN_ERR_UNSUPPORTED, "tile_fwd: head width %d", dh);
     GCGCN_CHECK_LAUNCH("tile_fwd");
     return GCGCN_OK;
 }

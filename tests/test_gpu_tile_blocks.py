@@ -63,16 +63,20 @@ def test_tile_kernel_matches_per_document_kernels(case, tile_switch):
                 assert float((out["dparams"][k] - v).abs().max()) <= 2e-5 * scale, "d" + k
 
 
-def test_tile_kernel_against_the_oracle(tile_switch):
-    gb, state = device_blocks(2, 8)
+@pytest.mark.parametrize("heads", [8, 4], ids=["8x16", "4x32"])
+def test_tile_kernel_against_the_oracle(heads, tile_switch):
+    gb, state = device_blocks(2, heads)
     sizes = [7, 11, 42, 3, 29, 5, 64, 1]
     docs = [S.make_doc(300 + i, n=n, L=32) for i, n in enumerate(sizes)]
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.timing_begin(st)
     res = run_blocks(gb, docs)
+    assert "tile_fwd" in _lib.timing_end(st), "the packed-tile kernel must be what ran"
     bt = res["bt"]
     for b, d in enumerate(docs):
-        r = oracle_blocks(d, state, 2, 8)
+        r = oracle_blocks(d, state, 2, heads)
         assert_close(bt.split_nodes(res["y2"])[b], r["y2"], FP32_TOL, f"doc{b} y2")
-        for h in range(8):
+        for h in range(heads):
             assert_close(bt.split_pairs(res["a1"][h])[b], r["a1"][h], 1e-5, f"doc{b} a1[{h}]")
         assert_close(bt.split_nodes(res["dx0"])[b], r["dx0"], FP32_TOL, f"doc{b} dx0")
         assert_close(bt.split_pairs(res["de1"])[b], r["de1"], FP32_TOL, f"doc{b} de1")
