@@ -765,28 +765,41 @@ __global__ void __launch_bounds__(TA_THREADS, 1) gemm_tc_tmema_kernel(const TcAr
         for (int mi = blockIdx.x; mi < tiles_m; mi += gridDim.x, ++it) {
             const int row = mi * TC_BM + quarter * 32 + lane;
             const float* src = args.A + static_cast<size_t>(row) * args.lda;
+            // The row's 64 values of this K half are loaded BEFORE the wait for the A region of tensor memory: the loads
+            // of row tile i + 1 then fly while the MMAs of tile i still read tile i's operand (they used to be issued
+            // after the wait, 16 at a time: four exposed HBM latencies per row tile).
+            float4 av[16];
+            const int kbase = khalf * 64;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = kbase + 4 * j;
+                if (k >= kblocks * TC_BK) {
+                    av[j] = make_float4(0.f, 0.f, 0.f, 0.f);           // columns beyond the K blocks in use are never read
+                } else if (row < args.M && a_vec && k + 4 <= args.K) {
+                    av[j] = *reinterpret_cast<const float4*>(src + k);
+                } else {
+                    float t[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) t[e] = (row < args.M && k + e < args.K) ? src[k + e] : 0.f;
+                    av[j] = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
             mbar_wait(a_empty, (it & 1) ^ 1);            // the MMAs of the previous row tile have retired
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c16 = 0; c16 < 4; ++c16) {
-                const int k0 = khalf * 64 + c16 * 16;
-                if (k0 >= kblocks * TC_BK) break;          // columns beyond the K blocks in use are never read
+                const int k0 = kbase + c16 * 16;
+                if (k0 >= kblocks * TC_BK) break;
                 uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float t[4];
-                    if (row < args.M && a_vec && k0 + j + 4 <= args.K) {
-                        const float4 v = *reinterpret_cast<const float4*>(src + k0 + j);
-                        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) t[e] = (row < args.M && k0 + j + e < args.K) ? src[k0 + j + e] : 0.f;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = av[4 * c16 + j];
+                    const float t[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t h = __float_as_uint(t[e]) & 0xffffe000u;
-                        hi[j + e] = h;
-                        lo[j + e] = __float_as_uint(t[e] - __uint_as_float(h));
+                        hi[4 * j + e] = h;
+                        lo[4 * j + e] = __float_as_uint(t[e] - __uint_as_float(h));
                     }
                 }
                 const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
