@@ -1119,7 +1119,8 @@ int launch_gemm_tc(int ta, int tb, int M, int N, int K, float alpha, const float
         gemm_tc_kernel<AK, BK, G, __VA_ARGS__><<<grid, tc_threads(G), TC_SMEM_BYTES, st>>>(a);           \
     } while (0)
     static const bool resa_on = getenv("GCGCN_GEMM_RESA") == nullptr || getenv("GCGCN_GEMM_RESA")[0] != '0';
-    const bool resa = bpre && resa_on && a.kblocks <= RA_KB && a.tiles_n >= 2 && a.partial == nullptr;
+    static const int resa_min_tiles = getenv("GCGCN_RESA_MIN_TILES") != nullptr ? atoi(getenv("GCGCN_RESA_MIN_TILES")) : 1;   // (one column tile: 40 us against 44 us for [119808,128]x[128,128])
+    const bool resa = bpre && resa_on && a.kblocks <= RA_KB && a.tiles_n >= resa_min_tiles && a.partial == nullptr;
     static const bool tmema_on = getenv("GCGCN_GEMM_TMEMA") == nullptr || getenv("GCGCN_GEMM_TMEMA")[0] != '0';   // =0: shared-memory resident-A kernel
     if (resa && tmema_on && !ta) {
         static std::atomic<unsigned long long> attr_done2{0};
