@@ -54,3 +54,19 @@ def test_library_is_built_for_sm_100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_tile_blocks_switch_and_batch_struct_layout(lib):
+    """gcgcn_set_tile_blocks returns the previous setting (no device work), and the ctypes mirror of gcgcn_batch has the
+    C struct's layout: three 4-byte-aligned tail fields after class_end (the packing hint of the tile kernel)."""
+    first = _lib.set_tile_blocks(False)
+    assert _lib.set_tile_blocks(True) is False
+    assert _lib.set_tile_blocks(first) is True
+    assert lib.gcgcn_set_tile_blocks(1 if first else 0) in (0, 1)
+    B = _lib.Batch
+    assert B.tile_doc.offset == B.class_end.offset + 16 and B.num_tiles.offset == B.tile_doc.offset + 8
+    assert B.tile_rows.offset == B.num_tiles.offset + 4 and ctypes.sizeof(B) == B.tile_rows.offset + 4
+    text = open(os.path.join(ROOT, "include", "gcgcn_b200.h")).read()
+    rows = int(re.search(r"#define GCGCN_TILE_ROWS (\d+)", text).group(1))
+    from gcgcn_b200.batch import TILE_ROWS
+    assert rows == TILE_ROWS == 96
